@@ -1,0 +1,199 @@
+/*
+ * kessler_b200.h -- C ABI of libkessler_b200.so: the B200 (sm_100a) implementation
+ * of Kessler's Monte Carlo conjunction hot path.
+ *
+ * The reference (kesslerlib/kessler v1.0.1) is pure Python and has no FFI; the
+ * path sits behind Python calls into the third-party package dsgp4.  Each entry
+ * point below names the reference call it replaces (file:line under
+ * /root/reference/kessler/).  INTEGRATION.md shows the ctypes stubs a Kessler
+ * maintainer would add to route those calls here.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns 0 on success, <0 on failure (KSL_E_*); it never
+ *     throws.  ksl_last_error() gives the message of the calling thread's last
+ *     failure.  Per-sample NUMERICAL conditions never fail a call: they are
+ *     reported in the int32 `err` arrays as a bitmask (KSL_ERR_*).
+ *   - pointers named d_* / without suffix are DEVICE pointers owned by the
+ *     caller (e.g. torch tensors' data_ptr()); the *_host entry points take HOST
+ *     pointers and do the transfers themselves (that is the end-to-end path).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     all device-pointer entry points are stream-ordered and asynchronous.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     returns KSL_E_CUDA.
+ *
+ * Units follow dsgp4: mean motion rad/min, angles rad, tsince minutes, SGP4
+ * output km and km/s (TEME); the Kessler-level entry points return metres, as
+ * util.propagate_upsample does (util.py:579).
+ */
+#ifndef KESSLER_B200_H
+#define KESSLER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KSL_VERSION 100
+
+/* return codes */
+#define KSL_OK 0
+#define KSL_E_ARG (-1)   /* bad argument (NULL pointer, negative size, unsupported combination) */
+#define KSL_E_CUDA (-2)  /* CUDA runtime error, or no CUDA device */
+#define KSL_E_NOMEM (-3) /* workspace too small / allocation failed */
+
+/* per-sample error bits (dsgp4 keeps the last Vallado code in tle._error; only
+ * the deep-space refusal is observable to Kessler, model.py:580-599) */
+#define KSL_ERR_ECC 1        /* em >= 1 or em < -0.001 at some epoch (Vallado error 1) */
+#define KSL_ERR_MEANMOTION 2 /* nm <= 0 (Vallado error 2) */
+#define KSL_ERR_SEMILATUS 4  /* pl < 0 (Vallado error 4) */
+#define KSL_ERR_DECAYED 8    /* mrt < 1: below the surface (Vallado error 6) */
+#define KSL_ERR_DEEPSPACE 16 /* period >= 225 min: dsgp4.initialize_tle raises */
+/* in ksl_screen the target's bits are in 0..7, the chaser's in 8..15 */
+#define KSL_ERR_CHASER_SHIFT 8
+
+/* layout of one initialised-TLE record, structure-of-arrays: consts[k*n + i] */
+#define KSL_NCONST 36
+enum ksl_const_index {
+    KSL_C_NO = 0, KSL_C_ECCO, KSL_C_INCLO, KSL_C_NODEO, KSL_C_ARGPO, KSL_C_MO, KSL_C_BSTAR,
+    KSL_C_MDOT, KSL_C_ARGPDOT, KSL_C_NODEDOT, KSL_C_NODECF, KSL_C_CC1, KSL_C_CC4, KSL_C_CC5, KSL_C_T2COF,
+    KSL_C_OMGCOF, KSL_C_XMCOF, KSL_C_ETA, KSL_C_DELMO, KSL_C_SINMAO, KSL_C_D2, KSL_C_D3, KSL_C_D4,
+    KSL_C_T3COF, KSL_C_T4COF, KSL_C_T5COF, KSL_C_AYCOF, KSL_C_XLCOF, KSL_C_CON41, KSL_C_X1MTH2,
+    KSL_C_X7THM1, KSL_C_ISIMP, KSL_C_COSIO, KSL_C_SINIO, KSL_C_AOBASE, KSL_C_PAD
+};
+/* element order of the SoA input `elems[k*n + i]`, k = 0..6 */
+enum ksl_elem_index { KSL_E_NO_KOZAI = 0, KSL_E_ECCO, KSL_E_INCLO, KSL_E_NODEO, KSL_E_ARGPO, KSL_E_MO, KSL_E_BSTAR };
+
+/* ksl_screen `mode` */
+#define KSL_SCREEN_ANALYTIC 0 /* per-coarse-segment closed form + exact re-evaluation of the candidates */
+#define KSL_SCREEN_BRUTE 1    /* every fine-grid point, as the reference does */
+
+/* ksl_pc_count `pairing` */
+#define KSL_PAIR_ALL 0
+#define KSL_PAIR_ELEMENTWISE 1
+
+/* summary record written by ksl_screen_summary: uint64 counts + double moments */
+#define KSL_SUM_NCOUNT 8
+enum ksl_summary_count {
+    KSL_SUM_N = 0,       /* traces seen */
+    KSL_SUM_PROP_ERR,    /* deep-space on target or chaser -> `conj=False` (model.py:584,595) */
+    KSL_SUM_CONJ_ANY,    /* i_conj >= 0 */
+    KSL_SUM_CONJ_REF,    /* i_conj > 0: what `if i_conj:` accepts (model.py:617) */
+    KSL_SUM_COLLISION,   /* d_min < collision threshold */
+    KSL_SUM_NUM_ERR,     /* any numerical error bit other than deep-space */
+    KSL_SUM_RESERVED0, KSL_SUM_RESERVED1
+};
+#define KSL_SUM_NMOMENT 4 /* n_valid, sum d_min, sum d_min^2 (about KSL_SUM_SHIFT), min d_min */
+
+int ksl_version(void);
+int ksl_nconst(void);
+const char *ksl_last_error(void);
+/* number of visible CUDA devices (0 when there is no driver/GPU); never fails */
+int ksl_device_count(void);
+
+/* ---- dsgp4.initialize_tle(tle | [tle...])  (model.py:581,592,536) ------------
+ * elems SoA [7][n] -> consts SoA [KSL_NCONST][n]; err[n] = 0 or KSL_ERR_DEEPSPACE. */
+int ksl_sgp4_init(const double *elems, int64_t n, double *consts, int32_t *err, void *stream);
+
+/* ---- dsgp4.propagate(tle, tsinces) / propagate_batch(batch, tsinces) ----------
+ * (util.py:571,576; model.py:541).  tsince is [m] shared by all n records
+ * (per_sample_t = 0) or [n][m] (per_sample_t = 1).  rv_km [n][m][6] = x,y,z km,
+ * vx,vy,vz km/s.  err[n] is OR-ed with the bits raised at any epoch (caller zeroes
+ * or passes the array ksl_sgp4_init filled). */
+int ksl_sgp4_prop(const double *consts, int64_t n, const double *tsince, int64_t m, int per_sample_t,
+                  double *rv_km, int32_t *err, void *stream);
+
+/* ---- util.upsample(s, target_resolution)  (util.py:541-555) -------------------
+ * x [n_in][ch] -> y [n_out][ch], torch's linear/align_corners=True arithmetic
+ * including its float32 floor of the source index. */
+int ksl_upsample(const double *x, int64_t n_in, int64_t ch, int64_t n_out, double *y, void *stream);
+
+/* ---- util.propagate_upsample(tle, times_mjd, upsample_factor)  (util.py:557-580)
+ * one initialised TLE (consts [KSL_NCONST], i.e. n = 1), its epoch as MJD,
+ * times_sub = times_mjd[::upsample_factor] ([n_sub]), n_out = len(times_mjd);
+ * out_m [n_out][6] in metres and m/s.  workspace: n_sub*6 doubles. */
+int ksl_propagate_upsample(const double *consts, double epoch_mjd, const double *times_sub, int64_t n_sub,
+                           int64_t n_out, double *out_m, double *workspace, int32_t *err, void *stream);
+
+/* ---- model.find_conjunction(tr0, tr1, miss_dist_threshold)  (model.py:23-52) ---
+ * tr0, tr1 [n][stride] with x,y,z in the first three columns.  out_i = {i_min,
+ * i_conj (-1 = None)}, out_d = {d_min, d_conj (NaN = None)}.  torch semantics:
+ * first index on ties, NaN counts as the minimum.  workspace: ksl_find_conjunction_ws(n) bytes. */
+int64_t ksl_find_conjunction_ws(int64_t n);
+int ksl_find_conjunction(const double *tr0, const double *tr1, int64_t n, int64_t stride, double thr,
+                         int64_t *out_i, double *out_d, void *workspace, void *stream);
+
+/* ---- the fused trace: space segment of Conjunction.forward()  (model.py:574-613)
+ * For every sample s: propagate target and chaser at the n_coarse epochs
+ * times_coarse[k] (MJD; tsince = (times_coarse[k] - epoch) * 1440, util.py:575),
+ * up-sample linearly to n_fine points (util.py:541-555), and search the fine grid
+ * for the global minimum distance and the first point below thr_m (model.py:23-52).
+ *   consts_t SoA [KSL_NCONST][n_t], epoch_t [n_t], n_t = 1 (one target shared by
+ *   all samples) or n;  consts_c SoA [KSL_NCONST][n], epoch_c [n].
+ *   init_err_t [n_t] / init_err_c [n]: err arrays from ksl_sgp4_init (NULL = none);
+ *   a deep-space record makes the trace a propagation error: i_min = -1.
+ * Outputs (device, [n]): i_min, d_min [m], i_conj (-1 = None), d_conj [m] (NaN = None),
+ * err (target bits 0..7, chaser bits 8..15).
+ * workspace: ksl_screen_ws(n_t, n, n_coarse) bytes of device memory. */
+int64_t ksl_screen_ws(int64_t n_t, int64_t n, int64_t n_coarse);
+int ksl_screen(const double *consts_t, const double *epoch_t, const int32_t *init_err_t, int64_t n_t,
+               const double *consts_c, const double *epoch_c, const int32_t *init_err_c, int64_t n,
+               const double *times_coarse, int64_t n_coarse, int64_t n_fine, double thr_m, int mode,
+               int64_t *i_min, double *d_min, int64_t *i_conj, double *d_conj, int32_t *err,
+               void *workspace, void *stream);
+
+/* counts (uint64 [KSL_SUM_NCOUNT]) and moments (double [KSL_SUM_NMOMENT]) over the
+ * outputs of ksl_screen; deterministic (fixed reduction order); these are the
+ * quantities all-reduced across GPUs.  workspace: ksl_screen_summary_ws(n) bytes. */
+int64_t ksl_screen_summary_ws(int64_t n);
+int ksl_screen_summary(const int64_t *i_conj, const double *d_min, const int32_t *err, int64_t n,
+                       double collision_thr_m, uint64_t *counts, double *moments, void *workspace, void *stream);
+
+/* ---- Monte Carlo covariance at TCA  (model.py:523-550) ------------------------
+ * elems SoA [7][n] (already converted as model.py:500,525-533 do: mean motion
+ * rad/min, e clamped at 0) -> sgp4init + sgp4 at one tsince -> states [n][6] in
+ * metres (optional, NULL to skip) and the shifted moments about ref_state_m[6]:
+ * moments[0] = n_ok, [1..6] = sum (x - ref), [7..27] = upper triangle (row-major)
+ * of sum (x - ref)(x - ref)^T.  Deterministic.  The host finishes mean / RTN
+ * rotation / np.cov(ddof=1).  err_count[0] = samples with any error bit.
+ * workspace: ksl_tca_moments_ws(n) bytes. */
+#define KSL_NMOMENT 28
+int64_t ksl_tca_moments_ws(int64_t n);
+int ksl_tca_moments(const double *elems, int64_t n, double tsince, const double *ref_state_m,
+                    double *states_m, double *moments, int64_t *err_count, void *workspace, void *stream);
+
+/* ---- Monte Carlo collision count  (model.py:432-437) --------------------------
+ * t_xyz SoA [3][nt], c_xyz SoA [3][nc] (metres).  count = #pairs with
+ * ((dx*dx + dy*dy) + dz*dz) < thr*thr evaluated without FMA contraction, so the
+ * integer is bit-exact against the oracle for identical samples. *count is
+ * ADDED to (caller zeroes it), which lets row shards accumulate. */
+int ksl_pc_count(const double *t_xyz, int64_t nt, const double *c_xyz, int64_t nc, double thr_m, int pairing,
+                 unsigned long long *count, void *stream);
+
+/* ---- end-to-end entry points: HOST buffers in, HOST buffers out ----------------
+ * What a Kessler-side binding calls for a batch of traces.  Allocates (and caches
+ * per device) its staging and scratch buffers; synchronous.
+ *   elems_t SoA [7][n_t], epoch_t [n_t], elems_c SoA [7][n], epoch_c [n],
+ *   times_coarse [n_coarse]  -- all host.  Outputs host [n] (err may be NULL).
+ *   summary_counts [KSL_SUM_NCOUNT] / summary_moments [KSL_SUM_NMOMENT] may be NULL. */
+int ksl_screen_host(int device, const double *elems_t, const double *epoch_t, int64_t n_t,
+                    const double *elems_c, const double *epoch_c, int64_t n,
+                    const double *times_coarse, int64_t n_coarse, int64_t n_fine, double thr_m, int mode,
+                    double collision_thr_m,
+                    int64_t *i_min, double *d_min, int64_t *i_conj, double *d_conj, int32_t *err,
+                    uint64_t *summary_counts, double *summary_moments);
+/* frees the cached buffers of ksl_*_host (all devices) */
+int ksl_host_cache_free(void);
+
+/* ---- measurement helpers ------------------------------------------------------
+ * dependent-free DFMA loop: blocks x threads x iters x 2*unroll flops; used by
+ * bench.py to MEASURE the FP64 peak (MEASURED_PEAKS.json has no FP64 entry). */
+int ksl_fp64_peak_kernel(int blocks, int threads, int64_t iters, double *sink, void *stream);
+/* number of kernel launches issued by this library since load (all threads) */
+int64_t ksl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KESSLER_B200_H */

@@ -1,0 +1,389 @@
+// sgp4_device.cuh -- FP64 near-earth SGP4 for sm_100a, written for the B200 FP64 pipe.
+//
+// Replaces dsgp4.initialize_tle / dsgp4.propagate / dsgp4.propagate_batch as Kessler
+// calls them (/root/reference/kessler/model.py:581,592,536,541; util.py:570-576).
+// Algorithm: Vallado et al. AIAA 2006-6753 near-earth branch, WGS-84, floor-mod
+// wrapping, as dsgp4 computes it.  This is NOT a
+// transcription of that code: the propagation is restructured for the GPU so that
+// one evaluation needs 4 full-range sincos instead of 16 sin/cos + atan2 + pow:
+//   * sin(mm) for the drag term, sin/cos of su, xnode, xinc and the Kepler iterates
+//     after the first are obtained by rotating an already-known (sin, cos) pair
+//     through a SMALL angle with a short Taylor kernel (angle-addition), with a
+//     full sincos fallback when the angle is not small;
+//   * atan2 is never taken: (sinu, cosu) is already the unit vector of u;
+//   * am^1.5 is am*sqrt(am); x/xke is x*(1/xke);
+//   * the secular angles are evaluated WITHOUT fma contraction so that their
+//     rounding matches the reference's mul-then-add (they carry |tsince| ~ 5e4 min
+//     of phase, where half an ulp is ~1e-9 km).
+// All of it is exact algebra; results agree with the oracle to ~1e-11 km.
+//
+// The functions are __host__ __device__ so tests/hostcheck can compile this very
+// file with g++ and compare it with the oracle on the CPU (test infrastructure;
+// the shipped library only ever instantiates the device side).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/kessler_b200.h"
+
+#if defined(__CUDACC__)
+#define KSL_HD __host__ __device__ __forceinline__
+#else
+#define KSL_HD inline
+#endif
+
+namespace ksl {
+
+constexpr double kMu = 398600.5;
+constexpr double kRe = 6378.137;
+constexpr double kJ2 = 0.00108262998905;
+constexpr double kJ3 = -0.00000253215306;
+constexpr double kJ4 = -0.00000161098761;
+constexpr double kJ3oJ2 = kJ3 / kJ2;
+constexpr double kTwoPi = 6.283185307179586;
+constexpr double kInvTwoPi = 0.15915494309189535;
+constexpr double kX2o3 = 2.0 / 3.0;
+// xke = 60/sqrt(re^3/mu), vkmpersec = re*xke/60: values of the FP64 expressions
+// dsgp4 evaluates (checked against the pickled _xke by tests/test_oracle_golden.py)
+constexpr double kXke = 0.07436685316871385;
+constexpr double kInvXke = 1.0 / kXke;
+constexpr double kVkmPerSec = kRe * kXke / 60.0;
+
+// ---- arithmetic with pinned rounding -------------------------------------------
+#if defined(__CUDA_ARCH__)
+KSL_HD double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+KSL_HD double add_rn(double a, double b) { return __dadd_rn(a, b); }
+KSL_HD double fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
+#else
+KSL_HD double mul_rn(double a, double b) { volatile double p = a * b; return p; }
+KSL_HD double add_rn(double a, double b) { volatile double s = a + b; return s; }
+KSL_HD double fma_rn(double a, double b, double c) { return fma(a, b, c); }
+#endif
+// a*b + c with the product rounded first (what `a*b + c` means in NumPy/torch)
+KSL_HD double mad_2r(double a, double b, double c) { return add_rn(mul_rn(a, b), c); }
+
+// Python/torch `x % 2pi` for finite x: the exact remainder with the sign of 2pi.
+// floor(x * (1/2pi)) can be off by one next to a multiple of 2pi; fma(-q, 2pi, x) is
+// exact (the remainder is representable), so one conditional step repairs it.  A tiny
+// negative x gives 2pi - |x| which ROUNDS to 2pi, exactly as fmod-based `%` does.
+KSL_HD double wrap_twopi(double x) {
+    const double q = floor(x * kInvTwoPi);
+    double r = fma_rn(-q, kTwoPi, x);
+    if (r < 0.0) r += kTwoPi;                                    // q one too large
+    else if (r > kTwoPi || (r == kTwoPi && x >= 0.0)) r -= kTwoPi;  // q one too small
+    return r;
+}
+
+KSL_HD void sincos_full(double x, double *s, double *c) {
+#if defined(__CUDA_ARCH__)
+    sincos(x, s, c);
+#else
+    *s = sin(x);
+    *c = cos(x);
+#endif
+}
+
+// sin/cos of a small angle, |d| <= kSmallAngle: truncation error < d^11/11! (2.5e-19 at 0.1)
+constexpr double kSmallAngle = 0.1;
+KSL_HD void sincos_small(double d, double *s, double *c) {
+    const double d2 = d * d;
+    double ps = fma_rn(d2, 2.7557319223985893e-06, -1.9841269841269841e-04);
+    ps = fma_rn(ps, d2, 8.3333333333333332e-03);
+    ps = fma_rn(ps, d2, -1.6666666666666666e-01);
+    *s = fma_rn(ps * d2, d, d);
+    double pc = fma_rn(d2, -2.7557319223985888e-07, 2.4801587301587302e-05);
+    pc = fma_rn(pc, d2, -1.3888888888888889e-03);
+    pc = fma_rn(pc, d2, 4.1666666666666664e-02);
+    pc = fma_rn(pc, d2, -0.5);
+    *c = fma_rn(pc, d2, 1.0);
+}
+
+// (s, c) of angle a  ->  (s, c) of angle a + d
+KSL_HD void rotate_by(double d, double a_plus_d, double *s, double *c) {
+    if (fabs(d) <= kSmallAngle) {
+        double sd, cd;
+        sincos_small(d, &sd, &cd);
+        const double s0 = *s, c0 = *c;
+        *s = fma_rn(s0, cd, c0 * sd);
+        *c = fma_rn(c0, cd, -(s0 * sd));
+    } else {
+        sincos_full(a_plus_d, s, c);
+    }
+}
+
+// ---- sgp4init -----------------------------------------------------------------
+// el = {no_kozai, ecco, inclo, nodeo, argpo, mo, bstar}; c[KSL_NCONST] with stride
+// `cs` between consecutive constants (1 for a private record, n for SoA).
+template <typename Store>
+KSL_HD int sgp4_init(const double el[7], Store &&put) {
+    const double no_kozai = el[0], ecco = el[1], inclo = el[2], nodeo = el[3], argpo = el[4], mo = el[5], bstar = el[6];
+    const double eccsq = ecco * ecco, omeosq = 1.0 - eccsq, rteosq = sqrt(omeosq);
+    double sinio, cosio;
+    sincos_full(inclo, &sinio, &cosio);
+    const double cosio2 = cosio * cosio;
+    const double ak = pow(kXke / no_kozai, kX2o3);
+    const double d1 = 0.75 * kJ2 * (3.0 * cosio2 - 1.0) / (rteosq * omeosq);
+    double del = d1 / (ak * ak);
+    const double adel = ak * (1.0 - del * del - del * (1.0 / 3.0 + 134.0 * del * del / 81.0));
+    del = d1 / (adel * adel);
+    const double no = no_kozai / (1.0 + del);
+    const double ao = pow(kXke / no, kX2o3);
+    const double po = ao * omeosq;
+    const double con42 = 1.0 - 5.0 * cosio2;
+    const double con41 = -con42 - cosio2 - cosio2;
+    const double posq = po * po;
+    const double rp = ao * (1.0 - ecco);
+    const bool isimp = rp < (220.0 / kRe + 1.0);
+    double sfour = 78.0 / kRe + 1.0;
+    const double qz0 = (120.0 - 78.0) / kRe;
+    double qzms24 = qz0 * qz0 * qz0 * qz0;
+    const double perige = (rp - 1.0) * kRe;
+    if (perige < 156.0) {
+        sfour = perige - 78.0;
+        if (perige < 98.0) sfour = 20.0;
+        const double q = (120.0 - sfour) / kRe;
+        qzms24 = q * q * q * q;
+        sfour = sfour / kRe + 1.0;
+    }
+    const double pinvsq = 1.0 / posq;
+    const double tsi = 1.0 / (ao - sfour);
+    const double eta = ao * ecco * tsi, etasq = eta * eta, eeta = ecco * eta;
+    const double psisq = fabs(1.0 - etasq);
+    const double tsi2 = tsi * tsi;
+    const double coef = qzms24 * (tsi2 * tsi2);
+    const double coef1 = coef / (psisq * psisq * psisq * sqrt(psisq));
+    const double cc2 = coef1 * no * (ao * (1.0 + 1.5 * etasq + eeta * (4.0 + etasq)) +
+                                     0.375 * kJ2 * tsi / psisq * con41 * (8.0 + 3.0 * etasq * (8.0 + etasq)));
+    const double cc1 = bstar * cc2;
+    double cc3 = 0.0;
+    if (ecco > 1.0e-4) cc3 = -2.0 * coef * tsi * kJ3oJ2 * no * sinio / ecco;
+    const double x1mth2 = 1.0 - cosio2;
+    double s2w, c2w;
+    sincos_full(2.0 * argpo, &s2w, &c2w);
+    (void)s2w;
+    const double cc4 = 2.0 * no * coef1 * ao * omeosq *
+                       (eta * (2.0 + 0.5 * etasq) + ecco * (0.5 + 2.0 * etasq) -
+                        kJ2 * tsi / (ao * psisq) *
+                            (-3.0 * con41 * (1.0 - 2.0 * eeta + etasq * (1.5 - 0.5 * eeta)) +
+                             0.75 * x1mth2 * (2.0 * etasq - eeta * (1.0 + etasq)) * c2w));
+    const double cc5 = 2.0 * coef1 * ao * omeosq * (1.0 + 2.75 * (etasq + eeta) + eeta * etasq);
+    const double cosio4 = cosio2 * cosio2;
+    const double temp1 = 1.5 * kJ2 * pinvsq * no;
+    const double temp2 = 0.5 * temp1 * kJ2 * pinvsq;
+    const double temp3 = -0.46875 * kJ4 * pinvsq * pinvsq * no;
+    const double mdot = no + 0.5 * temp1 * rteosq * con41 + 0.0625 * temp2 * rteosq * (13.0 - 78.0 * cosio2 + 137.0 * cosio4);
+    const double argpdot = -0.5 * temp1 * con42 + 0.0625 * temp2 * (7.0 - 114.0 * cosio2 + 395.0 * cosio4) +
+                           temp3 * (3.0 - 36.0 * cosio2 + 49.0 * cosio4);
+    const double xhdot1 = -temp1 * cosio;
+    const double nodedot = xhdot1 + (0.5 * temp2 * (4.0 - 19.0 * cosio2) + 2.0 * temp3 * (3.0 - 7.0 * cosio2)) * cosio;
+    double sw, cw;
+    sincos_full(argpo, &sw, &cw);
+    (void)sw;
+    const double omgcof = bstar * cc3 * cw;
+    double xmcof = 0.0;
+    if (ecco > 1.0e-4) xmcof = -kX2o3 * coef * bstar / eeta;
+    const double nodecf = 3.5 * omeosq * xhdot1 * cc1;
+    const double t2cof = 1.5 * cc1;
+    const double xl_den = (fabs(cosio + 1.0) > 1.5e-12) ? (1.0 + cosio) : 1.5e-12;
+    const double xlcof = -0.25 * kJ3oJ2 * sinio * (3.0 + 5.0 * cosio) / xl_den;
+    const double aycof = -0.5 * kJ3oJ2 * sinio;
+    double smo, cmo;
+    sincos_full(mo, &smo, &cmo);
+    const double delmotemp = 1.0 + eta * cmo;
+    const double delmo = delmotemp * delmotemp * delmotemp;
+    const double x7thm1 = 7.0 * cosio2 - 1.0;
+    double d2 = 0, d3 = 0, d4 = 0, t3cof = 0, t4cof = 0, t5cof = 0;
+    if (!isimp) {
+        const double cc1sq = cc1 * cc1;
+        d2 = 4.0 * ao * tsi * cc1sq;
+        const double temp = d2 * tsi * cc1 / 3.0;
+        d3 = (17.0 * ao + sfour) * temp;
+        d4 = 0.5 * temp * ao * tsi * (221.0 * ao + 31.0 * sfour) * cc1;
+        t3cof = d2 + 2.0 * cc1sq;
+        t4cof = 0.25 * (3.0 * d3 + cc1 * (12.0 * d2 + 10.0 * cc1sq));
+        t5cof = 0.2 * (3.0 * d4 + 12.0 * cc1 * d3 + 6.0 * d2 * d2 + 15.0 * cc1sq * (2.0 * d2 + cc1sq));
+    }
+    put(KSL_C_NO, no); put(KSL_C_ECCO, ecco); put(KSL_C_INCLO, inclo); put(KSL_C_NODEO, nodeo);
+    put(KSL_C_ARGPO, argpo); put(KSL_C_MO, mo); put(KSL_C_BSTAR, bstar); put(KSL_C_MDOT, mdot);
+    put(KSL_C_ARGPDOT, argpdot); put(KSL_C_NODEDOT, nodedot); put(KSL_C_NODECF, nodecf); put(KSL_C_CC1, cc1);
+    put(KSL_C_CC4, cc4); put(KSL_C_CC5, cc5); put(KSL_C_T2COF, t2cof); put(KSL_C_OMGCOF, omgcof);
+    put(KSL_C_XMCOF, xmcof); put(KSL_C_ETA, eta); put(KSL_C_DELMO, delmo); put(KSL_C_SINMAO, smo);
+    put(KSL_C_D2, d2); put(KSL_C_D3, d3); put(KSL_C_D4, d4); put(KSL_C_T3COF, t3cof); put(KSL_C_T4COF, t4cof);
+    put(KSL_C_T5COF, t5cof); put(KSL_C_AYCOF, aycof); put(KSL_C_XLCOF, xlcof); put(KSL_C_CON41, con41);
+    put(KSL_C_X1MTH2, x1mth2); put(KSL_C_X7THM1, x7thm1); put(KSL_C_ISIMP, isimp ? 1.0 : 0.0);
+    put(KSL_C_COSIO, cosio); put(KSL_C_SINIO, sinio); put(KSL_C_AOBASE, ao); put(KSL_C_PAD, 0.0);
+    if (!(no > 0.0) || !(no < 1.0e300)) return KSL_ERR_DEEPSPACE;   // NaN / inf / non-positive
+    return (kTwoPi / no >= 225.0) ? KSL_ERR_DEEPSPACE : 0;
+}
+
+// ---- sgp4 ---------------------------------------------------------------------
+// Load: c(k) returns constant k of this record (register array, shared memory
+// broadcast or an SoA global load).  r [km], v [km/s] (v skipped when !kVel).
+template <bool kVel, typename Load>
+KSL_HD int sgp4_prop(Load &&c, double t, double r[3], double v[3]) {
+    int err = 0;
+    // secular terms: product rounded, then the sum (reference rounding; see header)
+    const double xmdf = mad_2r(c(KSL_C_MDOT), t, c(KSL_C_MO));
+    const double argpdf = mad_2r(c(KSL_C_ARGPDOT), t, c(KSL_C_ARGPO));
+    const double nodedf = mad_2r(c(KSL_C_NODEDOT), t, c(KSL_C_NODEO));
+    const double t2 = t * t;
+    double nodem = mad_2r(c(KSL_C_NODECF), t2, nodedf);
+    const double cc1 = c(KSL_C_CC1), bstar = c(KSL_C_BSTAR);
+    double tempa = 1.0 - cc1 * t;
+    double tempe = (bstar * c(KSL_C_CC4)) * t;
+    double templ = c(KSL_C_T2COF) * t2;
+    double mm = xmdf, argpm = argpdf;
+    if (c(KSL_C_ISIMP) == 0.0) {
+        double sx, cx;
+        sincos_full(xmdf, &sx, &cx);
+        const double delomg = c(KSL_C_OMGCOF) * t;
+        const double delmtemp = 1.0 + c(KSL_C_ETA) * cx;
+        const double delm = c(KSL_C_XMCOF) * (delmtemp * delmtemp * delmtemp - c(KSL_C_DELMO));
+        const double temp = delomg + delm;
+        mm = add_rn(xmdf, temp);
+        argpm = add_rn(argpdf, -temp);
+        const double t3 = t2 * t, t4 = t3 * t;
+        tempa = tempa - c(KSL_C_D2) * t2 - c(KSL_C_D3) * t3 - c(KSL_C_D4) * t4;
+        rotate_by(temp, mm, &sx, &cx);   // sx = sin(mm)
+        tempe = tempe + (bstar * c(KSL_C_CC5)) * (sx - c(KSL_C_SINMAO));
+        templ = templ + c(KSL_C_T3COF) * t3 + t4 * (c(KSL_C_T4COF) + t * c(KSL_C_T5COF));
+    }
+    const double no = c(KSL_C_NO);
+    const double am = c(KSL_C_AOBASE) * tempa * tempa;
+    double em = c(KSL_C_ECCO) - tempe;
+    if (em >= 1.0 || em < -0.001) err |= KSL_ERR_ECC;
+    if (em < 1.0e-6) em = 1.0e-6;
+    mm = mad_2r(no, templ, mm);
+    const double xlm = add_rn(add_rn(mm, argpm), nodem);
+    nodem = wrap_twopi(nodem);
+    argpm = wrap_twopi(argpm);
+    const double xlmw = wrap_twopi(xlm);
+    mm = wrap_twopi(add_rn(add_rn(xlmw, -argpm), -nodem));
+
+    double sarg, carg;
+    sincos_full(argpm, &sarg, &carg);
+    const double axnl = em * carg;
+    double temp = 1.0 / (am * (1.0 - em * em));
+    const double aynl = em * sarg + temp * c(KSL_C_AYCOF);
+    const double xl = add_rn(add_rn(add_rn(mm, argpm), nodem), temp * c(KSL_C_XLCOF) * axnl);
+    const double u = wrap_twopi(add_rn(xl, -nodem));
+
+    // Kepler: u = eo1 - axnl sin(eo1) + aynl cos(eo1); Newton with the +-0.95 clamp.
+    // (se, ce) always belongs to the CURRENT eo1: a vectorised dsgp4 call iterates
+    // every lane until its slowest lane converged, which leaves converged lanes with
+    // sin/cos consistent with eo1; an exhausted lane keeps the pair one step behind.
+    double eo1 = u, se, ce;
+    sincos_full(u, &se, &ce);
+    double se_prev = se, ce_prev = ce;
+    bool converged = false;
+#pragma unroll 1
+    for (int ktr = 1; ktr <= 10; ++ktr) {
+        const double den = 1.0 - ce * axnl - se * aynl;
+        double d = (u - aynl * ce + axnl * se - eo1) / den;
+        d = (d >= 0.95) ? 0.95 : d;
+        d = (d <= -0.95) ? -0.95 : d;
+        eo1 += d;
+        se_prev = se;
+        ce_prev = ce;
+        rotate_by(d, eo1, &se, &ce);
+        if (fabs(d) < 1.0e-12) { converged = true; break; }
+    }
+    if (!converged) { se = se_prev; ce = ce_prev; }
+
+    const double ecose = axnl * ce + aynl * se;
+    const double esine = axnl * se - aynl * ce;
+    const double el2 = axnl * axnl + aynl * aynl;
+    const double pl = am * (1.0 - el2);
+    if (pl < 0.0) err |= KSL_ERR_SEMILATUS;
+    const double rl = am * (1.0 - ecose);
+    const double betal = sqrt(1.0 - el2);
+    temp = esine / (1.0 + betal);
+    const double amorl = am / rl;
+    double sinu = amorl * (se - aynl - axnl * temp);
+    double cosu = amorl * (ce - axnl + aynl * temp);
+    const double sin2u = (cosu + cosu) * sinu;
+    const double cos2u = 1.0 - 2.0 * sinu * sinu;
+    const double ipl = 1.0 / pl;
+    const double temp1 = 0.5 * kJ2 * ipl;
+    const double temp2 = temp1 * ipl;
+    const double con41 = c(KSL_C_CON41), x1mth2 = c(KSL_C_X1MTH2);
+    const double mrt = rl * (1.0 - 1.5 * temp2 * betal * con41) + 0.5 * temp1 * x1mth2 * cos2u;
+    const double cosio = c(KSL_C_COSIO), sinio = c(KSL_C_SINIO);
+    const double dsu = -0.25 * temp2 * c(KSL_C_X7THM1) * sin2u;   // su    = atan2(sinu,cosu) + dsu
+    const double dnode = 1.5 * temp2 * cosio * sin2u;             // xnode = nodem + dnode
+    const double dinc = 1.5 * temp2 * cosio * sinio * cos2u;      // xinc  = inclo + dinc
+
+    double sinsu, cossu, snod, cnod, sini, cosi;
+    if (fabs(dsu) <= kSmallAngle && fabs(dnode) <= kSmallAngle && fabs(dinc) <= kSmallAngle) {
+        // (sinu, cosu) is the unit vector of u up to rounding; renormalise to first order
+        const double h = fma_rn(-0.5, fma_rn(sinu, sinu, cosu * cosu) - 1.0, 1.0);
+        sinsu = sinu * h;
+        cossu = cosu * h;
+        rotate_by(dsu, 0.0, &sinsu, &cossu);
+        sincos_full(nodem, &snod, &cnod);
+        rotate_by(dnode, 0.0, &snod, &cnod);
+        sini = sinio;
+        cosi = cosio;
+        rotate_by(dinc, 0.0, &sini, &cosi);
+    } else {   // far from any physical orbit (pl << 1): take the long way round
+        const double su = atan2(sinu, cosu) + dsu;
+        sincos_full(su, &sinsu, &cossu);
+        sincos_full(nodem + dnode, &snod, &cnod);
+        sincos_full(c(KSL_C_INCLO) + dinc, &sini, &cosi);
+    }
+    const double xmx = -snod * cosi, xmy = cnod * cosi;
+    const double ux = xmx * sinsu + cnod * cossu;
+    const double uy = xmy * sinsu + snod * cossu;
+    const double uz = sini * sinsu;
+    const double mr = mrt * kRe;
+    r[0] = mr * ux;
+    r[1] = mr * uy;
+    r[2] = mr * uz;
+    if (mrt < 1.0) err |= KSL_ERR_DECAYED;
+    if (kVel) {
+        const double sqrt_am = sqrt(am);
+        const double nm = kXke / (am * sqrt_am);
+        if (nm <= 0.0) err |= KSL_ERR_MEANMOTION;
+        const double irl = 1.0 / rl;
+        const double rdotl = sqrt_am * esine * irl;
+        const double rvdotl = sqrt(pl) * irl;
+        const double mvt = rdotl - nm * temp1 * x1mth2 * sin2u * kInvXke;
+        const double rvdot = rvdotl + nm * temp1 * (x1mth2 * cos2u + 1.5 * con41) * kInvXke;
+        const double vx = xmx * cossu - cnod * sinsu;
+        const double vy = xmy * cossu - snod * sinsu;
+        const double vz = sini * cossu;
+        v[0] = (mvt * ux + rvdot * vx) * kVkmPerSec;
+        v[1] = (mvt * uy + rvdot * vy) * kVkmPerSec;
+        v[2] = (mvt * uz + rvdot * vz) * kVkmPerSec;
+    }
+    return err;
+}
+
+// ---- util.upsample index arithmetic (torch upsample_linear1d, align_corners) ----
+// scale = (n_in-1)/(n_out-1) in FP64; the integer part goes through FLOAT32.
+KSL_HD void upsample_index(int64_t j, double scale, int64_t n_in, int64_t *i0, int64_t *i1, double *w0, double *w1) {
+    const double src = (double)j * scale;
+    int64_t a = (int64_t)floorf((float)src);
+    if (a > n_in - 1) a = n_in - 1;
+    const int64_t b = (a + 1 < n_in) ? a + 1 : n_in - 1;
+    double l = src - (double)a;
+    l = l < 0.0 ? 0.0 : l;
+    l = l > 1.0 ? 1.0 : l;
+    *i0 = a;
+    *i1 = b;
+    *w1 = l;
+    *w0 = 1.0 - l;
+}
+
+// one interpolated coordinate, rounding exactly as torch's CPU upsample_linear1d kernel:
+// fma(w0, x0, w1*x1) (established against torch 2.11, tests/test_oracle_golden.py)
+KSL_HD double lerp_torch(double w0, double x0, double w1, double x1) { return fma_rn(w0, x0, mul_rn(w1, x1)); }
+// ... and in metres (util.py:579 `*1e3`)
+KSL_HD double lerp_m(double w0, double x0, double w1, double x1) { return mul_rn(lerp_torch(w0, x0, w1, x1), 1.0e3); }
+
+// squared distance, direct-difference form, no contraction
+KSL_HD double sqdist3(double dx, double dy, double dz) {
+    return add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
+}
+
+}  // namespace ksl

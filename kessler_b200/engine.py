@@ -1,0 +1,229 @@
+"""Thin torch-facing wrappers over the C ABI (include/kessler_b200.h).
+
+torch is plumbing here: it owns device memory and the current stream; every
+function below hands raw pointers to libkessler_b200.so.  All tensors are FP64
+(int64/int32 for indices/flags) on the current CUDA device.  There is no CPU path:
+calling any of these without a GPU raises ``KesslerCudaError``.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native as N
+from ._native import KesslerCudaError, ptr, stream_ptr  # noqa: F401
+
+F64 = torch.float64
+
+
+def _dev():
+    N.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _cf64(x, dev):
+    """contiguous FP64 tensor on dev"""
+    if not torch.is_tensor(x):
+        x = torch.as_tensor(np.asarray(x, dtype=np.float64))
+    return x.to(device=dev, dtype=F64).contiguous()
+
+
+# --- dsgp4.initialize_tle -------------------------------------------------------------
+def sgp4_init(elems):
+    """elems SoA [7, n] (no_kozai rad/min, ecco, inclo, nodeo, argpo, mo, bstar)
+    -> (consts [36, n], err [n] int32)."""
+    dev = _dev()
+    elems = _cf64(elems, dev)
+    assert elems.dim() == 2 and elems.shape[0] == 7
+    n = elems.shape[1]
+    consts = torch.empty((N.NCONST, n), dtype=F64, device=dev)
+    err = torch.empty(n, dtype=torch.int32, device=dev)
+    N.check(N.lib().ksl_sgp4_init(ptr(elems), n, ptr(consts), ptr(err), stream_ptr()), "ksl_sgp4_init")
+    return consts, err
+
+
+# --- dsgp4.propagate / propagate_batch ------------------------------------------------
+def sgp4_prop(consts, tsince, per_sample_t=False, err=None):
+    """consts [36, n]; tsince [m] (shared) or [n, m] -> rv [n, m, 6] km, km/s; err [n]."""
+    dev = _dev()
+    consts = _cf64(consts, dev)
+    tsince = _cf64(tsince, dev)
+    n = consts.shape[1]
+    m = tsince.shape[-1] if tsince.dim() > 0 else 1
+    if per_sample_t:
+        assert tsince.numel() == n * m
+    rv = torch.empty((n, m, 6), dtype=F64, device=dev)
+    if err is None:
+        err = torch.zeros(n, dtype=torch.int32, device=dev)
+    N.check(N.lib().ksl_sgp4_prop(ptr(consts), n, ptr(tsince), m, 1 if per_sample_t else 0, ptr(rv), ptr(err),
+                                  stream_ptr()), "ksl_sgp4_prop")
+    return rv, err
+
+
+# --- util.upsample ---------------------------------------------------------------------
+def upsample(x, n_out):
+    dev = _dev()
+    x = _cf64(x, dev)
+    assert x.dim() == 2
+    y = torch.empty((n_out, x.shape[1]), dtype=F64, device=dev)
+    N.check(N.lib().ksl_upsample(ptr(x), x.shape[0], x.shape[1], n_out, ptr(y), stream_ptr()), "ksl_upsample")
+    return y
+
+
+# --- util.propagate_upsample -----------------------------------------------------------
+def propagate_upsample(consts1, epoch_mjd, times_sub, n_out):
+    """consts1 [36] or [36,1]; times_sub = times_mjd[::upsample_factor] -> ([n_out, 6] m, m/s; err int32[1])."""
+    dev = _dev()
+    consts1 = _cf64(consts1, dev).reshape(-1)
+    assert consts1.numel() == N.NCONST
+    times_sub = _cf64(times_sub, dev)
+    n_sub = times_sub.numel()
+    out = torch.empty((n_out, 6), dtype=F64, device=dev)
+    ws = torch.empty(n_sub * 6, dtype=F64, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    N.check(N.lib().ksl_propagate_upsample(ptr(consts1), float(epoch_mjd), ptr(times_sub), n_sub, n_out, ptr(out),
+                                           ptr(ws), ptr(err), stream_ptr()), "ksl_propagate_upsample")
+    return out, err
+
+
+# --- model.find_conjunction ------------------------------------------------------------
+def find_conjunction(tr0, tr1, thr):
+    """tr0, tr1 [n, >=3] device tensors (row stride taken from the tensor).
+    Returns (out_i int64[2] = i_min, i_conj|-1 ; out_d f64[2] = d_min, d_conj|nan)."""
+    dev = _dev()
+    tr0 = tr0.to(device=dev, dtype=F64)
+    tr1 = tr1.to(device=dev, dtype=F64)
+    if tr0.stride(-1) != 1 or tr0.stride(0) != tr1.stride(0) or tr1.stride(-1) != 1:
+        tr0, tr1 = tr0.contiguous(), tr1.contiguous()
+    n, stride = tr0.shape[0], tr0.stride(0)
+    if n == 1:
+        stride = max(stride, 3)
+    out_i = torch.empty(2, dtype=torch.int64, device=dev)
+    out_d = torch.empty(2, dtype=F64, device=dev)
+    ws = torch.empty(int(N.lib().ksl_find_conjunction_ws(n)), dtype=torch.uint8, device=dev)
+    N.check(N.lib().ksl_find_conjunction(ptr(tr0), ptr(tr1), n, stride, float(thr), ptr(out_i), ptr(out_d), ptr(ws),
+                                         stream_ptr()), "ksl_find_conjunction")
+    return out_i, out_d
+
+
+# --- the fused trace -------------------------------------------------------------------
+def screen(consts_t, epoch_t, consts_c, epoch_c, times_coarse, n_fine, thr_m, mode=N.SCREEN_ANALYTIC,
+           init_err_t=None, init_err_c=None):
+    """Returns dict(i_min, d_min, i_conj, d_conj, err) of device tensors [n]."""
+    dev = _dev()
+    consts_t, consts_c = _cf64(consts_t, dev), _cf64(consts_c, dev)
+    if consts_t.dim() == 1:
+        consts_t = consts_t.reshape(N.NCONST, 1)
+    epoch_t = _cf64(epoch_t, dev).reshape(-1)
+    epoch_c = _cf64(epoch_c, dev).reshape(-1)
+    times_coarse = _cf64(times_coarse, dev)
+    n_t, n = consts_t.shape[1], consts_c.shape[1]
+    assert epoch_t.numel() == n_t and epoch_c.numel() == n and n_t in (1, n)
+    out = dict(i_min=torch.empty(n, dtype=torch.int64, device=dev), d_min=torch.empty(n, dtype=F64, device=dev),
+               i_conj=torch.empty(n, dtype=torch.int64, device=dev), d_conj=torch.empty(n, dtype=F64, device=dev),
+               err=torch.empty(n, dtype=torch.int32, device=dev))
+    n_coarse = times_coarse.numel()
+    ws = torch.empty(int(N.lib().ksl_screen_ws(n_t, n, n_coarse)), dtype=torch.uint8, device=dev)
+    N.check(N.lib().ksl_screen(ptr(consts_t), ptr(epoch_t), ptr(init_err_t), n_t, ptr(consts_c), ptr(epoch_c),
+                               ptr(init_err_c), n, ptr(times_coarse), n_coarse, int(n_fine), float(thr_m), int(mode),
+                               ptr(out["i_min"]), ptr(out["d_min"]), ptr(out["i_conj"]), ptr(out["d_conj"]),
+                               ptr(out["err"]), ptr(ws), stream_ptr()), "ksl_screen")
+    return out
+
+
+def screen_summary(res, collision_thr_m):
+    """res = dict from screen(); returns (counts uint64-as-int64 [8], moments f64 [4]) device tensors."""
+    dev = _dev()
+    n = res["i_min"].numel()
+    counts = torch.zeros(N.SUM_NCOUNT, dtype=torch.int64, device=dev)
+    moments = torch.zeros(N.SUM_NMOMENT, dtype=F64, device=dev)
+    ws = torch.empty(int(N.lib().ksl_screen_summary_ws(n)), dtype=torch.uint8, device=dev)
+    N.check(N.lib().ksl_screen_summary(ptr(res["i_conj"]), ptr(res["d_min"]), ptr(res["err"]), n, float(collision_thr_m),
+                                       ptr(counts), ptr(moments), ptr(ws), stream_ptr()), "ksl_screen_summary")
+    return counts, moments
+
+
+# --- Monte Carlo covariance at TCA -------------------------------------------------------
+def tca_moments(elems, tsince, ref_state_m, want_states=False):
+    """elems SoA [7, n] -> (moments f64[28], err_count int64[1], states [n,6] m or None)."""
+    dev = _dev()
+    elems = _cf64(elems, dev)
+    n = elems.shape[1]
+    ref = _cf64(ref_state_m, dev).reshape(-1)
+    assert ref.numel() == 6
+    moments = torch.empty(N.NMOMENT, dtype=F64, device=dev)
+    errc = torch.zeros(1, dtype=torch.int64, device=dev)
+    states = torch.empty((n, 6), dtype=F64, device=dev) if want_states else None
+    ws = torch.empty(int(N.lib().ksl_tca_moments_ws(n)), dtype=torch.uint8, device=dev)
+    N.check(N.lib().ksl_tca_moments(ptr(elems), n, float(tsince), ptr(ref), ptr(states), ptr(moments), ptr(errc), ptr(ws),
+                                    stream_ptr()), "ksl_tca_moments")
+    return moments, errc, states
+
+
+# --- Monte Carlo collision count ----------------------------------------------------------
+def pc_count(t_xyz, c_xyz, thr_m, pairing=N.PAIR_ALL, count=None):
+    """t_xyz SoA [3, nt], c_xyz SoA [3, nc] metres -> int64[1] device tensor (accumulated into `count`)."""
+    dev = _dev()
+    t_xyz, c_xyz = _cf64(t_xyz, dev), _cf64(c_xyz, dev)
+    assert t_xyz.shape[0] == 3 and c_xyz.shape[0] == 3
+    if count is None:
+        count = torch.zeros(1, dtype=torch.int64, device=dev)
+    N.check(N.lib().ksl_pc_count(ptr(t_xyz), t_xyz.shape[1], ptr(c_xyz), c_xyz.shape[1], float(thr_m), int(pairing),
+                                 ptr(count), stream_ptr()), "ksl_pc_count")
+    return count
+
+
+# --- end-to-end: host buffers in / out -----------------------------------------------------
+def screen_host(elems_t, epoch_t, elems_c, epoch_c, times_coarse, n_fine, thr_m, mode=N.SCREEN_ANALYTIC,
+                collision_thr_m=70.0, device=None, out=None, want_summary=True):
+    """numpy (or pinned torch CPU) arrays in, numpy arrays out; all transfers inside."""
+    N.require_cuda()
+    if device is None:
+        device = torch.cuda.current_device()
+    as_np = lambda a: np.ascontiguousarray(a.numpy() if torch.is_tensor(a) else a, dtype=np.float64)
+    elems_t, elems_c = as_np(elems_t), as_np(elems_c)
+    if elems_t.ndim == 1:
+        elems_t = elems_t.reshape(7, 1)
+    epoch_t = as_np(np.atleast_1d(epoch_t))
+    epoch_c = as_np(np.atleast_1d(epoch_c))
+    times_coarse = as_np(times_coarse)
+    n_t, n = elems_t.shape[1], elems_c.shape[1]
+    if out is None:
+        out = dict(i_min=np.empty(n, dtype=np.int64), d_min=np.empty(n), i_conj=np.empty(n, dtype=np.int64),
+                   d_conj=np.empty(n), err=np.empty(n, dtype=np.int32))
+    counts = np.zeros(N.SUM_NCOUNT, dtype=np.uint64) if want_summary else None
+    moments = np.zeros(N.SUM_NMOMENT) if want_summary else None
+    N.check(N.lib().ksl_screen_host(int(device), ptr(elems_t), ptr(epoch_t), n_t, ptr(elems_c), ptr(epoch_c), n,
+                                    ptr(times_coarse), times_coarse.size, int(n_fine), float(thr_m), int(mode),
+                                    float(collision_thr_m), ptr(out["i_min"]), ptr(out["d_min"]), ptr(out["i_conj"]),
+                                    ptr(out["d_conj"]), ptr(out["err"]), ptr(counts), ptr(moments)), "ksl_screen_host")
+    out = dict(out)
+    out["counts"], out["moments"] = counts, moments
+    return out
+
+
+# --- measurement ---------------------------------------------------------------------------
+def fp64_peak_tflops(iters=20000, reps=5):
+    """Measured DFMA throughput of the current device (dependent-free chains), TFLOP/s."""
+    dev = _dev()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    blocks, threads = sms * 8, 256
+    sink = torch.zeros(1, dtype=F64, device=dev)
+    run = lambda it: N.check(N.lib().ksl_fp64_peak_kernel(blocks, threads, it, ptr(sink), stream_ptr()), "fp64_peak")
+    run(1000)
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(iters)
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        flops = 2.0 * 8 * iters * blocks * threads
+        best = max(best, flops / (ms * 1e-3) / 1e12)
+    return best
+
+
+def launch_count():
+    return int(N.lib().ksl_launch_count())

@@ -1,0 +1,122 @@
+"""The dsgp4 calls Kessler's hot path makes, served by the B200 kernels.
+
+Same names and argument meaning as the reference's call sites
+(/root/reference/kessler/model.py:514-516,536-541,581,592; util.py:570-576):
+``initialize_tle(tle | [tle...])``, ``propagate(tle, tsinces)``,
+``propagate_batch(tle_batch, tsinces)``, ``sgp4(tle, tsince)``, plus
+``util.get_gravity_constants``.  Deep-space TLEs raise ``ValueError`` from
+``initialize_tle`` as dsgp4 does, which is what Conjunction.forward()'s bare ``except``
+turns into ``conj=False`` (model.py:580-599).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import engine
+from . import _native as N
+from .tle import TLE, from_datetime_to_mjd
+
+CONST_NAMES = ("no_unkozai", "ecco", "inclo", "nodeo", "argpo", "mo", "bstar", "mdot", "argpdot", "nodedot", "nodecf",
+               "cc1", "cc4", "cc5", "t2cof", "omgcof", "xmcof", "eta", "delmo", "sinmao", "d2", "d3", "d4", "t3cof",
+               "t4cof", "t5cof", "aycof", "xlcof", "con41", "x1mth2", "x7thm1", "isimp", "cosio", "sinio", "aobase", "pad")
+
+
+class util:  # namespace mirroring dsgp4.util for the few helpers Kessler calls
+    @staticmethod
+    def get_gravity_constants(gravity_constant_name="wgs-84"):
+        """(tumin, mu, radiusearthkm, xke, j2, j3, j4, j3oj2) -- model.py:571."""
+        if gravity_constant_name != "wgs-84":
+            raise RuntimeError("only wgs-84 is supported (the constant set Kessler uses, model.py:571)")
+        mu, re = 398600.5, 6378.137
+        xke = 60.0 / math.sqrt(re * re * re / mu)
+        j2, j3, j4 = 0.00108262998905, -0.00000253215306, -0.00000161098761
+        return (torch.tensor(1.0 / xke), torch.tensor(mu), torch.tensor(re), torch.tensor(xke), torch.tensor(j2),
+                torch.tensor(j3), torch.tensor(j4), torch.tensor(j3 / j2))
+
+    from_datetime_to_mjd = staticmethod(from_datetime_to_mjd)
+
+
+class TLEBatch:
+    """What ``initialize_tle([tle, ...])`` returns as its second value: the initialised
+    records as a device-resident SoA block (consts [36, n]) ready for propagate_batch."""
+
+    def __init__(self, consts, err, tles):
+        self.consts, self.err, self.tles = consts, err, tles
+
+    def __len__(self):
+        return self.consts.shape[1]
+
+
+def _elements(tles):
+    return np.stack([t.elements() for t in tles], axis=1)
+
+
+def initialize_tle(tles, gravity_constant_name="wgs-84", with_grad=False):
+    """dsgp4.initialize_tle: runs sgp4init on the GPU.  Single TLE: sets the coefficient
+    attributes (``_cc1`` ... as dsgp4 does) and returns its element tensor; list: returns
+    (elements [n, 7], TLEBatch).  Raises ValueError for a deep-space orbit."""
+    if with_grad:
+        raise NotImplementedError("differentiable SGP4 is outside the Monte Carlo hot path")
+    single = isinstance(tles, TLE)
+    lst = [tles] if single else list(tles)
+    el = _elements(lst)
+    consts, err = engine.sgp4_init(el)
+    err_h = err.cpu().numpy()
+    if (err_h & N.ERR_DEEPSPACE).any():
+        bad = int(np.nonzero(err_h & N.ERR_DEEPSPACE)[0][0])
+        raise ValueError(f"TLE {bad}: deep-space orbit (period >= 225 min) is not supported by the near-earth SGP4 "
+                         "(dsgp4.initialize_tle raises here as well)")
+    ch = consts.cpu().numpy()
+    for i, t in enumerate(lst):
+        for k, name in enumerate(CONST_NAMES[:-1]):
+            setattr(t, "_no_unkozai" if name == "no_unkozai" else "_" + name, float(ch[k, i]))
+        t._isimp = int(ch[31, i])
+        t._consts = consts[:, i].contiguous()
+        t._initialized = True
+    if single:
+        return torch.from_numpy(el[:, 0].copy())
+    return torch.from_numpy(el.T.copy()), TLEBatch(consts, err, lst)
+
+
+def _consts_of(tle):
+    if not getattr(tle, "_initialized", False):
+        initialize_tle(tle)
+    return tle._consts
+
+
+def propagate(tle, tsinces, initialized=True):
+    """dsgp4.propagate(tle, tsinces) -> CPU tensor [N, 2, 3] (or [2, 3] for a scalar) km, km/s."""
+    ts = torch.as_tensor(tsinces, dtype=torch.float64)
+    scalar = ts.dim() == 0
+    rv, err = engine.sgp4_prop(_consts_of(tle).reshape(N.NCONST, 1), ts.reshape(-1))
+    tle._error = int(err[0])
+    out = rv[0].reshape(-1, 2, 3).cpu()
+    return out[0] if scalar else out
+
+
+sgp4 = propagate
+
+
+def propagate_batch(tle_batch, tsinces, initialized=True):
+    """dsgp4.propagate_batch(batch, tsinces[n]) -> CPU tensor [n, 2, 3]: record i at tsinces[i]."""
+    ts = torch.as_tensor(tsinces, dtype=torch.float64).reshape(-1)
+    assert ts.numel() == len(tle_batch)
+    rv, err = engine.sgp4_prop(tle_batch.consts, ts.reshape(-1, 1), per_sample_t=True)
+    return rv.reshape(-1, 2, 3).cpu()
+
+
+def propagate_upsample_device(tle, times_mjd, upsample_factor=1):
+    """util.propagate_upsample on the device: [N, 6] metres, m/s (stays in HBM)."""
+    times_mjd = np.asarray(times_mjd, dtype=np.float64)
+    consts = _consts_of(tle)
+    epoch = from_datetime_to_mjd(tle._epoch)
+    take_every = max(int(upsample_factor), 1)
+    if int(upsample_factor) == 1:                                # util.py:569-571: no interpolation at all
+        rv, err = engine.sgp4_prop(consts.reshape(N.NCONST, 1), (times_mjd - epoch) * 1440.0)
+        tle._error = int(err[0])
+        return rv[0] * 1e3
+    sub = np.ascontiguousarray(times_mjd[::take_every])          # util.py:573-574
+    out, err = engine.propagate_upsample(consts, epoch, sub, len(times_mjd))
+    tle._error = int(err[0])
+    return out

@@ -172,6 +172,31 @@ def rotation_matrix(state):
     return np.vstack((u, t, w))
 
 
+def cartesian_to_keplerian(r_vec, v_vec, mu):
+    """util.py:187-264 in NumPy (elliptic branch): (a, e, i, Omega, omega, M)."""
+    r_vec, v_vec = np.asarray(r_vec, dtype=np.float64), np.asarray(v_vec, dtype=np.float64)
+    r, v = np.linalg.norm(r_vec), np.linalg.norm(v_vec)
+    h_vec = np.cross(r_vec, v_vec)
+    h = np.linalg.norm(h_vec)
+    i = np.arccos(h_vec[2] / h) if h != 0 else 0.0
+    n_vec = np.cross(np.array([0.0, 0.0, 1.0]), h_vec)
+    n = np.linalg.norm(n_vec)
+    e_vec = (1 / mu) * ((v ** 2 - mu / r) * r_vec - np.dot(r_vec, v_vec) * v_vec)
+    e = np.linalg.norm(e_vec)
+    energy = v ** 2 / 2 - mu / r
+    a = -mu / (2 * energy) if abs(e - 1.0) > 1e-8 else np.inf
+    raw = np.arccos(np.clip(n_vec[0] / n, -1.0, 1.0)) if n != 0 else 0.0
+    Omega = (raw if n_vec[1] >= 0 else 2 * np.pi - raw) if n != 0 else 0.0
+    raw = np.arccos(np.clip(np.dot(n_vec, e_vec) / (n * e + 1e-12), -1.0, 1.0))
+    omega = (raw if e_vec[2] >= 0 else 2 * np.pi - raw) if (n != 0 and e != 0) else 0.0
+    raw = np.arccos(np.clip(np.dot(e_vec, r_vec) / (e * r + 1e-12), -1.0, 1.0))
+    nu = (raw if np.dot(r_vec, v_vec) >= 0 else 2 * np.pi - raw) if e != 0 else 0.0
+    E = 2 * np.arctan(np.tan(nu / 2) * np.sqrt((1 - e) / (1 + e)))
+    M = E - e * np.sin(E)
+    wrap = lambda x: x - (2 * np.pi) * np.floor(x / (2 * np.pi))
+    return a, e, i, wrap(Omega), wrap(omega), wrap(M)
+
+
 # --------------------------------------------------------------------------
 # Monte Carlo covariance at TCA (model.py:497-551), given the element samples
 # --------------------------------------------------------------------------

@@ -12,6 +12,9 @@ Fixture 1  trace_golden.json
     plus time0 / delta_time / i_conj / time_conj / d_conj / time_min / d_min /
     max_ncdm / time_cdm_i.
 
+Fixture 3  population.json
+    The 20 TLEs of docs/notebooks/tles_sample_population.txt as text + parsed elements.
+
 Fixture 2  reference_functions.npz
     Outputs of the reference's OWN functions that do not need dsgp4 arithmetic
     (kessler/util.py: upsample, find_closest, rotation_matrix,
@@ -260,7 +263,25 @@ def make_reference_functions():
     return out
 
 
+def make_population():
+    """docs/notebooks/tles_sample_population.txt -> population.json (parsed numbers only)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import sgp4_ref as S
+    lines = open(os.path.join(REF, "docs/notebooks/tles_sample_population.txt")).read().splitlines()
+    pop = []
+    for i in range(0, len(lines), 3):
+        p = S.parse_tle_lines(lines[i + 1], lines[i + 2])
+        p.pop("epoch_dt")
+        p["name"] = lines[i][2:].strip()
+        p["line1"], p["line2"] = lines[i + 1], lines[i + 2]
+        pop.append(p)
+    with open(os.path.join(HERE, "population.json"), "w") as fh:
+        json.dump(pop, fh, indent=1, sort_keys=True)
+    return pop
+
+
 if __name__ == "__main__":
+    print("population.json:", len(make_population()), "TLEs")
     g = make_trace_golden()
     print("trace_golden.json:", len(g["sites"]), "sites,", len(g["tles"]), "tles,", len(g["cdms"]), "cdms")
     o = make_reference_functions()

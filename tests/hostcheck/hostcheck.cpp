@@ -1,0 +1,91 @@
+// hostcheck.cpp -- TEST INFRASTRUCTURE.  Compiles kessler_b200/csrc/sgp4_device.cuh
+// (the very header the CUDA kernels instantiate) for the HOST with g++, so the
+// restructured SGP4 algebra can be compared with the oracle on a machine without
+// a GPU (tests/test_hostcheck.py).  Never linked into libkessler_b200.so.
+#include <cstdint>
+#include <vector>
+#include "../../kessler_b200/csrc/sgp4_device.cuh"
+#include "../../kessler_b200/csrc/screen_device.cuh"
+
+extern "C" {
+
+int hc_sgp4_init(const double *elems, int64_t n, double *consts, int32_t *err) {
+    for (int64_t i = 0; i < n; ++i) {
+        double el[7];
+        for (int k = 0; k < 7; ++k) el[k] = elems[k * n + i];
+        int e = ksl::sgp4_init(el, [&](int k, double v) { consts[(int64_t)k * n + i] = v; });
+        if (err) err[i] = e;
+    }
+    return 0;
+}
+
+int hc_sgp4_prop(const double *consts, int64_t n, const double *tsince, int64_t m, int per_sample_t, int want_vel,
+                 double *rv, int32_t *err) {
+    for (int64_t i = 0; i < n; ++i) {
+        int e = 0;
+        auto ld = [&](int k) { return consts[(int64_t)k * n + i]; };
+        for (int64_t j = 0; j < m; ++j) {
+            double t = per_sample_t ? tsince[i * m + j] : tsince[j];
+            double *o = rv + (i * m + j) * 6;
+            if (want_vel) e |= ksl::sgp4_prop<true>(ld, t, o, o + 3);
+            else { e |= ksl::sgp4_prop<false>(ld, t, o, o + 3); o[3] = o[4] = o[5] = 0.0; }
+        }
+        if (err) err[i] |= e;
+    }
+    return 0;
+}
+
+int hc_upsample_index(int64_t j, int64_t n_in, int64_t n_out, int64_t *i0, int64_t *i1, double *w0, double *w1) {
+    double scale = n_out > 1 ? (double)(n_in - 1) / (double)(n_out - 1) : 0.0;
+    ksl::upsample_index(j, scale, n_in, i0, i1, w0, w1);
+    return 0;
+}
+
+double hc_wrap_twopi(double x) { return ksl::wrap_twopi(x); }
+
+// Host emulation of k_screen's data flow (kessler_b200.cu): kThreads "threads" walk the
+// coarse epochs in chunks of kThreads with a one-epoch overlap, each keeping its own
+// running Best (which is what the analytic pruning sees), merged at the end.
+int hc_screen(const double *consts_t, const double *epoch_t, int64_t n_t, const double *consts_c, const double *epoch_c,
+              int64_t n, const double *times_coarse, int64_t n_coarse, int64_t n_fine, double thr, int mode,
+              int64_t *i_min, double *d_min, int64_t *i_conj, double *d_conj, int32_t *err) {
+    const int kThreads = 256;
+    const double scale = n_fine > 1 ? (double)(n_coarse - 1) / (double)(n_fine - 1) : 0.0;
+    const double thr2 = thr * thr;
+    const long long last = n_coarse - 1;
+    std::vector<double> pt(3 * n_coarse), pc(3 * n_coarse);
+    for (int64_t s = 0; s < n; ++s) {
+        const int64_t it = (n_t == 1) ? 0 : s;
+        int et = 0, ec = 0;
+        auto ldt = [&](int q) { return consts_t[(int64_t)q * n_t + it]; };
+        auto ldc = [&](int q) { return consts_c[(int64_t)q * n + s]; };
+        for (int64_t k = 0; k < n_coarse; ++k) {
+            double v[3];
+            et |= ksl::sgp4_prop<false>(ldt, (times_coarse[k] - epoch_t[it]) * 1440.0, &pt[3 * k], v);
+            ec |= ksl::sgp4_prop<false>(ldc, (times_coarse[k] - epoch_c[s]) * 1440.0, &pc[3 * k], v);
+        }
+        std::vector<ksl::Best> best(kThreads);
+        for (auto &b : best) ksl::best_init(b);
+        for (long long base = 0; base < last || base == 0; base += kThreads - 1) {
+            for (int tid = 0; tid < kThreads; ++tid) {
+                const long long k = base + tid;
+                const bool owner = (k < last && tid < kThreads - 1) || (k == last);
+                if (!owner) continue;
+                const long long nb = (k == last) ? k : k + 1;
+                if (mode == 0)
+                    ksl::segment_search<0>(k, last, scale, n_coarse, n_fine, thr2, &pt[3 * k], &pt[3 * nb], &pc[3 * k], &pc[3 * nb], best[tid]);
+                else
+                    ksl::segment_search<1>(k, last, scale, n_coarse, n_fine, thr2, &pt[3 * k], &pt[3 * nb], &pc[3 * k], &pc[3 * nb], best[tid]);
+            }
+        }
+        ksl::Best b = best[0];
+        for (int tid = 1; tid < kThreads; ++tid) ksl::best_merge(b, best[tid]);
+        long long im, ic;
+        ksl::best_result(b, &im, d_min + s, &ic, d_conj + s);
+        i_min[s] = im;
+        i_conj[s] = ic;
+        err[s] = et | (ec << KSL_ERR_CHASER_SHIFT);
+    }
+    return 0;
+}
+}

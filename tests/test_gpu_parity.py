@@ -1,0 +1,333 @@
+"""Parity of the CUDA path (through the C ABI, via kessler_b200.engine) against the oracle.
+
+Bar (BASELINE.json north_star): positions within 1e-6 km, TCA within 1e-3 s (= the exact
+fine-grid index; the grid step is 1.008 s), collision counts bit-exact on identical samples.
+The tolerances actually asserted are tighter and are written next to each check."""
+import numpy as np
+import pytest
+import torch
+
+import common
+from oracle import c_oracle as C
+from oracle import kessler_path as K
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL_KM = 1e-6      # north-star tolerance of record
+POS_TIGHT_KM = 5e-8    # what we hold the kernels to when they compute their own sgp4init
+POS_SAMEC_KM = 1e-9    # ... and when fed the oracle's constants (isolates propagation)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from kessler_b200 import engine
+    torch.cuda.set_device(0)
+    return engine
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------
+def test_sgp4init_parity(eng):
+    el, _ = common.population_elems()
+    gt, _, gc, _, _ = common.golden_pair()
+    el = np.concatenate([gt[:, None], gc[:, None], el, common.synthetic_catalog(4000)], axis=1)
+    c_ref, e_ref = C.sgp4_init(el)
+    c, e = eng.sgp4_init(el)
+    c, e = _np(c), _np(e)
+    assert np.array_equal(e, e_ref)                    # deep-space refusal: flag parity
+    ok = e_ref == 0
+    rel = np.abs(c[:, ok] - c_ref[:, ok]) / np.maximum(np.abs(c_ref[:, ok]), 1e-300)
+    assert rel.max() < 5e-13
+    assert np.array_equal(c[31], c_ref[31])            # isimp branch identical
+    # golden coefficients straight from trace.pickle
+    g = common.golden_trace()["tles"]
+    for col, who in enumerate(("t_tle", "c_tle")):
+        for idx, name in ((11, "_cc1"), (12, "_cc4"), (7, "_mdot"), (0, "_no_unkozai"), (25, "_t5cof"), (27, "_xlcof")):
+            assert c[idx, col] == pytest.approx(g[who][name], rel=1e-14, abs=0)
+
+
+def test_sgp4_prop_parity_window(eng):
+    """Both golden TLEs + the 20 population TLEs over +-5e4 min, own init and oracle init."""
+    el, _ = common.population_elems()
+    gt, _, gc, _, _ = common.golden_pair()
+    el = np.concatenate([gt[:, None], gc[:, None], el], axis=1)
+    ts = np.linspace(-5.0e4, 5.0e4, 2001)
+    c_ref, e0 = C.sgp4_init(el)
+    rv_ref, e_ref = C.sgp4_prop(c_ref, ts)
+    rv_same, e_same = eng.sgp4_prop(torch.from_numpy(c_ref), ts)
+    c_own, _ = eng.sgp4_init(el)
+    rv_own, e_own = eng.sgp4_prop(c_own, ts)
+    rv_same, rv_own = _np(rv_same), _np(rv_own)
+    good = e_ref == 0
+    assert good.sum() >= 19
+    assert np.array_equal(_np(e_same), e_ref) and np.array_equal(_np(e_own), e_ref)
+    assert np.abs(rv_same[good][..., :3] - rv_ref[good][..., :3]).max() < POS_SAMEC_KM
+    assert np.abs(rv_same[good][..., 3:] - rv_ref[good][..., 3:]).max() < 1e-12
+    assert np.abs(rv_own[good][..., :3] - rv_ref[good][..., :3]).max() < POS_TIGHT_KM < POS_TOL_KM
+    assert np.abs(rv_own[good][..., 3:] - rv_ref[good][..., 3:]).max() < 1e-10
+
+
+def test_sgp4_prop_parity_catalog_and_flags(eng):
+    """Synthetic prior-like catalog incl. every branch the fixtures miss; per-sample tsince."""
+    el = common.synthetic_catalog(3000, seed=11)
+    rng = np.random.default_rng(12)
+    ts = rng.uniform(-3.0e4, 3.0e4, (3000, 7))
+    c_ref, e0 = C.sgp4_init(el)
+    rv_ref, e_ref = C.sgp4_prop(c_ref, ts, per_sample_t=True)
+    c_own, e0g = eng.sgp4_init(el)
+    rv, e = eng.sgp4_prop(c_own, ts, per_sample_t=True)
+    rv, e = _np(rv), _np(e)
+    assert np.array_equal(_np(e0g), e0)
+    ok = e0 == 0
+    assert np.array_equal(e[ok], e_ref[ok])            # Vallado error bits: flag parity
+    good = ok & (e_ref == 0)
+    assert good.sum() > 2000
+    assert np.abs(rv[good][..., :3] - rv_ref[good][..., :3]).max() < POS_TIGHT_KM
+    bad = ok & (e_ref != 0)
+    assert np.array_equal(np.isnan(rv[bad]), np.isnan(rv_ref[bad]))
+
+
+def test_reference_unit_test_state_at_epoch(eng):
+    """tests/test_util.py:105-131 through the GPU: sgp4(tle, 0) -> Kepler elements, 5 places."""
+    from oracle import sgp4_ref as S
+    p = S.parse_tle_lines(*common.TLE_34427)
+    el = np.array([[p[k]] for k in ("no_kozai", "ecco", "inclo", "nodeo", "argpo", "mo", "bstar")])
+    c, _ = eng.sgp4_init(el)
+    rv, _ = eng.sgp4_prop(c, [0.0])
+    rv = _np(rv)[0, 0] * 1e3
+    kep = K.cartesian_to_keplerian(rv[:3], rv[3:], common.MU_POLIASTRO)
+    for got, want in zip(kep, common.KEPLER_34427):
+        assert abs(got - want) < 5e-6
+
+
+def test_upsample_bit_exact_vs_reference(eng, refnpz):
+    """util.upsample outputs of the reference's own code (torch F.interpolate): bit-equal."""
+    for tag in "abcde":
+        x, n_f = refnpz[f"upsample_{tag}_in"], int(refnpz[f"upsample_{tag}_nf"])
+        y = _np(eng.upsample(x, n_f))
+        if f"upsample_{tag}_idx" in refnpz:
+            assert np.allclose(y.sum(axis=0), refnpz[f"upsample_{tag}_sum"], rtol=1e-12)
+            y = y[refnpz[f"upsample_{tag}_idx"]]
+        assert np.array_equal(y, refnpz[f"upsample_{tag}_out"])
+    for n_in, n_out in ((50, 13), (5, 1), (3, 3), (1, 4)):
+        x = np.random.default_rng(n_in).standard_normal((n_in, 3))
+        assert np.array_equal(_np(eng.upsample(x, n_out)), C.upsample(x, n_out))
+
+
+def test_find_conjunction_vs_reference(eng, refnpz):
+    for a, b, res in zip(refnpz["fc_tr0"], refnpz["fc_tr1"], refnpz["fc_res"]):
+        oi, od = eng.find_conjunction(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), 5e3)
+        oi, od = _np(oi), _np(od)
+        assert oi[0] == int(res[0]) and oi[1] == int(res[2])
+        assert od[0] == pytest.approx(res[1], rel=1e-13)
+        if res[2] >= 0:
+            assert od[1] == pytest.approx(res[3], rel=1e-13)
+        else:
+            assert np.isnan(od[1])
+    # NaN is the minimum; strided [n,2,3] view as forward() slices it (model.py:611-612)
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((700, 2, 3)) * 1e4
+    b = a + 1e5
+    b[417, 0, 1] = np.nan
+    oi, od = eng.find_conjunction(torch.from_numpy(a).cuda()[:, 0], torch.from_numpy(b).cuda()[:, 0], 5e3)
+    assert int(oi[0]) == 417 and np.isnan(float(od[0])) and int(oi[1]) == -1
+
+
+def test_propagate_upsample_parity(eng):
+    et, ept, _, _, s = common.golden_pair()
+    times = K.time_grid(s["time0"], 7.0, 6e5)
+    c_ref, _ = C.sgp4_init(et[:, None])
+    rv_ref, _ = C.sgp4_prop(c_ref, (times[::100] - ept) * 1440.0)
+    want = C.upsample(rv_ref[0], len(times)) * 1e3
+    got, err = eng.propagate_upsample(torch.from_numpy(c_ref[:, 0].copy()), ept, times[::100], len(times))
+    got = _np(got)
+    assert int(err[0]) == 0 and got.shape == (600000, 6)
+    assert np.abs(got[:, :3] - want[:, :3]).max() < POS_SAMEC_KM * 1e3     # metres
+    assert np.abs(got[:, 3:] - want[:, 3:]).max() < 1e-9
+
+
+# ---------------------------------------------------------------------------------------
+def _golden_batch(n, seed):
+    et, ept, ec, epc, s = common.golden_pair()
+    times = K.time_grid(s["time0"], 7.0, 6e5)
+    rng = np.random.default_rng(seed)
+    elt, elc = np.repeat(et[:, None], n, 1), np.repeat(ec[:, None], n, 1)
+    for arr in (elt, elc):
+        m = np.round(rng.uniform(0, 360, n), 4) * np.pi / 180
+        m[0] = arr[5, 0]
+        arr[5] = m
+    for i in range(1, n // 3):
+        elt[5, i] = et[5] + rng.normal() * 2e-5
+        elc[5, i] = ec[5] + rng.normal() * 2e-5
+    return elt, np.full(n, ept), elc, np.full(n, epc), times, s
+
+
+def _screen(eng, elt, ept, elc, epc, tc, n_fine, thr, mode):
+    ct, it = eng.sgp4_init(elt)
+    cc, ic = eng.sgp4_init(elc)
+    r = eng.screen(ct, ept, cc, epc, tc, n_fine, thr, mode, init_err_t=it, init_err_c=ic)
+    return {k: _np(v) for k, v in r.items()}
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_screen_golden_trace_and_oracle(eng, mode):
+    """Known answer of docs/notebooks/trace.pickle + 96 seeded traces against the C oracle."""
+    elt, ept, elc, epc, times, s = _golden_batch(96, 5)
+    tc = np.ascontiguousarray(times[::100])
+    ref = C.screen(elt, ept, elc, epc, tc, len(times), 5e3)
+    r = _screen(eng, elt, ept, elc, epc, tc, len(times), 5e3, mode)
+    assert r["i_conj"][0] == s["i_conj"] == 305767 and r["i_min"][0] == 305768
+    assert times[r["i_min"][0]] == s["time_min"] and times[r["i_conj"][0]] == s["time_conj"]
+    assert abs(r["d_min"][0] - s["d_min"]) < 1e-4 and abs(r["d_conj"][0] - s["d_conj"]) < 1e-4     # metres
+    assert np.array_equal(r["i_min"], ref["i_min"])         # TCA: exact fine-grid index (<< 1e-3 s)
+    assert np.array_equal(r["i_conj"], ref["i_conj"])
+    assert np.abs(r["d_min"] - ref["d_min"]).max() < POS_TIGHT_KM * 1e3 * 4
+    both = ref["i_conj"] >= 0
+    assert both.sum() >= 20
+    assert np.abs(r["d_conj"][both] - ref["d_conj"][both]).max() < POS_TIGHT_KM * 1e3 * 4
+    assert np.isnan(r["d_conj"][~both]).all() and (r["err"] == 0).all()
+
+
+@pytest.mark.parametrize("n_coarse,n_fine", [(61, 6001), (7, 61), (2, 9), (300, 29901), (257, 25601), (256, 2551),
+                                             (511, 51001), (1, 5), (40, 13), (5, 1), (7000, 70001)])
+def test_screen_ragged_grids(eng, n_coarse, n_fine):
+    el, ep = common.population_elems()
+    rng = np.random.default_rng(n_coarse * 1000 + n_fine)
+    pairs = [(i, j) for i in range(20) for j in range(20) if i != j]
+    sel = [pairs[k] for k in rng.choice(len(pairs), 24, replace=False)]
+    elt = np.stack([el[:, i] for i, _ in sel], 1)
+    elc = np.stack([el[:, j] for _, j in sel], 1)
+    ept, epc = ep[[i for i, _ in sel]], ep[[j for _, j in sel]]
+    tc = (ep.mean() - 3.5) + np.arange(n_coarse) * (7.0 / n_coarse)
+    thr = 4.0e6
+    ref = C.screen(elt, ept, elc, epc, tc, n_fine, thr)
+    for mode in (1, 0):
+        r = _screen(eng, elt, ept, elc, epc, tc, n_fine, thr, mode)
+        assert np.array_equal(r["i_min"], ref["i_min"]), mode
+        assert np.array_equal(r["i_conj"], ref["i_conj"]), mode
+        assert np.allclose(r["d_min"], ref["d_min"], rtol=0, atol=1e-3)
+        assert np.array_equal(r["err"], ref["err"])
+
+
+def test_screen_shared_target_catalog(eng):
+    """One-vs-catalog (BASELINE config 4 shape): shared target path == per-sample target path
+    == oracle, incl. deep-space refusals, decayed / non-finite chasers and their flags."""
+    gt, ept, _, _, s = common.golden_pair()
+    n = 160
+    elc = common.synthetic_catalog(n, seed=21)
+    epc = np.full(n, ept) + np.random.default_rng(3).uniform(-2, 2, n)
+    times = K.time_grid(s["time0"], 7.0, 6e4)
+    tc = np.ascontiguousarray(times[::100])
+    ref = C.screen(gt[:, None], [ept], elc, epc, tc, len(times), 5e4)
+    shared = _screen(eng, gt[:, None], [ept], elc, epc, tc, len(times), 5e4, 0)
+    full = _screen(eng, np.repeat(gt[:, None], n, 1), np.full(n, ept), elc, epc, tc, len(times), 5e4, 0)
+    brute = _screen(eng, gt[:, None], [ept], elc, epc, tc, len(times), 5e4, 1)
+    for r in (shared, full, brute):
+        assert np.array_equal(r["err"], ref["err"])
+        assert np.array_equal(r["i_min"], ref["i_min"]) and np.array_equal(r["i_conj"], ref["i_conj"])
+        fin = np.isfinite(ref["d_min"])
+        assert np.array_equal(np.isnan(r["d_min"]), np.isnan(ref["d_min"]))
+        assert np.abs(r["d_min"][fin] - ref["d_min"][fin]).max() < 1e-3
+    assert (ref["i_min"] == -1).sum() >= 2                 # deep-space chasers -> propagation error
+    assert np.isnan(ref["d_min"][ref["i_min"] >= 0]).any()   # NaN states: first-NaN index semantics exercised
+
+
+def test_screen_degenerate_identical_objects(eng):
+    el, ep = common.population_elems()
+    tc = ep[0] + np.arange(300) * 0.001
+    for mode in (1, 0):
+        r = _screen(eng, el[:, :1], ep[:1], el[:, :1], ep[:1], tc, 29901, 5e3, mode)
+        assert r["i_min"][0] == 0 and r["d_min"][0] == 0.0 and r["i_conj"][0] == 0 and r["d_conj"][0] == 0.0
+
+
+def test_screen_analytic_equals_brute_large(eng):
+    """Size-independent property at a larger batch than the oracle can follow: the closed-form
+    search returns exactly what enumeration of all 600 000 fine points returns."""
+    elt, ept, elc, epc, times, _ = _golden_batch(3000, 77)
+    tc = np.ascontiguousarray(times[::100])
+    a = _screen(eng, elt, ept, elc, epc, tc, len(times), 5e3, 0)
+    b = _screen(eng, elt, ept, elc, epc, tc, len(times), 5e3, 1)
+    assert np.array_equal(a["i_min"], b["i_min"]) and np.array_equal(a["i_conj"], b["i_conj"])
+    assert np.array_equal(a["d_min"], b["d_min"])           # same candidates, same arithmetic: bit-equal
+    assert np.array_equal(np.isnan(a["d_conj"]), np.isnan(b["d_conj"]))
+    assert (a["i_conj"] >= 0).sum() > 500
+    # permutation invariance (samples are independent)
+    perm = np.random.default_rng(1).permutation(3000)
+    c = _screen(eng, elt[:, perm], ept, elc[:, perm], epc, tc, len(times), 5e3, 0)
+    assert np.array_equal(c["i_min"], a["i_min"][perm]) and np.array_equal(c["d_min"], a["d_min"][perm])
+
+
+def test_screen_host_and_summary(eng):
+    elt, ept, elc, epc, times, _ = _golden_batch(500, 9)
+    tc = np.ascontiguousarray(times[::100])
+    dev = _screen(eng, elt, ept, elc, epc, tc, len(times), 5e3, 0)
+    host = eng.screen_host(elt, ept, elc, epc, tc, len(times), 5e3, 0, collision_thr_m=4900.0)
+    for k in ("i_min", "i_conj", "err"):
+        assert np.array_equal(host[k], dev[k])
+    assert np.array_equal(host["d_min"], dev["d_min"])
+    cnt = host["counts"].astype(np.int64)
+    assert cnt[0] == 500 and cnt[1] == 0
+    assert cnt[2] == (dev["i_conj"] >= 0).sum() and cnt[3] == (dev["i_conj"] > 0).sum()
+    assert cnt[4] == (dev["d_min"] < 4900.0).sum() > 0 and cnt[5] == 0
+    m = host["moments"]
+    assert m[0] == 500 and m[1] == pytest.approx(dev["d_min"].sum(), rel=1e-12)
+    assert m[2] == pytest.approx((dev["d_min"] ** 2).sum(), rel=1e-12) and m[3] == dev["d_min"].min()
+
+
+# ---------------------------------------------------------------------------------------
+def test_tca_moments_parity(eng):
+    """model.py:523-550 on the default mc_samples = 100 and on 20 000 samples."""
+    gt, ept, _, _, s = common.golden_pair()
+    tsince = (s["time_min"] - ept) * 1440.0
+    for n, seed in ((100, 1), (20000, 2)):
+        el = common.perturbed_samples(gt, n, seed)
+        st_ref, e_ref = C.tca_states(el, tsince)
+        mean_ref, cov_ref = C.mc_cov(st_ref)
+        ref_state = st_ref[0]
+        mom, errc, states = eng.tca_moments(el, tsince, ref_state, want_states=True)
+        mom, states = _np(mom), _np(states)
+        assert int(errc[0]) == 0 and mom[0] == n
+        assert np.abs(states[:, :3] - st_ref[:, :3]).max() < POS_TIGHT_KM * 1e3
+        assert np.abs(states[:, 3:] - st_ref[:, 3:]).max() < 1e-7
+        from kessler_b200.stats import moments_to_mean_cov_rtn
+        mean, cov = moments_to_mean_cov_rtn(mom, ref_state)
+        assert np.allclose(mean, mean_ref, rtol=0, atol=1e-4)
+        scale = np.sqrt(np.outer(np.diag(cov_ref), np.diag(cov_ref)))
+        assert np.abs(cov - cov_ref).max() / scale.max() < 1e-6
+        assert np.allclose(cov, cov_ref, rtol=1e-5, atol=1e-9 * scale.max())
+
+
+def test_pc_count_bit_exact(eng):
+    """model.py:432-437 at the reference size (10^4 x 10^4) and ragged sizes: integer-exact."""
+    rng = np.random.default_rng(4)
+    for nt, nc in ((10000, 10000), (1, 1), (257, 1023), (1025, 3), (5000, 1)):
+        t = rng.standard_normal((3, nt)) * np.array([[40.0], [900.0], [30.0]])
+        c = rng.standard_normal((3, nc)) * np.array([[60.0], [1200.0], [45.0]]) + np.array([[50.0], [0.0], [0.0]])
+        want = C.pc_count(t, c, 70.0, 0)
+        got = int(eng.pc_count(t, c, 70.0)[0])
+        assert got == want, (nt, nc)
+    assert want >= 0
+    t = rng.standard_normal((3, 100000)) * 60.0
+    c = rng.standard_normal((3, 100000)) * 60.0
+    assert int(eng.pc_count(t, c, 70.0, pairing=1)[0]) == C.pc_count(t, c, 70.0, 1) > 0
+    # boundary pairs: distances that differ from the threshold in the last bits
+    t = np.zeros((3, 64))
+    c = np.zeros((3, 64))
+    c[0] = 70.0 * (1.0 + (np.arange(64) - 32) * 2.2e-16)
+    assert int(eng.pc_count(t, c, 70.0, pairing=1)[0]) == C.pc_count(t, c, 70.0, 1)
+    # row shards accumulate into the same counter (multi-GPU decomposition, single device here)
+    t = rng.standard_normal((3, 4000)) * 50.0
+    c = rng.standard_normal((3, 3000)) * 50.0
+    cnt = None
+    for lo in range(0, 4000, 1000):
+        cnt = eng.pc_count(np.ascontiguousarray(t[:, lo:lo + 1000]), c, 70.0, count=cnt)
+    assert int(cnt[0]) == C.pc_count(t, c, 70.0, 0)
+
+
+def test_fp64_peak_probe_runs(eng):
+    tf = eng.fp64_peak_tflops(iters=4000, reps=2)
+    assert 5.0 < tf < 80.0
+    assert eng.launch_count() > 0

@@ -1,0 +1,178 @@
+"""CPU check of the DEVICE code's algebra: kessler_b200/csrc/{sgp4,screen}_device.cuh are
+__host__ __device__, so tests/hostcheck/hostcheck.cpp compiles them with g++ and the
+restructured SGP4 (4 sincos + small-angle rotations instead of 16 trig calls + atan2) and
+the closed-form segment search are compared with the oracle here, without a GPU.  The GPU
+tests (-m gpu) repeat the comparison through the C ABI on the real kernels."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import common
+from oracle import c_oracle as C
+from oracle import kessler_path as K
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+D = ctypes.POINTER(ctypes.c_double)
+I32 = ctypes.POINTER(ctypes.c_int32)
+I64 = ctypes.POINTER(ctypes.c_int64)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+@pytest.fixture(scope="module")
+def hc(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("hostcheck") / "libhostcheck.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=off", "-x", "c++",
+                           os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp"), "-o", so])
+    return ctypes.CDLL(so)
+
+
+def hc_init(hc, el):
+    el = np.ascontiguousarray(el)
+    n = el.shape[1]
+    c = np.zeros((36, n))
+    e = np.zeros(n, np.int32)
+    hc.hc_sgp4_init(_p(el, D), ctypes.c_int64(n), _p(c, D), _p(e, I32))
+    return c, e
+
+
+def hc_prop(hc, c, ts, vel=1):
+    c, ts = np.ascontiguousarray(c), np.ascontiguousarray(ts)
+    n, m = c.shape[1], ts.shape[-1]
+    rv = np.zeros((n, m, 6))
+    e = np.zeros(n, np.int32)
+    hc.hc_sgp4_prop(_p(c, D), ctypes.c_int64(n), _p(ts, D), ctypes.c_int64(m), 0, vel, _p(rv, D), _p(e, I32))
+    return rv, e
+
+
+def hc_screen(hc, ct, ept, cc, epc, tc, n_fine, thr, mode):
+    ct, cc, tc = np.ascontiguousarray(ct), np.ascontiguousarray(cc), np.ascontiguousarray(tc)
+    ept, epc = np.ascontiguousarray(ept, dtype=np.float64), np.ascontiguousarray(epc, dtype=np.float64)
+    n_t, n = ct.shape[1], cc.shape[1]
+    out = dict(i_min=np.zeros(n, np.int64), d_min=np.zeros(n), i_conj=np.zeros(n, np.int64), d_conj=np.zeros(n),
+               err=np.zeros(n, np.int32))
+    hc.hc_screen(_p(ct, D), _p(ept, D), ctypes.c_int64(n_t), _p(cc, D), _p(epc, D), ctypes.c_int64(n), _p(tc, D),
+                 ctypes.c_int64(len(tc)), ctypes.c_int64(n_fine), ctypes.c_double(thr), mode,
+                 _p(out["i_min"], I64), _p(out["d_min"], D), _p(out["i_conj"], I64), _p(out["d_conj"], D), _p(out["err"], I32))
+    return out
+
+
+def test_device_sgp4init_matches_oracle(hc):
+    el, _ = common.population_elems()
+    el = np.concatenate([el, common.synthetic_catalog(300)], axis=1)
+    c1, e1 = C.sgp4_init(el)
+    c2, e2 = hc_init(hc, el)
+    assert (e1 == e2).all()
+    ok = e1 == 0
+    assert np.allclose(c1[:, ok], c2[:, ok], rtol=2e-13, atol=0)
+
+
+def test_device_sgp4_matches_oracle(hc):
+    el, _ = common.population_elems()
+    el = np.concatenate([el, common.synthetic_catalog(300)], axis=1)
+    c1, e1 = C.sgp4_init(el)
+    ts = np.linspace(-5.0e4, 5.0e4, 401)
+    rv1, ea = C.sgp4_prop(c1, ts)
+    rv2, eb = hc_prop(hc, c1, ts)          # same constants: isolates the propagation algebra
+    good = (e1 == 0) & (ea == 0)
+    assert (ea == eb)[e1 == 0].all()
+    assert good.sum() > 200
+    assert np.abs(rv1[good][..., :3] - rv2[good][..., :3]).max() < 1e-9     # km  (tolerance of record: 1e-6 km)
+    assert np.abs(rv1[good][..., 3:] - rv2[good][..., 3:]).max() < 1e-12    # km/s
+    rv3, _ = hc_prop(hc, c1, ts, vel=0)
+    assert np.array_equal(rv3[..., :3][good], rv2[..., :3][good])           # position-only path is the same arithmetic
+    # bad-physics lanes: same non-finite pattern
+    bad = (e1 == 0) & (ea != 0)
+    assert np.array_equal(np.isnan(rv1[bad][..., :3]), np.isnan(rv2[bad][..., :3]))
+
+
+def test_device_wrap_is_python_mod(hc):
+    hc.hc_wrap_twopi.restype = ctypes.c_double
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(-4e3, 4e3, 20000), [0.0, -0.0, 2 * np.pi, -2 * np.pi, 6.283185307179586 * 7, 1e-300, -1e-300]])
+    for x in xs:
+        assert hc.hc_wrap_twopi(ctypes.c_double(x)) == float(np.mod(x, 2 * np.pi)), x
+
+
+def _golden_batch(n, seed):
+    et, ept, ec, epc, s = common.golden_pair()
+    times = K.time_grid(s["time0"], 7.0, 6e5)
+    rng = np.random.default_rng(seed)
+    elt, elc = np.repeat(et[:, None], n, 1), np.repeat(ec[:, None], n, 1)
+    for arr in (elt, elc):
+        m = np.round(rng.uniform(0, 360, n), 4) * np.pi / 180     # TLE-text quantised mean anomalies (model.py:269,308)
+        m[0] = arr[5, 0]
+        arr[5] = m
+    for i in range(1, n // 3):                                     # near-golden: conjunctions persist
+        elt[5, i] = et[5] + rng.normal() * 2e-5
+        elc[5, i] = ec[5] + rng.normal() * 2e-5
+    return elt, np.full(n, ept), elc, np.full(n, epc), times, s
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_device_screen_matches_oracle_default_grid(hc, mode):
+    elt, ept, elc, epc, times, s = _golden_batch(24, 5)
+    tc = np.ascontiguousarray(times[::100])
+    ref = C.screen(elt, ept, elc, epc, tc, len(times), 5e3)
+    ct, _ = C.sgp4_init(elt)
+    cc, _ = C.sgp4_init(elc)
+    r = hc_screen(hc, ct, ept, cc, epc, tc, len(times), 5e3, mode)
+    assert r["i_min"][0] == 305768 and r["i_conj"][0] == s["i_conj"]
+    assert np.array_equal(r["i_min"], ref["i_min"]) and np.array_equal(r["i_conj"], ref["i_conj"])
+    assert np.nanmax(np.abs(r["d_min"] - ref["d_min"])) < 1e-6                  # metres
+    both = ref["i_conj"] >= 0
+    assert both.sum() >= 5
+    assert np.abs(r["d_conj"][both] - ref["d_conj"][both]).max() < 1e-6
+    assert np.isnan(r["d_conj"][~both]).all()
+
+
+@pytest.mark.parametrize("n_coarse,n_fine", [(61, 6001), (7, 61), (2, 9), (300, 29901), (257, 25601), (256, 2551), (1, 5), (40, 13), (5, 1)])
+def test_device_screen_ragged_grids(hc, n_coarse, n_fine):
+    """Analytic == brute == oracle on odd grid shapes (chunk boundaries at 255/256 epochs,
+    single epoch, down-sampling, single output)."""
+    el, ep = common.population_elems()
+    rng = np.random.default_rng(n_coarse * 1000 + n_fine)
+    pairs = [(i, j) for i in range(20) for j in range(20) if i != j]
+    sel = [pairs[k] for k in rng.choice(len(pairs), 12, replace=False)]
+    elt = np.stack([el[:, i] for i, _ in sel], 1)
+    elc = np.stack([el[:, j] for _, j in sel], 1)
+    ept, epc = ep[[i for i, _ in sel]], ep[[j for _, j in sel]]
+    t0 = ep.mean() - 3.5
+    tc = t0 + np.arange(n_coarse) * (7.0 / max(n_coarse, 1))
+    thr = 4.0e6                                     # large threshold so that crossings exist on these random pairs
+    ref = C.screen(elt, ept, elc, epc, tc, n_fine, thr)
+    ct, _ = C.sgp4_init(elt)
+    cc, _ = C.sgp4_init(elc)
+    for mode in (1, 0):
+        r = hc_screen(hc, ct, ept, cc, epc, tc, n_fine, thr, mode)
+        assert np.array_equal(r["i_min"], ref["i_min"]), mode
+        assert np.array_equal(r["i_conj"], ref["i_conj"]), mode
+        assert np.allclose(r["d_min"], ref["d_min"], rtol=0, atol=1e-5)
+
+
+def test_device_screen_degenerate_and_nan(hc):
+    """Identical objects (d == 0 everywhere -> first index), and NaN states (torch.argmin
+    returns the first NaN index; NaN < thr is False)."""
+    el, ep = common.population_elems()
+    n_coarse, n_fine = 300, 29901
+    tc = ep[0] + np.arange(n_coarse) * 0.001
+    same_t, same_c = el[:, :1].copy(), el[:, :1].copy()
+    bad = common.synthetic_catalog(16)[:, [5, 9]]       # lanes that go non-finite (see tests/common.py)
+    elt = np.concatenate([same_t, el[:, 1:3]], 1)
+    elc = np.concatenate([same_c, bad], 1)
+    ept = np.array([ep[0], ep[1], ep[2]])
+    epc = np.array([ep[0], ep[1] + 30.0, ep[2] + 30.0])
+    ref = C.screen(elt, ept, elc, epc, tc, n_fine, 5e3)
+    ct, _ = C.sgp4_init(elt)
+    cc, _ = C.sgp4_init(elc)
+    assert ref["i_min"][0] == 0 and ref["d_min"][0] == 0.0 and ref["i_conj"][0] == 0
+    assert np.isnan(ref["d_min"][1:]).any()
+    for mode in (1, 0):
+        r = hc_screen(hc, ct, ept, cc, epc, tc, n_fine, 5e3, mode)
+        assert np.array_equal(r["i_min"], ref["i_min"]) and np.array_equal(r["i_conj"], ref["i_conj"])
+        assert np.array_equal(np.isnan(r["d_min"]), np.isnan(ref["d_min"]))
