@@ -213,6 +213,15 @@ class TLE:
         l1 = l1[:68].ljust(68)
         l2 = l2[:68].ljust(68)
         self._from_lines(l1 + str(_checksum(l1)), l2 + str(_checksum(l2)), name)
+        # dsgp4 keeps the caller's values in the public fields and derives only the SGP4 inputs
+        # (_mo, _no_kozai, ...) from the text: after update({'mean_anomaly': 0.4932476473698829}) the
+        # pickled golden TLE has mean_anomaly = that sample but _mo = 0.49324749990611744 (28.2610 deg)
+        for k, v in d.items():
+            if k in self._data and k not in ("epoch_year", "epoch_days"):
+                self._data[k] = v
+                setattr(self, k, v)
+        if float(d["mean_motion"]) > 0:
+            self.semi_major_axis = (MU_EARTH / float(d["mean_motion"]) ** 2) ** (1.0 / 3.0)
 
     def _set(self, d, line1, line2, name):
         self._data = d
