@@ -37,11 +37,11 @@ def test_dsgp4_surface(kb, golden):
     for name in ("_cc1", "_cc4", "_mdot", "_no_unkozai", "_t5cof", "_xlcof", "_nodedot", "_delmo"):
         assert getattr(t_tle, name) == pytest.approx(g[name], rel=1e-13)
     assert t_tle._isimp == g["_isimp"]
-    st = sgp4.propagate(t_tle, torch.tensor(g["_t"]))
+    st = sgp4.propagate(t_tle, torch.tensor(g["_t"], dtype=torch.float64))
     assert st.shape == (2, 3)
     el, batch = sgp4.initialize_tle([t_tle, c_tle])
     assert el.shape == (2, 7) and len(batch) == 2
-    rv = sgp4.propagate_batch(batch, torch.tensor([g["_t"], 10.0]))
+    rv = sgp4.propagate_batch(batch, torch.tensor([g["_t"], 10.0], dtype=torch.float64))
     assert rv.shape == (2, 2, 3) and np.allclose(rv[0].numpy(), st.numpy(), rtol=0, atol=1e-9)
     c_ref, _ = C.sgp4_init(t_tle.elements()[:, None])
     rv_ref, _ = C.sgp4_prop(c_ref, np.array([g["_t"]]))
