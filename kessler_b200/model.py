@@ -449,7 +449,7 @@ class Conjunction:
         time_to_tca = util.from_date_str_to_days(cdm0['TCA'], date0=cdm0['CREATION_DATE'])
         vals['cdm0_time_to_tca'] = (time_to_tca, self._likelihood_time_to_tca_stddev)
         for k, (v, _) in vals.items():
-            ppl.deterministic(k, torch.as_tensor(v))
+            ppl.deterministic(k, torch.as_tensor(v, dtype=torch.float64))
         for k, (v, s) in vals.items():
             ppl.sample('obs_' + k, Normal(torch.as_tensor(v, dtype=torch.float64), s), obs=v)
 

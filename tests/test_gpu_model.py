@@ -163,7 +163,8 @@ def test_mc_covariance_against_oracle(kb, golden):
     # same draws through the oracle
     torch.manual_seed(11)
     Cov = model.tle_covariance(state_m, cov_diag)
-    mu = torch.tensor([float(obs_tle.semi_major_axis), obs_tle._ecco, obs_tle._inclo, obs_tle._nodeo, obs_tle._argpo, obs_tle._mo])
+    mu = torch.tensor([float(obs_tle.semi_major_axis), obs_tle._ecco, obs_tle._inclo, obs_tle._nodeo, obs_tle._argpo, obs_tle._mo],
+                      dtype=torch.float64)
     smp = torch.distributions.MultivariateNormal(loc=mu, covariance_matrix=torch.tensor(Cov)).sample((100,)).numpy()
     el = M.quantize_sgp4_inputs((398600.5e9 / smp[:, 0] ** 3) ** 0.5, np.maximum(smp[:, 1], 0.0), smp[:, 2], smp[:, 3], smp[:, 4],
                                 smp[:, 5], np.full(100, obs_tle.b_star))
