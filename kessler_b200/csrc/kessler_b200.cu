@@ -292,13 +292,13 @@ __global__ void __launch_bounds__(kScreenThreads, 2) k_screen(const ScreenParams
             const long long k = base + tid;
             if (k <= last) {
                 const double tm = grid_in_smem ? s_times[k] : p.times_coarse[k];
-                double r[3], v[3];
-                e_c |= ksl::sgp4_prop<false>([&](int q) { return s_cc[q]; }, (tm - epoch_c) * 1440.0, r, v);
+                double r[3];
+                e_c |= ksl::sgp4_position([&](int q) { return s_cc[q]; }, (tm - epoch_c) * 1440.0, r);
                 s_pc[tid][0] = r[0]; s_pc[tid][1] = r[1]; s_pc[tid][2] = r[2];
                 if (kSharedTarget) {
                     r[0] = p.target_pos[3 * k]; r[1] = p.target_pos[3 * k + 1]; r[2] = p.target_pos[3 * k + 2];
                 } else {
-                    e_t |= ksl::sgp4_prop<false>([&](int q) { return s_ct[q]; }, (tm - epoch_t) * 1440.0, r, v);
+                    e_t |= ksl::sgp4_position([&](int q) { return s_ct[q]; }, (tm - epoch_t) * 1440.0, r);
                 }
                 s_pt[tid][0] = r[0]; s_pt[tid][1] = r[1]; s_pt[tid][2] = r[2];
             }
@@ -339,8 +339,8 @@ __global__ void __launch_bounds__(128) k_target_positions(const double *__restri
                                                           long long n_coarse, double *__restrict__ pos, int *__restrict__ err) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_coarse) return;
-    double r[3], v[3];
-    const int e = ksl::sgp4_prop<false>([&](int q) { return __ldg(consts + q); }, (times[k] - epoch[0]) * 1440.0, r, v);
+    double r[3];
+    const int e = ksl::sgp4_position([&](int q) { return __ldg(consts + q); }, (times[k] - epoch[0]) * 1440.0, r);
     pos[3 * k] = r[0]; pos[3 * k + 1] = r[1]; pos[3 * k + 2] = r[2];
     if (e) atomicOr(err, e);
 }

@@ -35,6 +35,23 @@ int hc_sgp4_prop(const double *consts, int64_t n, const double *tsince, int64_t 
     return 0;
 }
 
+// position through the fast path; fast_used[i*m + j] = 1 when the branch-free path accepted the epoch
+int hc_sgp4_position(const double *consts, int64_t n, const double *tsince, int64_t m, double *pos, int32_t *err,
+                     int32_t *fast_used) {
+    for (int64_t i = 0; i < n; ++i) {
+        auto ld = [&](int k) { return consts[(int64_t)k * n + i]; };
+        int e = 0;
+        for (int64_t j = 0; j < m; ++j) {
+            double *o = pos + (i * m + j) * 3;
+            double tmp[3];
+            fast_used[i * m + j] = ksl::sgp4_prop_fast(ld, tsince[j], tmp) ? 1 : 0;
+            e |= ksl::sgp4_position(ld, tsince[j], o);
+        }
+        err[i] |= e;
+    }
+    return 0;
+}
+
 int hc_upsample_index(int64_t j, int64_t n_in, int64_t n_out, int64_t *i0, int64_t *i1, double *w0, double *w1) {
     double scale = n_out > 1 ? (double)(n_in - 1) / (double)(n_out - 1) : 0.0;
     ksl::upsample_index(j, scale, n_in, i0, i1, w0, w1);
@@ -60,9 +77,8 @@ int hc_screen(const double *consts_t, const double *epoch_t, int64_t n_t, const 
         auto ldt = [&](int q) { return consts_t[(int64_t)q * n_t + it]; };
         auto ldc = [&](int q) { return consts_c[(int64_t)q * n + s]; };
         for (int64_t k = 0; k < n_coarse; ++k) {
-            double v[3];
-            et |= ksl::sgp4_prop<false>(ldt, (times_coarse[k] - epoch_t[it]) * 1440.0, &pt[3 * k], v);
-            ec |= ksl::sgp4_prop<false>(ldc, (times_coarse[k] - epoch_c[s]) * 1440.0, &pc[3 * k], v);
+            et |= ksl::sgp4_position(ldt, (times_coarse[k] - epoch_t[it]) * 1440.0, &pt[3 * k]);
+            ec |= ksl::sgp4_position(ldc, (times_coarse[k] - epoch_c[s]) * 1440.0, &pc[3 * k]);
         }
         std::vector<ksl::Best> best(kThreads);
         for (auto &b : best) ksl::best_init(b);
