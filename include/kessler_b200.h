@@ -68,6 +68,9 @@ enum ksl_elem_index { KSL_E_NO_KOZAI = 0, KSL_E_ECCO, KSL_E_INCLO, KSL_E_NODEO, 
 /* ksl_screen `mode` */
 #define KSL_SCREEN_ANALYTIC 0 /* per-coarse-segment closed form + exact re-evaluation of the candidates */
 #define KSL_SCREEN_BRUTE 1    /* every fine-grid point, as the reference does */
+/* OR-ed into `mode` (testing / tuning): pin the work decomposition instead of choosing by batch size */
+#define KSL_SCREEN_FORCE_CTA 16  /* one CTA per trace  (small batches) */
+#define KSL_SCREEN_FORCE_WARP 32 /* one warp per trace (large batches) */
 
 /* ksl_pc_count `pairing` */
 #define KSL_PAIR_ALL 0

@@ -12,7 +12,7 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "lib", "libkessler_b200.so")
+LIB_PATH = os.environ.get("KSL_LIB_PATH") or os.path.join(_PKG, "lib", "libkessler_b200.so")   # env override: tuning experiments only
 SRC = os.path.join(_PKG, "csrc", "kessler_b200.cu")
 HEADERS = [os.path.join(_PKG, "csrc", "sgp4_device.cuh"), os.path.join(_PKG, "csrc", "screen_device.cuh"),
            os.path.join(_ROOT, "include", "kessler_b200.h")]
@@ -23,6 +23,8 @@ SUM_NCOUNT = 8
 SUM_NMOMENT = 4
 SCREEN_ANALYTIC = 0
 SCREEN_BRUTE = 1
+SCREEN_FORCE_CTA = 16
+SCREEN_FORCE_WARP = 32
 PAIR_ALL = 0
 PAIR_ELEMENTWISE = 1
 ERR_ECC, ERR_MEANMOTION, ERR_SEMILATUS, ERR_DECAYED, ERR_DEEPSPACE = 1, 2, 4, 8, 16

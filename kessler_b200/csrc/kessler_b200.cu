@@ -225,7 +225,16 @@ __global__ void __launch_bounds__(256) k_findconj_final(const Best *__restrict__
 // non-finite or ill-conditioned.  Segments whose analytic minimum cannot beat the
 // thread's running best (nor the threshold) are skipped.
 // ------------------------------------------------------------------------------------
-constexpr int kScreenThreads = 256;
+#ifndef KSL_SCREEN_THREADS
+#define KSL_SCREEN_THREADS 256
+#endif
+#ifndef KSL_SCREEN_MIN_CTAS
+#define KSL_SCREEN_MIN_CTAS 2
+#endif
+#ifndef KSL_SCREEN_GRID_SMEM
+#define KSL_SCREEN_GRID_SMEM 1   // stage the time grid in shared memory (north star); 0 = read it through L1
+#endif
+constexpr int kScreenThreads = KSL_SCREEN_THREADS;
 constexpr int kMaxGridInSmem = 6144;  // time grid staged in shared memory up to this many epochs
 
 struct ScreenParams {
@@ -246,7 +255,7 @@ struct ScreenParams {
 };
 
 template <bool kSharedTarget, int kMode>
-__global__ void __launch_bounds__(kScreenThreads, 2) k_screen(const ScreenParams p) {
+__global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen(const ScreenParams p) {
     extern __shared__ double s_times[];  // [min(n_coarse, kMaxGridInSmem)]
     __shared__ double s_ct[KSL_NCONST], s_cc[KSL_NCONST];
     __shared__ double s_pt[kScreenThreads][3], s_pc[kScreenThreads][3];
@@ -255,7 +264,7 @@ __global__ void __launch_bounds__(kScreenThreads, 2) k_screen(const ScreenParams
     __shared__ int s_flags[2];
 
     const int tid = threadIdx.x;
-    const bool grid_in_smem = p.n_coarse <= kMaxGridInSmem;
+    const bool grid_in_smem = KSL_SCREEN_GRID_SMEM && p.n_coarse <= kMaxGridInSmem;
     if (grid_in_smem)
         for (long long k = tid; k < p.n_coarse; k += kScreenThreads) s_times[k] = p.times_coarse[k];
 
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(kScreenThreads, 2) k_screen(const ScreenParams
         const long long it = (p.n_t == 1) ? 0 : s;
         if (tid < KSL_NCONST) s_cc[tid] = p.consts_c[(long long)tid * p.n + s];
         if (!kSharedTarget && tid >= 64 && tid < 64 + KSL_NCONST) s_ct[tid - 64] = p.consts_t[(long long)(tid - 64) * p.n_t + it];
-        if (tid == 128) {
+        if (tid == kScreenThreads - 1) {
             s_epoch[0] = p.epoch_t[it];
             s_epoch[1] = p.epoch_c[s];
             s_flags[0] = p.init_err_t ? p.init_err_t[it] : 0;
@@ -293,12 +302,12 @@ __global__ void __launch_bounds__(kScreenThreads, 2) k_screen(const ScreenParams
             if (k <= last) {
                 const double tm = grid_in_smem ? s_times[k] : p.times_coarse[k];
                 double r[3];
-                e_c |= ksl::sgp4_position([&](int q) { return s_cc[q]; }, (tm - epoch_c) * 1440.0, r);
+                e_c |= ksl::sgp4_position(s_cc, 1, (tm - epoch_c) * 1440.0, r);
                 s_pc[tid][0] = r[0]; s_pc[tid][1] = r[1]; s_pc[tid][2] = r[2];
                 if (kSharedTarget) {
                     r[0] = p.target_pos[3 * k]; r[1] = p.target_pos[3 * k + 1]; r[2] = p.target_pos[3 * k + 2];
                 } else {
-                    e_t |= ksl::sgp4_position([&](int q) { return s_ct[q]; }, (tm - epoch_t) * 1440.0, r);
+                    e_t |= ksl::sgp4_position(s_ct, 1, (tm - epoch_t) * 1440.0, r);
                 }
                 s_pt[tid][0] = r[0]; s_pt[tid][1] = r[1]; s_pt[tid][2] = r[2];
             }
@@ -333,6 +342,101 @@ __global__ void __launch_bounds__(kScreenThreads, 2) k_screen(const ScreenParams
     }
 }
 
+// ------------------------------------------------------------------------------------
+// K3w  the fused trace, one WARP per sample.  Same work decomposition as k_screen (lane <->
+// coarse epoch, lane i owns segment [k, k+1]) but nothing is shared between warps after the
+// prologue: the neighbour's positions come from warp shuffles, the per-trace constants sit in a
+// per-warp slice of shared memory, and the only block-wide barrier is the one after the time
+// grid is staged.  Warps therefore drift apart and the FP64 pipe sees a mix of the FP64-dense
+// and the integer/selection phases of different warps instead of CTA-wide lock-step phases
+// (ncu, round 1: FP64 pipe 57 % active with `wait` + `barrier` on top).  Cost: one of every 32
+// epochs is evaluated twice (the chunk overlap).  Used when there are enough samples to fill
+// the machine with warps; k_screen (CTA per trace) serves small batches.
+// ------------------------------------------------------------------------------------
+constexpr int kWarpsPerCta = kScreenThreads / 32;
+
+__device__ __forceinline__ double shfl_down_d(double v, int delta) { return __shfl_down_sync(0xffffffffu, v, delta); }
+
+template <bool kSharedTarget, int kMode>
+__global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_warp(const ScreenParams p) {
+    extern __shared__ double s_times[];
+    __shared__ double s_c[kWarpsPerCta][2][KSL_NCONST];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool grid_in_smem = KSL_SCREEN_GRID_SMEM && p.n_coarse <= kMaxGridInSmem;
+    if (grid_in_smem)
+        for (long long k = tid; k < p.n_coarse; k += kScreenThreads) s_times[k] = p.times_coarse[k];
+    __syncthreads();
+
+    double *s_ct = s_c[warp][0], *s_cc = s_c[warp][1];
+    const long long warps_total = (long long)gridDim.x * kWarpsPerCta;
+    const long long last = p.n_coarse - 1;
+    for (long long s = (long long)blockIdx.x * kWarpsPerCta + warp; s < p.n; s += warps_total) {
+        const long long it = (p.n_t == 1) ? 0 : s;
+        __syncwarp();
+        for (int q = lane; q < KSL_NCONST; q += 32) {
+            s_cc[q] = p.consts_c[(long long)q * p.n + s];
+            if (!kSharedTarget) s_ct[q] = p.consts_t[(long long)q * p.n_t + it];
+        }
+        const double epoch_t = p.epoch_t[it], epoch_c = p.epoch_c[s];
+        const int ierr_t = p.init_err_t ? p.init_err_t[it] : 0, ierr_c = p.init_err_c ? p.init_err_c[s] : 0;
+        __syncwarp();
+        if ((ierr_t | ierr_c) & KSL_ERR_DEEPSPACE) {
+            if (lane == 0) {
+                p.i_min[s] = -1;
+                p.d_min[s] = NAN;
+                p.i_conj[s] = -1;
+                p.d_conj[s] = NAN;
+                p.err[s] = ierr_t | (ierr_c << KSL_ERR_CHASER_SHIFT);
+            }
+            continue;
+        }
+        Best best;
+        best_init(best);
+        int e_t = 0, e_c = 0;
+        for (long long base = 0; base < last || base == 0; base += 31) {
+            const long long k = base + lane;
+            double rt[3] = {0.0, 0.0, 0.0}, rc[3] = {0.0, 0.0, 0.0};
+            if (k <= last) {
+                const double tm = grid_in_smem ? s_times[k] : __ldg(p.times_coarse + k);
+                e_c |= ksl::sgp4_position(s_cc, 1, (tm - epoch_c) * 1440.0, rc);
+                if (kSharedTarget) {
+                    rt[0] = __ldg(p.target_pos + 3 * k); rt[1] = __ldg(p.target_pos + 3 * k + 1); rt[2] = __ldg(p.target_pos + 3 * k + 2);
+                } else {
+                    e_t |= ksl::sgp4_position(s_ct, 1, (tm - epoch_t) * 1440.0, rt);
+                }
+            }
+            double t1[3], c1[3];
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                t1[x] = shfl_down_d(rt[x], 1);
+                c1[x] = shfl_down_d(rc[x], 1);
+            }
+            const bool owner = (k < last && lane < 31) || (k == last);
+            if (owner) {
+                if (k == last) {
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) { t1[x] = rt[x]; c1[x] = rc[x]; }
+                }
+                ksl::segment_search<kMode>(k, last, p.scale, p.n_coarse, p.n_fine, p.thr2, rt, t1, rc, c1, best);
+            }
+        }
+        e_t = __reduce_or_sync(0xffffffffu, e_t);
+        e_c = __reduce_or_sync(0xffffffffu, e_c);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            Best o = best_shfl_down(best, d);
+            best_merge(best, o);
+        }
+        if (lane == 0) {
+            ksl::best_result(best, p.i_min + s, p.d_min + s, p.i_conj + s, p.d_conj + s);
+            int et = e_t | ierr_t;
+            if (kSharedTarget && p.target_err) et |= *p.target_err;
+            p.err[s] = et | ((e_c | ierr_c) << KSL_ERR_CHASER_SHIFT);
+        }
+    }
+}
+
 // target positions for the shared-target case: thread per coarse epoch
 __global__ void __launch_bounds__(128) k_target_positions(const double *__restrict__ consts,
                                                           const double *__restrict__ epoch, const double *__restrict__ times,
@@ -340,7 +444,7 @@ __global__ void __launch_bounds__(128) k_target_positions(const double *__restri
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_coarse) return;
     double r[3];
-    const int e = ksl::sgp4_position([&](int q) { return __ldg(consts + q); }, (times[k] - epoch[0]) * 1440.0, r);
+    const int e = ksl::sgp4_position(consts, 1, (times[k] - epoch[0]) * 1440.0, r);
     pos[3 * k] = r[0]; pos[3 * k + 1] = r[1]; pos[3 * k + 2] = r[2];
     if (e) atomicOr(err, e);
 }
@@ -664,6 +768,8 @@ int ksl_screen(const double *consts_t, const double *epoch_t, const int32_t *ini
                double *d_min, int64_t *i_conj, double *d_conj, int32_t *err, void *workspace, void *stream) {
     if (n < 0 || n_coarse <= 0 || n_fine <= 0 || (n_t != 1 && n_t != n))
         return fail(KSL_E_ARG, "ksl_screen: need n >= 0, n_coarse > 0, n_fine > 0, n_t in {1, n}");
+    const int force = mode & (KSL_SCREEN_FORCE_CTA | KSL_SCREEN_FORCE_WARP);
+    mode &= ~(KSL_SCREEN_FORCE_CTA | KSL_SCREEN_FORCE_WARP);
     if (mode != KSL_SCREEN_ANALYTIC && mode != KSL_SCREEN_BRUTE) return fail(KSL_E_ARG, "ksl_screen: unknown mode %d", mode);
     if (n == 0) return KSL_OK;
     if (!consts_t || !epoch_t || !consts_c || !epoch_c || !times_coarse || !i_min || !d_min || !i_conj || !d_conj || !err)
@@ -692,13 +798,21 @@ int ksl_screen(const double *consts_t, const double *epoch_t, const int32_t *ini
         p.target_pos = pos;
         p.target_err = terr;
     }
-    long long grid = (long long)sms * 2;
-    if (grid > n) grid = n;
-    const size_t dyn = (n_coarse <= kMaxGridInSmem) ? sizeof(double) * (size_t)n_coarse : 0;
+    const size_t dyn = (KSL_SCREEN_GRID_SMEM && n_coarse <= kMaxGridInSmem) ? sizeof(double) * (size_t)n_coarse : 0;
+    // enough samples to give every resident warp its own trace -> warp-per-trace kernel, else CTA-per-trace
+    const bool per_warp = (force & KSL_SCREEN_FORCE_WARP) ||
+                          (!(force & KSL_SCREEN_FORCE_CTA) && n >= (long long)sms * KSL_SCREEN_MIN_CTAS * kWarpsPerCta);
+    long long grid = (long long)sms * KSL_SCREEN_MIN_CTAS;
+    if (!per_warp && grid > n) grid = n;
 #define KSL_SCREEN_LAUNCH(SH, MD)                                                                       \
     do {                                                                                                \
-        KSL_CUDA(cudaFuncSetAttribute(k_screen<SH, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-        k_screen<SH, MD><<<(unsigned)grid, kScreenThreads, dyn, S(stream)>>>(p);                        \
+        if (per_warp) {                                                                                 \
+            KSL_CUDA(cudaFuncSetAttribute(k_screen_warp<SH, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+            k_screen_warp<SH, MD><<<(unsigned)grid, kScreenThreads, dyn, S(stream)>>>(p);               \
+        } else {                                                                                        \
+            KSL_CUDA(cudaFuncSetAttribute(k_screen<SH, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+            k_screen<SH, MD><<<(unsigned)grid, kScreenThreads, dyn, S(stream)>>>(p);                    \
+        }                                                                                               \
     } while (0)
     if (shared) {
         if (mode == KSL_SCREEN_ANALYTIC) KSL_SCREEN_LAUNCH(true, KSL_SCREEN_ANALYTIC);

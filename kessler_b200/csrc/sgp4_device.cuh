@@ -23,6 +23,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/kessler_b200.h"
 
@@ -374,17 +375,76 @@ KSL_HD int sgp4_prop(Load &&c, double t, double r[3], double v[3]) {
 //   * sqrt(1 - el2) from its series (el2 = e^2 <~ 1e-2);
 //   * polynomial coefficients live in constant memory.
 // Position only (the closest-approach search never reads the velocity).
-#if defined(__CUDA_ARCH__)
-#define KSL_TABLE __constant__ const double
+// Tables are deliberately NOT const on the device: ptxas folds const initialisers into 64-bit
+// immediates that cost two UMOV issue slots per use; a mutable __constant__ array is read with
+// uniform LDCU loads (one slot per 64 or 128 bits) that the compiler can also keep resident.
+#if defined(__CUDACC__)
+#define KSL_TABLE __constant__ double
 #else
 #define KSL_TABLE static const double
 #endif
 // sin(d) = d + d^3 (S0 + S1 d^2 + S2 d^4 + S3 d^6);  cos(d) = 1 + d^2 (C0 + C1 d^2 + ... + C4 d^8)
-KSL_TABLE kTrigTab[9] = {-1.6666666666666666e-01, 8.3333333333333332e-03, -1.9841269841269841e-04, 2.7557319223985893e-06,
-                         -0.5, 4.1666666666666664e-02, -1.3888888888888889e-03, 2.4801587301587302e-05,
-                         -2.7557319223985888e-07};
+KSL_TABLE kTrigTab[10] = {-1.6666666666666666e-01, 8.3333333333333332e-03, -1.9841269841269841e-04, 2.7557319223985893e-06,
+                          -0.5, 4.1666666666666664e-02, -1.3888888888888889e-03, 2.4801587301587302e-05,
+                          -2.7557319223985888e-07, 0.0};
 // sqrt(1 - x) = 1 - x/2 - x^2/8 - x^3/16 - 5x^4/128 - 7x^5/256 - 21x^6/1024
 KSL_TABLE kSqrtTab[6] = {-0.5, -0.125, -0.0625, -0.0390625, -0.02734375, -0.0205078125};
+// full-range sincos (|x| < 1e5): Cody-Waite reduction by pi/2 in three pieces (33 + 33 + 53 bits) and the
+// fdlibm minimax kernels on [-pi/4, pi/4] (K. C. Ng, 1993; < 1 ulp)
+//   [0] 2/pi  [1] 1.5*2^52  [2] pio2_1  [3] pio2_2  [4] pio2_2t
+//   [5..10]  S1..S6    [11..16] C1..C6
+KSL_TABLE kSinCosTab[18] = {
+    6.36619772367581382433e-01, 6755399441055744.0, 1.57079632673412561417e+00, 6.07710050630396597660e-11,
+    2.02226624879595063154e-21,
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, 2.75573137070700676789e-06,
+    -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07,
+    2.08757232129817482790e-09, -1.13596475577881948265e-11, 0.0};
+
+KSL_HD int lo_word(double t) {
+#if defined(__CUDA_ARCH__)
+    return __double2loint(t);
+#else
+    long long b;
+    memcpy(&b, &t, 8);
+    return (int)(b & 0xffffffffLL);
+#endif
+}
+KSL_HD double flip_sign_if(double v, int nonzero) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(v) ^ (nonzero ? 0x80000000 : 0), __double2loint(v));
+#else
+    return nonzero ? -v : v;
+#endif
+}
+// branch-free sincos for |x| < kSinCosMaxArg (callers flag anything larger for the exact path)
+constexpr double kSinCosMaxArg = 1.0e5;
+KSL_HD void sincos_cw(double x, double &s, double &c) {
+    const double t = fma_rn(x, kSinCosTab[0], kSinCosTab[1]);   // 1.5*2^52 + rint(x * 2/pi)
+    const int q = lo_word(t);
+    const double fn = t - kSinCosTab[1];
+    double r = fma_rn(-fn, kSinCosTab[2], x);
+    r = fma_rn(-fn, kSinCosTab[3], r);
+    r = fma_rn(-fn, kSinCosTab[4], r);
+    const double z = r * r;
+    double ps = fma_rn(z, kSinCosTab[10], kSinCosTab[9]);
+    ps = fma_rn(ps, z, kSinCosTab[8]);
+    ps = fma_rn(ps, z, kSinCosTab[7]);
+    ps = fma_rn(ps, z, kSinCosTab[6]);
+    ps = fma_rn(ps, z, kSinCosTab[5]);
+    const double ks = fma_rn(ps * z, r, r);
+    double pc = fma_rn(z, kSinCosTab[16], kSinCosTab[15]);
+    pc = fma_rn(pc, z, kSinCosTab[14]);
+    pc = fma_rn(pc, z, kSinCosTab[13]);
+    pc = fma_rn(pc, z, kSinCosTab[12]);
+    pc = fma_rn(pc, z, kSinCosTab[11]);
+    const double kc = fma_rn(z, fma_rn(pc, z, -0.5), 1.0);
+    const bool swap = (q & 1) != 0;
+    const double sv = swap ? kc : ks;
+    const double cv = swap ? ks : kc;
+    s = flip_sign_if(sv, q & 2);
+    c = flip_sign_if(cv, (q + 1) & 2);
+}
 
 KSL_HD double rcp_seed(double b) {
 #if defined(__CUDA_ARCH__)
@@ -454,9 +514,10 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {
     double templ = c(KSL_C_T2COF) * t2;
     double mm = xmdf, argpm = argpdf;
     double worst = 0.0;   // largest small-angle argument seen, checked once at the end
+    bool ok_arg = true;
     if (c(KSL_C_ISIMP) == 0.0) {   // uniform over the record
         double sx, cx;
-        sincos_full(xmdf, &sx, &cx);
+        sincos_cw(xmdf, sx, cx);
         const double delmtemp = fma_rn(c(KSL_C_ETA), cx, 1.0);
         const double delm = c(KSL_C_XMCOF) * (delmtemp * delmtemp * delmtemp - c(KSL_C_DELMO));
         const double temp = fma_rn(c(KSL_C_OMGCOF), t, delm);
@@ -465,13 +526,14 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {
         const double t3 = t2 * t, t4 = t3 * t;
         tempa = tempa - c(KSL_C_D2) * t2 - c(KSL_C_D3) * t3 - c(KSL_C_D4) * t4;
         worst = fabs(temp);
+        ok_arg = fabs(xmdf) < kSinCosMaxArg;
         rotate_small(temp, sx, cx);   // sx = sin(mm); feeds a 1e-6-weighted term
         tempe = fma_rn(bstar * c(KSL_C_CC5), sx - c(KSL_C_SINMAO), tempe);
         templ = templ + c(KSL_C_T3COF) * t3 + t4 * fma_rn(t, c(KSL_C_T5COF), c(KSL_C_T4COF));
     }
     const double am = c(KSL_C_AOBASE) * tempa * tempa;
     const double em = c(KSL_C_ECCO) - tempe;
-    bool ok = (em >= 1.0e-6) && (em < 0.12);   // no clamp, no error 1
+    bool ok = ok_arg && (em >= 1.0e-6) && (em < 0.12);   // no clamp, no error 1
     mm = mad_2r(c(KSL_C_NO), templ, mm);
     const double xlm = add_rn(add_rn(mm, argpm), nodem);
     nodem = wrap_twopi(nodem);
@@ -480,7 +542,7 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {
     mm = wrap_twopi(add_rn(add_rn(xlmw, -argpm), -nodem));
 
     double sarg, carg;
-    sincos_full(argpm, &sarg, &carg);
+    sincos_cw(argpm, sarg, carg);
     const double axnl = em * carg;
     double temp = rcp_1(am * fma_rn(-em, em, 1.0));            // * aycof / xlcof ~ 1e-3: 1e-12 is plenty
     const double aynl = fma_rn(em, sarg, temp * c(KSL_C_AYCOF));
@@ -489,7 +551,7 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {
 
     // Kepler: u = E - axnl sin E + aynl cos E
     double se, ce;
-    sincos_full(u, &se, &ce);
+    sincos_cw(u, se, ce);
     double den = fma_rn(-se, aynl, fma_rn(-ce, axnl, 1.0));
     double rden = rcp_2(den);
     double d = (fma_rn(axnl, se, fma_rn(-aynl, ce, u)) - u) * rden;            // first step from E = u
@@ -548,7 +610,7 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {
     double sinsu = sinu * h, cossu = cosu * h;
     rotate_tiny(dsu, sinsu, cossu);
     double snod, cnod;
-    sincos_full(nodem, &snod, &cnod);
+    sincos_cw(nodem, snod, cnod);
     rotate_tiny(dnode, snod, cnod);
     double sini = sinio, cosi = cosio;
     rotate_tiny(dinc, sini, cosi);
@@ -561,12 +623,23 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {
     return ok && (mrt >= 1.0) && (fabs(mr) < 1.0e300);
 }
 
-// position at t through the fast path, falling back to the exact path when needed
-template <typename Load>
-KSL_HD int sgp4_position(Load &&c, double t, double r[3]) {
-    if (sgp4_prop_fast(c, t, r)) return 0;
+// position at t through the fast path, falling back to the exact path when needed.  The exact path
+// is kept out of line on the device so that its registers do not count against the hot path.
+#if defined(__CUDACC__)
+__device__ __noinline__ int sgp4_position_exact(const double *c, int stride, double t, double *r) {
     double v[3];
-    return sgp4_prop<false>(c, t, r, v);
+    return sgp4_prop<false>([&](int k) { return c[(long long)k * stride]; }, t, r, v);
+}
+#endif
+// c: pointer to constant 0 of the record, `stride` doubles between consecutive constants
+KSL_HD int sgp4_position(const double *c, int stride, double t, double r[3]) {
+    if (sgp4_prop_fast([&](int k) { return c[(long long)k * stride]; }, t, r)) return 0;
+#if defined(__CUDA_ARCH__)
+    return sgp4_position_exact(c, stride, t, r);
+#else
+    double v[3];
+    return sgp4_prop<false>([&](int k) { return c[(long long)k * stride]; }, t, r, v);
+#endif
 }
 
 // ---- util.upsample index arithmetic (torch upsample_linear1d, align_corners) ----

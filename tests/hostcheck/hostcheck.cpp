@@ -45,7 +45,7 @@ int hc_sgp4_position(const double *consts, int64_t n, const double *tsince, int6
             double *o = pos + (i * m + j) * 3;
             double tmp[3];
             fast_used[i * m + j] = ksl::sgp4_prop_fast(ld, tsince[j], tmp) ? 1 : 0;
-            e |= ksl::sgp4_position(ld, tsince[j], o);
+            e |= ksl::sgp4_position(consts + i, (int)n, tsince[j], o);
         }
         err[i] |= e;
     }
@@ -77,8 +77,8 @@ int hc_screen(const double *consts_t, const double *epoch_t, int64_t n_t, const 
         auto ldt = [&](int q) { return consts_t[(int64_t)q * n_t + it]; };
         auto ldc = [&](int q) { return consts_c[(int64_t)q * n + s]; };
         for (int64_t k = 0; k < n_coarse; ++k) {
-            et |= ksl::sgp4_position(ldt, (times_coarse[k] - epoch_t[it]) * 1440.0, &pt[3 * k]);
-            ec |= ksl::sgp4_position(ldc, (times_coarse[k] - epoch_c[s]) * 1440.0, &pc[3 * k]);
+            et |= ksl::sgp4_position(consts_t + it, (int)n_t, (times_coarse[k] - epoch_t[it]) * 1440.0, &pt[3 * k]);
+            ec |= ksl::sgp4_position(consts_c + s, (int)n, (times_coarse[k] - epoch_c[s]) * 1440.0, &pc[3 * k]);
         }
         std::vector<ksl::Best> best(kThreads);
         for (auto &b : best) ksl::best_init(b);

@@ -278,6 +278,31 @@ def test_screen_analytic_equals_brute_large(eng):
     assert np.array_equal(c["i_min"], a["i_min"][perm]) and np.array_equal(c["d_min"], a["d_min"][perm])
 
 
+def test_screen_cta_and_warp_decompositions_agree(eng):
+    """k_screen (CTA per trace) and k_screen_warp (warp per trace) are the same function of the inputs,
+    on the default grid, a ragged grid and the one-vs-catalog shape, in both search modes."""
+    from kessler_b200 import _native as NV
+    elt, ept, elc, epc, times, _ = _golden_batch(200, 31)
+    tc = np.ascontiguousarray(times[::100])
+    for mode in (0, 1):
+        a = _screen(eng, elt, ept, elc, epc, tc, len(times), 5e3, mode | NV.SCREEN_FORCE_CTA)
+        b = _screen(eng, elt, ept, elc, epc, tc, len(times), 5e3, mode | NV.SCREEN_FORCE_WARP)
+        for k in ("i_min", "i_conj", "err"):
+            assert np.array_equal(a[k], b[k]), (mode, k)
+        assert np.array_equal(a["d_min"], b["d_min"]) and np.array_equal(np.isnan(a["d_conj"]), np.isnan(b["d_conj"]))
+    ref = C.screen(elt[:, :24].copy(), ept[:24], elc[:, :24].copy(), epc[:24], tc, len(times), 5e3)
+    assert np.array_equal(b["i_min"][:24], ref["i_min"]) and np.array_equal(b["i_conj"][:24], ref["i_conj"])
+    gt = elt[:, :1].copy()
+    cat = common.synthetic_catalog(96, seed=5)
+    epc2 = np.full(96, ept[0])
+    tc2 = tc[:613]
+    ref = C.screen(gt, ept[:1], cat, epc2, tc2, 61201, 2e5)
+    for force in (NV.SCREEN_FORCE_CTA, NV.SCREEN_FORCE_WARP):
+        r = _screen(eng, gt, ept[:1], cat, epc2, tc2, 61201, 2e5, force)
+        assert np.array_equal(r["i_min"], ref["i_min"]) and np.array_equal(r["i_conj"], ref["i_conj"])
+        assert np.array_equal(r["err"], ref["err"])
+
+
 def test_screen_host_and_summary(eng):
     elt, ept, elc, epc, times, _ = _golden_batch(500, 9)
     tc = np.ascontiguousarray(times[::100])
