@@ -278,6 +278,7 @@ def run_ours(args):
     same = bool(np.array_equal(r_host["i_min"], res["i_min"].cpu().numpy()))
 
     if rank != 0:
+        D.barrier()
         return
     # ---- roofline of the dominant kernel (k_screen), FP64 vector pipe ------------------------
     peak_tf = engine.fp64_peak_tflops()
@@ -320,7 +321,8 @@ def run_ours(args):
                     "ms_per_step": e2e_s * 1e3 / args.steps, "matches_device_arm": same},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "summary": {"counts": counts_h, "moments": moments_h}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    D.barrier()
 
 
 def main():
@@ -336,7 +338,12 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        try:
+            run_ours(args)
+        finally:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -225,11 +225,13 @@ __global__ void __launch_bounds__(256) k_findconj_final(const Best *__restrict__
 // non-finite or ill-conditioned.  Segments whose analytic minimum cannot beat the
 // thread's running best (nor the threshold) are skipped.
 // ------------------------------------------------------------------------------------
+// Shape of the fused-trace kernels, tuned on B200 (profiles/README.md, round 1): one 512-thread CTA per SM
+// (16 warps, 128 registers/thread) beat 2 x 256, 3 x 256 (80 regs, spills) and 5-7 x 128.
 #ifndef KSL_SCREEN_THREADS
-#define KSL_SCREEN_THREADS 256
+#define KSL_SCREEN_THREADS 512
 #endif
 #ifndef KSL_SCREEN_MIN_CTAS
-#define KSL_SCREEN_MIN_CTAS 2
+#define KSL_SCREEN_MIN_CTAS 1
 #endif
 #ifndef KSL_SCREEN_GRID_SMEM
 #define KSL_SCREEN_GRID_SMEM 1   // stage the time grid in shared memory (north star); 0 = read it through L1
@@ -279,6 +281,9 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen(
             s_flags[0] = p.init_err_t ? p.init_err_t[it] : 0;
             s_flags[1] = p.init_err_c ? p.init_err_c[s] : 0;
         }
+        __syncthreads();
+        if (tid == 0) ksl::mask_isimp_constants(s_cc, 1);
+        if (!kSharedTarget && tid == 32) ksl::mask_isimp_constants(s_ct, 1);
         __syncthreads();
         const int ierr_t = s_flags[0], ierr_c = s_flags[1];
         if ((ierr_t | ierr_c) & KSL_ERR_DEEPSPACE) {  // dsgp4.initialize_tle raises -> prop error (model.py:584,595)
@@ -381,6 +386,9 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
         const double epoch_t = p.epoch_t[it], epoch_c = p.epoch_c[s];
         const int ierr_t = p.init_err_t ? p.init_err_t[it] : 0, ierr_c = p.init_err_c ? p.init_err_c[s] : 0;
         __syncwarp();
+        if (lane == 0) ksl::mask_isimp_constants(s_cc, 1);
+        if (!kSharedTarget && lane == 1) ksl::mask_isimp_constants(s_ct, 1);
+        __syncwarp();
         if ((ierr_t | ierr_c) & KSL_ERR_DEEPSPACE) {
             if (lane == 0) {
                 p.i_min[s] = -1;
@@ -399,12 +407,18 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
             double rt[3] = {0.0, 0.0, 0.0}, rc[3] = {0.0, 0.0, 0.0};
             if (k <= last) {
                 const double tm = grid_in_smem ? s_times[k] : __ldg(p.times_coarse + k);
-                e_c |= ksl::sgp4_position(s_cc, 1, (tm - epoch_c) * 1440.0, rc);
+                // both fast evaluations back to back: one straight-line block with two independent
+                // dependency chains for the scheduler; the (rare) exact fallbacks come after
+                const double ts_c = (tm - epoch_c) * 1440.0, ts_t = (tm - epoch_t) * 1440.0;
+                const bool ok_c = ksl::sgp4_prop_fast([&](int q) { return s_cc[q]; }, ts_c, rc);
+                bool ok_t = true;
                 if (kSharedTarget) {
                     rt[0] = __ldg(p.target_pos + 3 * k); rt[1] = __ldg(p.target_pos + 3 * k + 1); rt[2] = __ldg(p.target_pos + 3 * k + 2);
                 } else {
-                    e_t |= ksl::sgp4_position(s_ct, 1, (tm - epoch_t) * 1440.0, rt);
+                    ok_t = ksl::sgp4_prop_fast([&](int q) { return s_ct[q]; }, ts_t, rt);
                 }
+                if (!ok_c) e_c |= ksl::sgp4_position_exact(s_cc, 1, ts_c, rc);
+                if (!ok_t) e_t |= ksl::sgp4_position_exact(s_ct, 1, ts_t, rt);
             }
             double t1[3], c1[3];
 #pragma unroll
@@ -443,8 +457,8 @@ __global__ void __launch_bounds__(128) k_target_positions(const double *__restri
                                                           long long n_coarse, double *__restrict__ pos, int *__restrict__ err) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_coarse) return;
-    double r[3];
-    const int e = ksl::sgp4_position(consts, 1, (times[k] - epoch[0]) * 1440.0, r);
+    double r[3], v[3];
+    const int e = ksl::sgp4_prop<false>([&](int q) { return __ldg(consts + q); }, (times[k] - epoch[0]) * 1440.0, r, v);
     pos[3 * k] = r[0]; pos[3 * k + 1] = r[1]; pos[3 * k + 2] = r[2];
     if (e) atomicOr(err, e);
 }

@@ -502,7 +502,7 @@ constexpr double kFastMaxEl2 = 0.0144;   // e <= 0.12: series for sqrt(1 - el2) 
 // returns true when the result is the one sgp4_prop would give (to rounding); false = assumptions
 // violated, nothing usable written: call sgp4_prop.  err receives the Vallado bits (0 on success).
 template <typename Load>
-KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {
+KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: MASKED constants (see below)
     const double xmdf = mad_2r(c(KSL_C_MDOT), t, c(KSL_C_MO));
     const double argpdf = mad_2r(c(KSL_C_ARGPDOT), t, c(KSL_C_ARGPO));
     const double nodedf = mad_2r(c(KSL_C_NODEDOT), t, c(KSL_C_NODEO));
@@ -512,25 +512,24 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {
     double tempa = 1.0 - c(KSL_C_CC1) * t;
     double tempe = (bstar * c(KSL_C_CC4)) * t;
     double templ = c(KSL_C_T2COF) * t2;
-    double mm = xmdf, argpm = argpdf;
-    double worst = 0.0;   // largest small-angle argument seen, checked once at the end
-    bool ok_arg = true;
-    if (c(KSL_C_ISIMP) == 0.0) {   // uniform over the record
-        double sx, cx;
-        sincos_cw(xmdf, sx, cx);
-        const double delmtemp = fma_rn(c(KSL_C_ETA), cx, 1.0);
-        const double delm = c(KSL_C_XMCOF) * (delmtemp * delmtemp * delmtemp - c(KSL_C_DELMO));
-        const double temp = fma_rn(c(KSL_C_OMGCOF), t, delm);
-        mm = add_rn(xmdf, temp);
-        argpm = add_rn(argpdf, -temp);
-        const double t3 = t2 * t, t4 = t3 * t;
-        tempa = tempa - c(KSL_C_D2) * t2 - c(KSL_C_D3) * t3 - c(KSL_C_D4) * t4;
-        worst = fabs(temp);
-        ok_arg = fabs(xmdf) < kSinCosMaxArg;
-        rotate_small(temp, sx, cx);   // sx = sin(mm); feeds a 1e-6-weighted term
-        tempe = fma_rn(bstar * c(KSL_C_CC5), sx - c(KSL_C_SINMAO), tempe);
-        templ = templ + c(KSL_C_T3COF) * t3 + t4 * fma_rn(t, c(KSL_C_T5COF), c(KSL_C_T4COF));
-    }
+    // Drag / long-period block, executed unconditionally: for an `isimp` record (perigee < 220 km) the
+    // caller hands in a MASKED copy of the constants (mask_isimp_constants: omgcof = xmcof = cc5 = 0, and
+    // sgp4init already left d2..d4, t3cof..t5cof at 0), which turns every term below into an exact +0.
+    double sx, cx;
+    sincos_cw(xmdf, sx, cx);
+    const bool ok_arg = fabs(xmdf) < kSinCosMaxArg;
+    const double delmtemp = fma_rn(c(KSL_C_ETA), cx, 1.0);
+    const double delm = c(KSL_C_XMCOF) * (delmtemp * delmtemp * delmtemp - c(KSL_C_DELMO));
+    const double temp0 = fma_rn(c(KSL_C_OMGCOF), t, delm);
+    const double mm0 = add_rn(xmdf, temp0);
+    double argpm = add_rn(argpdf, -temp0);
+    const double t3 = t2 * t, t4 = t3 * t;
+    tempa = tempa - c(KSL_C_D2) * t2 - c(KSL_C_D3) * t3 - c(KSL_C_D4) * t4;
+    double worst = fabs(temp0);   // largest small-angle argument seen, checked once at the end
+    rotate_small(temp0, sx, cx);   // sx = sin(mm); feeds a 1e-6-weighted term
+    tempe = fma_rn(bstar * c(KSL_C_CC5), sx - c(KSL_C_SINMAO), tempe);
+    templ = templ + c(KSL_C_T3COF) * t3 + t4 * fma_rn(t, c(KSL_C_T5COF), c(KSL_C_T4COF));
+    double mm = mm0;
     const double am = c(KSL_C_AOBASE) * tempa * tempa;
     const double em = c(KSL_C_ECCO) - tempe;
     bool ok = ok_arg && (em >= 1.0e-6) && (em < 0.12);   // no clamp, no error 1
@@ -623,7 +622,17 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {
     return ok && (mrt >= 1.0) && (fabs(mr) < 1.0e300);
 }
 
-// position at t through the fast path, falling back to the exact path when needed.  The exact path
+// In-place masking of a private (shared-memory / local) copy of a record for sgp4_prop_fast.  The exact
+// path ignores these three constants when isimp is set, so the masked copy serves both paths.
+KSL_HD void mask_isimp_constants(double *c, int stride) {
+    if (c[(long long)KSL_C_ISIMP * stride] != 0.0) {
+        c[(long long)KSL_C_OMGCOF * stride] = 0.0;
+        c[(long long)KSL_C_XMCOF * stride] = 0.0;
+        c[(long long)KSL_C_CC5 * stride] = 0.0;
+    }
+}
+
+// position at t through the fast path, falling back to the exact path when needed (c: masked record).  The exact path
 // is kept out of line on the device so that its registers do not count against the hot path.
 #if defined(__CUDACC__)
 __device__ __noinline__ int sgp4_position_exact(const double *c, int stride, double t, double *r) {
