@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Secondary BASELINE.json configs (the headline bench line is bench.py = configs[1]).
+
+    python benchmarks/run_configs.py [--config 3 4] [--n3 1e8] [--n4 30000]
+    torchrun --nproc-per-node N benchmarks/run_configs.py --config 3      # configs[2] sharded over N GPUs
+
+configs[2]  1e8-sample Monte Carlo collision-probability estimate of one pair (device-side draws,
+            sgp4init + sgp4 at TCA for both objects, elementwise count + moments), NCCL count all-reduce.
+configs[3]  one-vs-catalog screening: 30k synthetic LEO TLEs vs one target over 7 days at the default
+            resolution (shared-target path of the fused kernel; the altitude pre-filter of model.py:567
+            reported next to the unfiltered rate).
+Each prints one JSON line (rank 0)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from kessler_b200 import distributed as D  # noqa: E402
+from kessler_b200 import engine, montecarlo as MC, workloads as W  # noqa: E402
+from kessler_b200.tle import MU_EARTH, R_EARTH  # noqa: E402
+
+
+def synthetic_leo_catalog(n, seed=3):
+    """n near-earth element sets in the spirit of default_prior() (model.py:54-153) restricted to what a
+    catalog screen keeps: period < 225 min and perigee > 120 km."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((7, 0))
+    while out.shape[1] < n:
+        m = 2 * n
+        n_rad_s = np.where(rng.uniform(size=m) < 0.9, rng.normal(1.03e-3, 4e-5, m), rng.normal(7.8e-4, 1.4e-4, m))
+        ecc = np.abs(np.where(rng.uniform(size=m) < 0.85, rng.normal(0.0029, 0.0025, m), rng.normal(0.0135, 0.0069, m)))
+        a = (MU_EARTH / n_rad_s ** 2) ** (1.0 / 3.0)
+        keep = (n_rad_s > 2 * np.pi / (225.0 * 60.0)) & (a * (1 - ecc) - R_EARTH > 120e3) & (n_rad_s < 1.2e-3)
+        el = np.stack([n_rad_s * 60.0, ecc, rng.uniform(0, np.pi, m), rng.uniform(0, 2 * np.pi, m), rng.uniform(0, 2 * np.pi, m),
+                       rng.uniform(0, 2 * np.pi, m), rng.normal(2e-4, 1.1e-3, m)])[:, keep]
+        out = np.concatenate([out, el], axis=1)
+    return np.ascontiguousarray(out[:, :n])
+
+
+def config3(n_total):
+    rank, local, world = D.init()
+    torch.cuda.set_device(local)
+    t_tle, c_tle = W.pair_a()
+    st_t, st_c = MC.nominal_state_m(t_tle, 0.0).reshape(2, 3), MC.nominal_state_m(c_tle, 0.0).reshape(2, 3)
+    tca = t_tle.date_mjd + 1.0
+    args = (t_tle, st_t, W.T_COV_RTN, c_tle, st_c, W.C_COV_RTN, tca)
+    MC.collision_probability(*args, n_total=max(world * 100000, 100000), seed=2)      # warm-up
+    torch.cuda.synchronize()
+    D.barrier()
+    t0 = time.perf_counter()
+    r = MC.collision_probability(*args, n_total=int(n_total), collision_threshold=70.0, seed=2)
+    torch.cuda.synchronize()
+    dt = D.max_over_ranks(time.perf_counter() - t0)
+    if rank == 0:
+        print(json.dumps({"config": "BASELINE configs[2]: Monte Carlo Pc of one pair, device-side draws", "n_samples": int(n_total),
+                          "n_gpus": world, "seconds": dt, "samples_per_s": n_total / dt,
+                          "sgp4_init_plus_eval_per_s": 2 * n_total / dt, "count": r["count"], "pc": r["pc"],
+                          "err_count": r["err_count"], "sigma_rtn_t_m": np.sqrt(np.diag(r["cov_rtn_t"])[:3]).tolist(),
+                          "sigma_rtn_c_m": np.sqrt(np.diag(r["cov_rtn_c"])[:3]).tolist()}), flush=True)
+    D.barrier()
+
+
+def config4(n_cat):
+    torch.cuda.set_device(0)
+    t_tle, _ = W.pair_a()
+    cat = synthetic_leo_catalog(int(n_cat))
+    time0 = t_tle.date_mjd - 3.5
+    times = W.time_grid(time0)
+    tc = np.ascontiguousarray(times[::100])
+    n = cat.shape[1]
+    ep_c = np.full(n, t_tle.date_mjd)
+    el_t = t_tle.elements().reshape(7, 1)
+    # altitude pre-filter of model.py:567 (vectorised)
+    a_c = (MU_EARTH / (cat[0] / 60.0) ** 2) ** (1.0 / 3.0)
+    apo_c, per_c = a_c * (1 + cat[1]) - R_EARTH, a_c * (1 - cat[1]) - R_EARTH
+    margin = 5e3 + 1000
+    pre = ((t_tle.apogee_alt() + margin) < per_c) | ((apo_c + margin) < t_tle.perigee_alt())
+    res = {}
+    for tag, sel in (("unfiltered", np.ones(n, bool)), ("prefiltered", ~pre)):
+        el = np.ascontiguousarray(cat[:, sel])
+        engine.screen_host(el_t, [t_tle.date_mjd], el, ep_c[sel], tc, len(times), 5e3)         # warm-up
+        t0 = time.perf_counter()
+        out = engine.screen_host(el_t, [t_tle.date_mjd], el, ep_c[sel], tc, len(times), 5e3)
+        dt = time.perf_counter() - t0
+        res[tag] = {"objects": int(sel.sum()), "seconds": dt, "objects_per_s": float(sel.sum() / dt),
+                    "sgp4_evals_per_s": float((sel.sum() + 1) * len(tc) / dt), "conjunctions_below_5km": int((out["i_conj"] > 0).sum()),
+                    "min_d_min_m": float(np.nanmin(out["d_min"]))}
+    print(json.dumps({"config": "BASELINE configs[3]: one-vs-catalog screening, 7 days, default resolution", "n_catalog": n,
+                      "rejected_by_altitude_filter": int(pre.sum()), **res}), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, nargs="+", default=[3, 4])
+    ap.add_argument("--n3", type=float, default=1e8)
+    ap.add_argument("--n4", type=float, default=30000)
+    a = ap.parse_args()
+    if 3 in a.config:
+        config3(a.n3)
+    if 4 in a.config and int(os.environ.get("RANK", 0)) == 0:
+        config4(a.n4)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()

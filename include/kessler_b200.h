@@ -174,6 +174,27 @@ int ksl_tca_moments(const double *elems, int64_t n, double tsince, const double 
 int ksl_pc_count(const double *t_xyz, int64_t nt, const double *c_xyz, int64_t nc, double thr_m, int pairing,
                  unsigned long long *count, void *stream);
 
+/* ---- scale-out Monte Carlo collision probability (BASELINE configs[2]) -----------
+ * The sample loop of model.py:497-541 for BOTH objects plus the miss-distance count of
+ * model.py:432-437 in its elementwise form, with the draws generated on the device:
+ * for global sample g = sample_offset + i, i < n:
+ *   (a,e,i,raan,argp,M) = mean + L z,  z = 6 standard normals from Philox4x32-10 keyed by
+ *   (seed, g, object) -- independent of how [0, N) is split over GPUs;
+ *   a -> mean motion, e < 0 -> 0 (model.py:500,525-533); sgp4init + sgp4 at tsince; metres.
+ * mean_*, ref_* [6] and chol_* [21] (row-major lower triangle of the Cholesky factor of the
+ * element covariance, model.py:461-478) are HOST pointers (they travel as kernel arguments);
+ * everything else is a device pointer.  *count / *err_count are ADDED to.
+ * moments_t, moments_c [KSL_NMOMENT]: shifted moments of the two states about ref_*; moments_t
+ * must have room for 2*KSL_NMOMENT doubles (moments_c may alias moments_t + KSL_NMOMENT).
+ * dump (optional, [n_dump][26]): per sample the 7+7 SGP4 inputs and the 6+6 state components,
+ * for parity checks against the oracle on IDENTICAL samples.  workspace: ksl_mc_pc_ws(n) bytes. */
+int64_t ksl_mc_pc_ws(int64_t n);
+int ksl_mc_pc(const double *mean_t, const double *chol_t, double bstar_t, double tsince_t, const double *ref_t,
+              const double *mean_c, const double *chol_c, double bstar_c, double tsince_c, const double *ref_c,
+              uint64_t seed, int64_t sample_offset, int64_t n, double thr_m, double mu_m3s2, unsigned long long *count,
+              double *moments_t, double *moments_c, unsigned long long *err_count, double *dump, int64_t n_dump,
+              void *workspace, void *stream);
+
 /* ---- end-to-end entry points: HOST buffers in, HOST buffers out ----------------
  * What a Kessler-side binding calls for a batch of traces.  Allocates (and caches
  * per device) its staging and scratch buffers; synchronous.

@@ -675,6 +675,165 @@ __global__ void __launch_bounds__(256) k_pc_elementwise(const double *__restrict
 }
 
 // ------------------------------------------------------------------------------------
+// K6  scale-out Monte Carlo collision probability (BASELINE configs[2]):
+// for every global sample index g: draw (a, e, i, Omega, omega, M) ~ N(mean, L L^T) for target and
+// chaser with a counter-based generator keyed by (seed, g) -- so the draws do not depend on how the
+// samples are sharded over GPUs --, convert as model.py:500,525-533 do, sgp4init + sgp4 at the TCA,
+// and reduce (i) the number of samples whose miss distance is below the threshold (exact integer)
+// and (ii) the shifted moments of both states.  Everything stays in registers; 96 B of moments per
+// CTA and one atomic per CTA leave the SM.
+// ------------------------------------------------------------------------------------
+struct McObject {
+    double mean[6];   // a [m], e, i, raan, argp, M
+    double chol[21];  // lower triangle of L, row-major: L00, L10, L11, L20, ...
+    double bstar, tsince;
+    double ref[6];    // reference state [m, m/s] for the shifted moments
+};
+
+__device__ __forceinline__ void philox4x32_10(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3,
+                                              unsigned int k0, unsigned int k1, unsigned int out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 53-bit uniform in (0, 1) from two 32-bit words
+__device__ __forceinline__ double u53(unsigned int a, unsigned int b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// six standard normals for (seed, sample g, stream s): three Box-Muller pairs from three Philox blocks
+__device__ __forceinline__ void normals6(unsigned long long seed, unsigned long long g, unsigned int stream, double z[6]) {
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        unsigned int w[4];
+        philox4x32_10((unsigned int)g, (unsigned int)(g >> 32), stream * 3u + b, 0x4b534c31u, (unsigned int)seed,
+                      (unsigned int)(seed >> 32), w);
+        const double rad = sqrt(-2.0 * log(u53(w[0], w[1])));
+        double sn, cs;
+        sincospi(2.0 * u53(w[2], w[3]), &sn, &cs);
+        z[2 * b] = rad * cs;
+        z[2 * b + 1] = rad * sn;
+    }
+}
+
+__device__ __forceinline__ int mc_state(const McObject &o, const double z[6], double mu, double el_out[7], double x[6]) {
+    double q[6];
+    int idx = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        double acc = o.mean[r];
+#pragma unroll
+        for (int cidx = 0; cidx <= r; ++cidx) acc += o.chol[idx++] * z[cidx];
+        q[r] = acc;
+    }
+    double el[7];
+    el[0] = sqrt(mu / (q[0] * q[0] * q[0])) * 60.0;   // model.py:500: a -> mean motion [rad/s]; *60 -> rad/min
+    el[1] = q[1] < 0.0 ? 0.0 : q[1];                  // model.py:525-528
+    el[2] = q[2]; el[3] = q[3]; el[4] = q[4]; el[5] = q[5];
+    el[6] = o.bstar;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) el_out[r] = el[r];
+    double c[KSL_NCONST];
+    int e = ksl::sgp4_init(el, [&](int k, double v) { c[k] = v; });
+    e |= ksl::sgp4_prop<true>([&](int k) { return c[k]; }, o.tsince, x, x + 3);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) x[r] *= 1e3;
+    return e;
+}
+
+__device__ __forceinline__ void accumulate_moments(double acc[KSL_NMOMENT], const double x[6], const double ref[6]) {
+    bool finite = true;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) finite = finite && (fabs(x[q]) < INFINITY);
+    if (!finite) return;
+    double d[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) d[q] = x[q] - ref[q];
+    acc[0] += 1.0;
+    int o = 7;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        acc[1 + a] += d[a];
+#pragma unroll
+        for (int b = a; b < 6; ++b) acc[o++] += d[a] * d[b];
+    }
+}
+
+constexpr int kMcThreads = 128;
+__global__ void __launch_bounds__(kMcThreads) k_mc_pc(const McObject tgt, const McObject chs, unsigned long long seed,
+                                                      long long offset, long long n, double thr2, double mu,
+                                                      unsigned long long *__restrict__ count,
+                                                      double *__restrict__ partial /*[grid][2][KSL_NMOMENT]*/,
+                                                      unsigned long long *__restrict__ nerr,
+                                                      double *__restrict__ dump /*[n_dump][26] or NULL*/, long long n_dump) {
+    double acc_t[KSL_NMOMENT], acc_c[KSL_NMOMENT];
+#pragma unroll
+    for (int q = 0; q < KSL_NMOMENT; ++q) { acc_t[q] = 0.0; acc_c[q] = 0.0; }
+    unsigned long long hits = 0, errs = 0;
+    for (long long i = (long long)blockIdx.x * kMcThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kMcThreads) {
+        const unsigned long long g = (unsigned long long)(offset + i);
+        double z[6], el_t[7], el_c[7], xt[6], xc[6];
+        normals6(seed, g, 0u, z);
+        const int e0 = mc_state(tgt, z, mu, el_t, xt);
+        normals6(seed, g, 1u, z);
+        const int e1 = mc_state(chs, z, mu, el_c, xc);
+        const double dx = ksl::add_rn(xt[0], -xc[0]), dy = ksl::add_rn(xt[1], -xc[1]), dz = ksl::add_rn(xt[2], -xc[2]);
+        hits += (ksl::sqdist3(dx, dy, dz) < thr2) ? 1u : 0u;
+        errs += (e0 | e1) ? 1u : 0u;
+        accumulate_moments(acc_t, xt, tgt.ref);
+        accumulate_moments(acc_c, xc, chs.ref);
+        if (dump && i < n_dump) {
+            double *o = dump + i * 26;
+#pragma unroll
+            for (int q = 0; q < 7; ++q) { o[q] = el_t[q]; o[7 + q] = el_c[q]; }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { o[14 + q] = xt[q]; o[20 + q] = xc[q]; }
+        }
+    }
+    __shared__ double sm[kMcThreads / 32][2 * KSL_NMOMENT];
+    __shared__ unsigned long long s_hits, s_errs;
+    if (threadIdx.x == 0) { s_hits = 0; s_errs = 0; }
+#pragma unroll
+    for (int q = 0; q < KSL_NMOMENT; ++q) {
+        double a = acc_t[q], b = acc_c[q];
+        for (int d = 16; d > 0; d >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, d);
+            b += __shfl_down_sync(0xffffffffu, b, d);
+        }
+        if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5][q] = a; sm[threadIdx.x >> 5][KSL_NMOMENT + q] = b; }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        hits += __shfl_down_sync(0xffffffffu, hits, d);
+        errs += __shfl_down_sync(0xffffffffu, errs, d);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        if (hits) atomicAdd(&s_hits, hits);
+        if (errs) atomicAdd(&s_errs, errs);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * KSL_NMOMENT) {
+        double v = 0.0;
+        for (int w = 0; w < kMcThreads / 32; ++w) v += sm[w][threadIdx.x];
+        partial[(long long)blockIdx.x * 2 * KSL_NMOMENT + threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) {
+        if (s_hits) atomicAdd(count, s_hits);
+        if (s_errs) atomicAdd(nerr, s_errs);
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // FP64 peak probe: 8 independent DFMA chains per thread
 // ------------------------------------------------------------------------------------
 __global__ void k_fp64_peak(long long iters, double *__restrict__ sink) {
@@ -943,6 +1102,41 @@ int ksl_propagate_upsample(const double *consts, double epoch_mjd, const double 
     if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
     k_upsample<true><<<(unsigned)blocks, 256, 0, S(stream)>>>(workspace, n_sub, 6, n_out, up_scale(n_sub, n_out), out_m);
     KSL_LAUNCH_CHECK();
+    return KSL_OK;
+}
+
+int64_t ksl_mc_pc_ws(int64_t n) {
+    (void)n;
+    return (int64_t)sizeof(double) * 2 * KSL_NMOMENT * 2048 + 64;
+}
+
+int ksl_mc_pc(const double *mean_t, const double *chol_t, double bstar_t, double tsince_t, const double *ref_t,
+              const double *mean_c, const double *chol_c, double bstar_c, double tsince_c, const double *ref_c,
+              uint64_t seed, int64_t sample_offset, int64_t n, double thr_m, double mu_m3s2, unsigned long long *count,
+              double *moments_t, double *moments_c, unsigned long long *err_count, double *dump, int64_t n_dump,
+              void *workspace, void *stream) {
+    if (n < 0 || !mean_t || !chol_t || !ref_t || !mean_c || !chol_c || !ref_c || !count || !moments_t || !moments_c ||
+        !err_count || !workspace || n_dump < 0 || (n_dump > 0 && !dump))
+        return fail(KSL_E_ARG, "ksl_mc_pc: bad argument");
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc) return rc;
+    McObject t, c;   // host pointers: the 2 x 35 parameters travel as kernel arguments
+    for (int i = 0; i < 6; ++i) { t.mean[i] = mean_t[i]; c.mean[i] = mean_c[i]; t.ref[i] = ref_t[i]; c.ref[i] = ref_c[i]; }
+    for (int i = 0; i < 21; ++i) { t.chol[i] = chol_t[i]; c.chol[i] = chol_c[i]; }
+    t.bstar = bstar_t; t.tsince = tsince_t; c.bstar = bstar_c; c.tsince = tsince_c;
+    long long blocks = (n + kMcThreads - 1) / kMcThreads;
+    const long long cap = (long long)sms * 4 < 2048 ? (long long)sms * 4 : 2048;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    double *partial = reinterpret_cast<double *>(workspace);
+    k_mc_pc<<<(unsigned)blocks, kMcThreads, 0, S(stream)>>>(t, c, (unsigned long long)seed, sample_offset, n, thr_m * thr_m, mu_m3s2,
+                                                             count, partial, err_count, dump, n_dump);
+    KSL_LAUNCH_CHECK();
+    k_moments_final<<<1, 64, 0, S(stream)>>>(partial, (int)blocks, 2 * KSL_NMOMENT, moments_t);
+    KSL_LAUNCH_CHECK();
+    if (moments_c != moments_t + KSL_NMOMENT)
+        KSL_CUDA(cudaMemcpyAsync(moments_c, moments_t + KSL_NMOMENT, sizeof(double) * KSL_NMOMENT, cudaMemcpyDeviceToDevice, S(stream)));
     return KSL_OK;
 }
 

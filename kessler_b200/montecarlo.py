@@ -1,0 +1,87 @@
+"""Scale-out Monte Carlo collision probability for one conjunction pair (BASELINE configs[2];
+SURVEY.md Sec. 8d C3): N element samples per object, sharded over the GPUs of one box by contiguous
+global-index ranges, one fused kernel per rank (draws + sgp4init + sgp4 + miss-distance count +
+moments), and ONE small all-reduce at the end: the int64 count (exact) and the shifted FP64 moments.
+
+The per-sample semantics are the reference's (model.py:461-541): element covariance from the RTN
+observation noise through the Kepler partials, MVN draws, a -> mean motion, e < 0 -> 0, SGP4 to the
+TCA; the count is model.py:432-437 in its elementwise form (sample i of the target against sample i
+of the chaser).  The all-pairs form on 10^4 x 10^4 positions is `all_pairs_probability`."""
+import numpy as np
+import torch
+
+from . import distributed as D
+from . import engine
+from .stats import moments_to_mean_cov_rtn
+from .tle import MU_EARTH
+from .workloads import tle_covariance
+
+
+def element_distribution(tle, state_xyz_m, cov_matrix_diagonal_rtn, mu_earth=MU_EARTH):
+    """(mean [6], Cholesky factor [6,6]) of the element distribution of model.py:461-497."""
+    cov = tle_covariance(state_xyz_m, cov_matrix_diagonal_rtn, mu_earth)
+    mean = np.array([float(tle.semi_major_axis), tle._ecco, tle._inclo, tle._nodeo, tle._argpo, tle._mo], dtype=np.float64)
+    return mean, np.linalg.cholesky(0.5 * (cov + cov.T))
+
+
+def nominal_state_m(tle, tsince):
+    """State [6] in metres at tsince of the un-perturbed element set (reference point of the moments)."""
+    c, _ = engine.sgp4_init(tle.elements().reshape(7, 1))
+    rv, _ = engine.sgp4_prop(c, [float(tsince)])
+    return rv[0, 0].cpu().numpy() * 1e3
+
+
+def collision_probability(t_tle, t_state_m, t_cov_rtn, c_tle, c_state_m, c_cov_rtn, time_ca_mjd, n_total,
+                          collision_threshold=70.0, seed=2, n_dump=0, chunk=1 << 26):
+    """Returns dict(pc, count, n, mean_t, cov_rtn_t, mean_c, cov_rtn_c, err_count[, dump]).  Call from every rank
+    of an initialised process group (or from a single process): each rank runs its shard, the result is
+    identical on all ranks and -- because the generator is keyed by the global sample index -- the count does
+    not depend on the number of ranks."""
+    rank, world = (torch.distributed.get_rank(), torch.distributed.get_world_size()) if (
+        torch.distributed.is_available() and torch.distributed.is_initialized()) else (0, 1)
+    lo, hi = D.shard_range(n_total, rank, world)
+    mean_t, L_t = element_distribution(t_tle, t_state_m, t_cov_rtn)
+    mean_c, L_c = element_distribution(c_tle, c_state_m, c_cov_rtn)
+    ts_t = (time_ca_mjd - t_tle.date_mjd) * 1440.0
+    ts_c = (time_ca_mjd - c_tle.date_mjd) * 1440.0
+    ref_t, ref_c = nominal_state_m(t_tle, ts_t), nominal_state_m(c_tle, ts_c)
+    count = err = None
+    mom_t = mom_c = None
+    dump = None
+    for start in range(lo, hi, chunk):
+        n = min(chunk, hi - start)
+        r = engine.mc_pc(mean_t, L_t, t_tle._bstar, ts_t, ref_t, mean_c, L_c, c_tle._bstar, ts_c, ref_c, seed, start, n,
+                         collision_threshold, n_dump=(n_dump if start == lo else 0), count=count, err_count=err)
+        count, err = r["count"], r["err_count"]
+        mom_t = r["moments_t"].clone() if mom_t is None else mom_t + r["moments_t"]
+        mom_c = r["moments_c"].clone() if mom_c is None else mom_c + r["moments_c"]
+        if r["dump"] is not None:
+            dump = r["dump"]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if count is None:   # empty shard
+        count, err = torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(1, dtype=torch.int64, device=dev)
+        mom_t, mom_c = torch.zeros(28, dtype=torch.float64, device=dev), torch.zeros(28, dtype=torch.float64, device=dev)
+    packed = torch.cat([count, err])
+    D.allreduce_counts(packed)
+    mom_t, mom_c = D.allgather_moments(mom_t), D.allgather_moments(mom_c)
+    mean_state_t, cov_t = moments_to_mean_cov_rtn(mom_t.cpu().numpy(), ref_t)
+    mean_state_c, cov_c = moments_to_mean_cov_rtn(mom_c.cpu().numpy(), ref_c)
+    cnt = int(packed[0])
+    out = dict(pc=cnt / float(n_total), count=cnt, n=int(n_total), err_count=int(packed[1]), mean_t=mean_state_t.reshape(2, 3),
+               cov_rtn_t=cov_t, mean_c=mean_state_c.reshape(2, 3), cov_rtn_c=cov_c, shard=(lo, hi))
+    if dump is not None:
+        out["dump"] = dump
+    return out
+
+
+def all_pairs_probability(t_xyz, c_xyz, collision_threshold=70.0):
+    """model.py:432-437 with target rows sharded over the ranks: count(||t_i - c_j|| < thr) / (nt * nc)."""
+    rank, world = (torch.distributed.get_rank(), torch.distributed.get_world_size()) if (
+        torch.distributed.is_available() and torch.distributed.is_initialized()) else (0, 1)
+    t_xyz = torch.as_tensor(t_xyz, dtype=torch.float64)
+    c_xyz = torch.as_tensor(c_xyz, dtype=torch.float64)
+    lo, hi = D.shard_range(t_xyz.shape[1], rank, world)
+    cnt = engine.pc_count(t_xyz[:, lo:hi].contiguous(), c_xyz, collision_threshold) if hi > lo else torch.zeros(
+        1, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+    D.allreduce_counts(cnt)
+    return int(cnt[0]) / float(t_xyz.shape[1] * c_xyz.shape[1]), int(cnt[0])

@@ -374,3 +374,60 @@ def test_fp64_peak_probe_runs(eng):
     tf = eng.fp64_peak_tflops(iters=4000, reps=2)
     assert 5.0 < tf < 80.0
     assert eng.launch_count() > 0
+
+
+# ---------------------------------------------------------------------------------------
+def test_mc_pc_kernel_against_oracle_and_shard_invariance(eng):
+    """BASELINE configs[2] at test size: device-side draws (Philox keyed by the global sample index), elements ->
+    SGP4 at TCA -> elementwise miss-distance count + moments.  Checked on IDENTICAL samples (the kernel's dump):
+    states vs the oracle's SGP4, the count bit-exactly, and the count/draws must not depend on the sharding."""
+    from kessler_b200 import montecarlo as MC, workloads as W
+    from kessler_b200.tle import TLE
+    g = common.golden_trace()
+    t_tle = TLE([g["tles"]["t_tle"]["line1"], g["tles"]["t_tle"]["line2"]])
+    # collision-like geometry: the chaser is the target's own orbit observed by a noisier instrument, TCA 0.2 d after
+    # the epoch -- so that a useful fraction of the pairs is inside the 70 m collision radius
+    c_tle = t_tle.copy()
+    tca = t_tle.date_mjd + 0.2
+    st_t = MC.nominal_state_m(t_tle, 0.0).reshape(2, 3)
+    st_c = MC.nominal_state_m(c_tle, 0.0).reshape(2, 3)
+    n = 200000
+    c_cov = W.C_COV_RTN * 4.0
+    r = MC.collision_probability(t_tle, st_t, W.T_COV_RTN, c_tle, st_c, c_cov, tca, n, collision_threshold=70.0, seed=7, n_dump=n)
+    d = r["dump"].cpu().numpy()
+    el_t, el_c, x_t, x_c = d[:, :7].T.copy(), d[:, 7:14].T.copy(), d[:, 14:20], d[:, 20:26]
+    # (1) the draws: sample mean / covariance of (a,e,i,raan,argp,M) vs N(mean, L L^T)
+    mean_t, L_t = MC.element_distribution(t_tle, st_t, W.T_COV_RTN)
+    a_t = (398600.5e9 / (el_t[0] / 60.0) ** 2) ** (1.0 / 3.0)
+    q = np.stack([a_t, el_t[1], el_t[2], el_t[3], el_t[4], el_t[5]], axis=1)
+    sig = np.sqrt(np.diag(L_t @ L_t.T))
+    z = np.linalg.solve(L_t, (q - mean_t).T).T                    # whitened draws: N(0, I)
+    assert np.abs(z.mean(axis=0)).max() < 5.0 / np.sqrt(n) + 2e-3   # + conversion rounding a -> n -> a (1e-9 m vs sigma_a 1e-5 m)
+    assert np.abs(np.cov(z.T) - np.eye(6)).max() < 0.02
+    assert np.array_equal(el_t[6], np.full(n, t_tle._bstar))
+    # (2) SGP4 of those very samples vs the oracle
+    ts_t, ts_c = (tca - t_tle.date_mjd) * 1440.0, (tca - c_tle.date_mjd) * 1440.0
+    ref_t, _ = C.tca_states(el_t, ts_t)
+    ref_c, _ = C.tca_states(el_c, ts_c)
+    assert np.abs(x_t[:, :3] - ref_t[:, :3]).max() < POS_TIGHT_KM * 1e3 and np.abs(x_c[:, :3] - ref_c[:, :3]).max() < POS_TIGHT_KM * 1e3
+    # (3) the count on identical positions: bit-exact integer
+    want = C.pc_count(np.ascontiguousarray(x_t[:, :3].T), np.ascontiguousarray(x_c[:, :3].T), 70.0, 1)
+    assert r["count"] == want and 0 < want < n and r["pc"] == want / n and r["err_count"] == 0
+    # (4) moments -> mean / RTN covariance vs np.cov of the dumped states
+    mean_ref, cov_ref = K.mc_covariance(x_c.reshape(-1, 2, 3))
+    assert np.abs(r["mean_c"] - mean_ref).max() < 1e-3
+    assert np.allclose(r["cov_rtn_c"], cov_ref, rtol=1e-6, atol=1e-9 * np.abs(cov_ref).max())
+    # (5) shard invariance: two half-range launches accumulate to the same count and produce the same draws
+    mean_c, L_c = MC.element_distribution(c_tle, st_c, c_cov)
+    rt, rc = MC.nominal_state_m(t_tle, ts_t), MC.nominal_state_m(c_tle, ts_c)
+    a = eng.mc_pc(mean_t, L_t, t_tle._bstar, ts_t, rt, mean_c, L_c, c_tle._bstar, ts_c, rc, 7, 0, n // 2, 70.0, n_dump=8)
+    b = eng.mc_pc(mean_t, L_t, t_tle._bstar, ts_t, rt, mean_c, L_c, c_tle._bstar, ts_c, rc, 7, n // 2, n - n // 2, 70.0, n_dump=8,
+                  count=a["count"], err_count=a["err_count"])
+    assert int(b["count"][0]) == want
+    assert np.array_equal(a["dump"].cpu().numpy(), d[:8]) and np.array_equal(b["dump"].cpu().numpy(), d[n // 2:n // 2 + 8])
+    # a different seed gives different draws
+    c2 = eng.mc_pc(mean_t, L_t, t_tle._bstar, ts_t, rt, mean_c, L_c, c_tle._bstar, ts_c, rc, 8, 0, 16, 70.0, n_dump=8)
+    assert not np.array_equal(c2["dump"].cpu().numpy(), d[:8])
+    # all-pairs form (reference semantics) through the sharded helper
+    pc, cnt = MC.all_pairs_probability(x_t[:3000, :3].T, x_c[:2000, :3].T, 70.0)
+    assert cnt == C.pc_count(np.ascontiguousarray(x_t[:3000, :3].T), np.ascontiguousarray(x_c[:2000, :3].T), 70.0, 0) > 0
