@@ -290,7 +290,7 @@ def run_ours(args):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    roofline = {"bound": "fp64", "kernel": "k_screen", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+    roofline = {"bound": "fp64", "kernel": "k_screen_warp (fused SGP4 x2 + closed-form TCA search, one warp per trace)", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": None,
                 "peak_source": "measured in this run: dependent-free DFMA probe (ksl_fp64_peak_kernel); MEASURED_PEAKS.json has no FP64 entry",
                 "flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": n * EVALS_PER_TRACE, "launch_ms": scr_s * 1e3,

@@ -29,7 +29,7 @@ class ConjunctionDataMessage:
         self._cov = np.full((2, 6, 6), np.nan)         # [object] RTN, m^2 ...
         if set_defaults:
             self._header["CCSDS_CDM_VERS"] = "1.0"
-            self._header["CREATION_DATE"] = datetime.datetime.utcnow().isoformat()
+            self._header["CREATION_DATE"] = datetime.datetime.now(datetime.timezone.utc).replace(tzinfo=None).isoformat()
             self._meta[0]["OBJECT"], self._meta[1]["OBJECT"] = "OBJECT1", "OBJECT2"
 
     def copy(self):
