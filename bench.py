@@ -290,8 +290,15 @@ def run_ours(args):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of k_screen_warp from the committed ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01b_k_screen_warp_traffic.json")))
+        traffic = tr["dram_bytes_total"] * (n / tr["traces_per_launch"])
+    except Exception:
+        pass
     roofline = {"bound": "fp64", "kernel": "k_screen_warp (fused SGP4 x2 + closed-form TCA search, one warp per trace)", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None,
+                "frac": achieved_tf / peak_tf, "traffic": traffic,
+                "traffic_source": "profiles/r01b_k_screen_warp_traffic.json (ncu --set full at 1e6 traces/launch; scaled by n if --samples differs)",
                 "peak_source": "measured in this run: dependent-free DFMA probe (ksl_fp64_peak_kernel); MEASURED_PEAKS.json has no FP64 entry",
                 "flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": n * EVALS_PER_TRACE, "launch_ms": scr_s * 1e3,
                 "hbm": {"achieved_gbs": n * BYTES_PER_TRACE / scr_s / 1e9, "peak_gbs": hbm_peak,
