@@ -267,8 +267,14 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen(
 
     const int tid = threadIdx.x;
     const bool grid_in_smem = KSL_SCREEN_GRID_SMEM && p.n_coarse <= kMaxGridInSmem;
+    int *s_ja = reinterpret_cast<int *>(s_times + (grid_in_smem ? p.n_coarse : 0));
     if (grid_in_smem)
         for (long long k = tid; k < p.n_coarse; k += kScreenThreads) s_times[k] = p.times_coarse[k];
+    const bool ja_in_smem = p.n_coarse <= kMaxGridInSmem && p.n_fine < 0x7fffffffLL;
+    if (ja_in_smem)
+        for (long long k = tid; k <= p.n_coarse; k += kScreenThreads)
+            s_ja[k] = (k == p.n_coarse) ? (int)p.n_fine : (int)ksl::first_fine_of(k, p.scale, p.n_coarse, p.n_fine);
+    const int *ja_tab = ja_in_smem ? s_ja : nullptr;
 
     for (long long s = blockIdx.x; s < p.n; s += gridDim.x) {
         __syncthreads();  // previous sample's readers are done with s_ct/s_cc/s_pt/s_pc
@@ -323,7 +329,7 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen(
             if (owner) {
                 const int nb = (k == last) ? tid : tid + 1;
                 const double *t0 = s_pt[tid], *t1 = s_pt[nb], *c0 = s_pc[tid], *c1 = s_pc[nb];
-                ksl::segment_search<kMode>(k, last, p.scale, p.n_coarse, p.n_fine, p.thr2, t0, t1, c0, c1, best);
+                ksl::segment_search<kMode>(k, last, p.scale, p.n_coarse, p.n_fine, p.thr2, t0, t1, c0, c1, best, ja_tab);
             }
             __syncthreads();
         }
@@ -369,8 +375,15 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool grid_in_smem = KSL_SCREEN_GRID_SMEM && p.n_coarse <= kMaxGridInSmem;
+    // first fine index of every coarse segment (+ n_fine at the end), behind the time grid in dynamic smem
+    int *s_ja = reinterpret_cast<int *>(s_times + (grid_in_smem ? p.n_coarse : 0));
     if (grid_in_smem)
         for (long long k = tid; k < p.n_coarse; k += kScreenThreads) s_times[k] = p.times_coarse[k];
+    const bool ja_in_smem = p.n_coarse <= kMaxGridInSmem && p.n_fine < 0x7fffffffLL;
+    if (ja_in_smem)
+        for (long long k = tid; k <= p.n_coarse; k += kScreenThreads)
+            s_ja[k] = (k == p.n_coarse) ? (int)p.n_fine : (int)ksl::first_fine_of(k, p.scale, p.n_coarse, p.n_fine);
+    const int *ja_tab = ja_in_smem ? s_ja : nullptr;
     __syncthreads();
 
     double *s_ct = s_c[warp][0], *s_cc = s_c[warp][1];
@@ -432,7 +445,11 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
 #pragma unroll
                     for (int x = 0; x < 3; ++x) { t1[x] = rt[x]; c1[x] = rc[x]; }
                 }
-                ksl::segment_search<kMode>(k, last, p.scale, p.n_coarse, p.n_fine, p.thr2, rt, t1, rc, c1, best);
+#ifndef KSL_EXPERIMENT_SKIP_SEARCH
+                ksl::segment_search<kMode>(k, last, p.scale, p.n_coarse, p.n_fine, p.thr2, rt, t1, rc, c1, best, ja_tab);
+#else   // tuning experiment only: cost of the SGP4 evaluations without the closed-form search
+                best_visit(best, (rt[0] - rc[0]) * (t1[0] - c1[0]) + rt[1] * rc[2], k, p.thr2);
+#endif
             }
         }
         e_t = __reduce_or_sync(0xffffffffu, e_t);
@@ -971,7 +988,8 @@ int ksl_screen(const double *consts_t, const double *epoch_t, const int32_t *ini
         p.target_pos = pos;
         p.target_err = terr;
     }
-    const size_t dyn = (KSL_SCREEN_GRID_SMEM && n_coarse <= kMaxGridInSmem) ? sizeof(double) * (size_t)n_coarse : 0;
+    const size_t dyn = ((KSL_SCREEN_GRID_SMEM && n_coarse <= kMaxGridInSmem) ? sizeof(double) * (size_t)n_coarse : 0) +
+                       ((n_coarse <= kMaxGridInSmem && n_fine < 0x7fffffffLL) ? sizeof(int) * (size_t)(n_coarse + 2) : 0);
     // enough samples to give every resident warp its own trace -> warp-per-trace kernel, else CTA-per-trace
     const bool per_warp = (force & KSL_SCREEN_FORCE_WARP) ||
                           (!(force & KSL_SCREEN_FORCE_CTA) && n >= (long long)sms * KSL_SCREEN_MIN_CTAS * kWarpsPerCta);

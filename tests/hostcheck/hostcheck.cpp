@@ -66,6 +66,9 @@ double hc_wrap_twopi(double x) { return ksl::wrap_twopi(x); }
 // Host emulation of k_screen's data flow (kessler_b200.cu): kThreads "threads" walk the
 // coarse epochs in chunks of kThreads with a one-epoch overlap, each keeping its own
 // running Best (which is what the analytic pruning sees), merged at the end.
+static int s_use_table = 1;
+int hc_set_use_table(int v) { s_use_table = v; return 0; }
+
 int hc_screen(const double *consts_t, const double *epoch_t, int64_t n_t, const double *consts_c, const double *epoch_c,
               int64_t n, const double *times_coarse, int64_t n_coarse, int64_t n_fine, double thr, int mode,
               int64_t *i_min, double *d_min, int64_t *i_conj, double *d_conj, int32_t *err) {
@@ -74,6 +77,9 @@ int hc_screen(const double *consts_t, const double *epoch_t, int64_t n_t, const 
     const double thr2 = thr * thr;
     const long long last = n_coarse - 1;
     std::vector<double> pt(3 * n_coarse), pc(3 * n_coarse);
+    std::vector<int> ja(n_coarse + 1);
+    for (int64_t k = 0; k <= n_coarse; ++k) ja[k] = (k == n_coarse) ? (int)n_fine : (int)ksl::first_fine_of(k, scale, n_coarse, n_fine);
+    const int *ja_tab = (s_use_table ? ja.data() : nullptr);
     for (int64_t s = 0; s < n; ++s) {
         const int64_t it = (n_t == 1) ? 0 : s;
         int et = 0, ec = 0;
@@ -94,9 +100,9 @@ int hc_screen(const double *consts_t, const double *epoch_t, int64_t n_t, const 
                 if (!owner) continue;
                 const long long nb = (k == last) ? k : k + 1;
                 if (mode == 0)
-                    ksl::segment_search<0>(k, last, scale, n_coarse, n_fine, thr2, &pt[3 * k], &pt[3 * nb], &pc[3 * k], &pc[3 * nb], best[tid]);
+                    ksl::segment_search<0>(k, last, scale, n_coarse, n_fine, thr2, &pt[3 * k], &pt[3 * nb], &pc[3 * k], &pc[3 * nb], best[tid], ja_tab);
                 else
-                    ksl::segment_search<1>(k, last, scale, n_coarse, n_fine, thr2, &pt[3 * k], &pt[3 * nb], &pc[3 * k], &pc[3 * nb], best[tid]);
+                    ksl::segment_search<1>(k, last, scale, n_coarse, n_fine, thr2, &pt[3 * k], &pt[3 * nb], &pc[3 * k], &pc[3 * nb], best[tid], ja_tab);
             }
         }
         ksl::Best b = best[0];
