@@ -329,7 +329,10 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen(
             if (owner) {
                 const int nb = (k == last) ? tid : tid + 1;
                 const double *t0 = s_pt[tid], *t1 = s_pt[nb], *c0 = s_pc[tid], *c1 = s_pc[nb];
-                ksl::segment_search<kMode>(k, last, p.scale, p.n_coarse, p.n_fine, p.thr2, t0, t1, c0, c1, best, ja_tab);
+                const double d0[3] = {t0[0] - c0[0], t0[1] - c0[1], t0[2] - c0[2]};
+                const double d1[3] = {t1[0] - c1[0], t1[1] - c1[1], t1[2] - c1[2]};
+                if (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable(d0, d1, best, p.thr2))
+                    ksl::segment_search<kMode>(k, last, p.scale, p.n_coarse, p.n_fine, p.thr2, t0, t1, c0, c1, best, ja_tab);
             }
             __syncthreads();
         }
@@ -433,24 +436,39 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
                 if (!ok_c) e_c |= ksl::sgp4_position_exact(s_cc, 1, ts_c, rc);
                 if (!ok_t) e_t |= ksl::sgp4_position_exact(s_ct, 1, ts_t, rt);
             }
-            double t1[3], c1[3];
+            // stage 1: relative position of this epoch and of the right-hand neighbour (3 shuffles)
+            const bool owner = (k < last && lane < 31) || (k == last);
+            double d0[3], d1[3];
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
-                t1[x] = shfl_down_d(rt[x], 1);
-                c1[x] = shfl_down_d(rc[x], 1);
+                d0[x] = rt[x] - rc[x];
+                d1[x] = shfl_down_d(d0[x], 1);
             }
-            const bool owner = (k < last && lane < 31) || (k == last);
-            if (owner) {
-                if (k == last) {
+            if (k == last) {
 #pragma unroll
-                    for (int x = 0; x < 3; ++x) { t1[x] = rt[x]; c1[x] = rc[x]; }
-                }
-#ifndef KSL_EXPERIMENT_SKIP_SEARCH
-                ksl::segment_search<kMode>(k, last, p.scale, p.n_coarse, p.n_fine, p.thr2, rt, t1, rc, c1, best, ja_tab);
-#else   // tuning experiment only: cost of the SGP4 evaluations without the closed-form search
-                best_visit(best, (rt[0] - rc[0]) * (t1[0] - c1[0]) + rt[1] * rc[2], k, p.thr2);
-#endif
+                for (int x = 0; x < 3; ++x) d1[x] = d0[x];
             }
+#ifndef KSL_EXPERIMENT_SKIP_SEARCH
+            const bool need = owner && (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable(d0, d1, best, p.thr2));
+            // stage 2 (rare): the neighbour's full positions, then the exact candidate evaluation
+            if (__any_sync(0xffffffffu, need)) {
+                double t1[3], c1[3];
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    t1[x] = shfl_down_d(rt[x], 1);
+                    c1[x] = shfl_down_d(rc[x], 1);
+                }
+                if (need) {
+                    if (k == last) {
+#pragma unroll
+                        for (int x = 0; x < 3; ++x) { t1[x] = rt[x]; c1[x] = rc[x]; }
+                    }
+                    ksl::segment_search<kMode>(k, last, p.scale, p.n_coarse, p.n_fine, p.thr2, rt, t1, rc, c1, best, ja_tab);
+                }
+            }
+#else   // tuning experiment only: cost of the SGP4 evaluations without the closed-form search
+            if (owner) best_visit(best, d0[0] * d1[0] + d0[1] * d1[2], k, p.thr2);
+#endif
         }
         e_t = __reduce_or_sync(0xffffffffu, e_t);
         e_c = __reduce_or_sync(0xffffffffu, e_c);

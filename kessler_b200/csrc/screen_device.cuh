@@ -115,37 +115,36 @@ KSL_HD double seg_sq(long long j, long long k, double scale, const double *t0, c
     return sqdist3(dx, dy, dz);
 }
 
+// Cheap, division-free test (most segments end here): with d0, d1 the relative positions (target -
+// chaser, km) at the two ends, q(l) = |d0 + l (d1 - d0)|^2 on l in [0, 1] bounds every fine point of the
+// segment from below.  True = that bound can neither beat the running minimum nor (while no crossing has
+// been found) the threshold, so no fine point of the segment matters.  NaN / inf never skip (an infinite
+// coordinate can still produce NaN fine points through 0 * inf).
+KSL_HD bool segment_skippable(const double d0[3], const double d1[3], const Best &best, double thr2) {
+    const double bx = d1[0] - d0[0], by = d1[1] - d0[1], bz = d1[2] - d0[2];
+    const double a0 = fma_rn(d0[0], d0[0], fma_rn(d0[1], d0[1], d0[2] * d0[2]));   // km^2
+    const double a1 = fma_rn(d0[0], bx, fma_rn(d0[1], by, d0[2] * bz));
+    const double a2 = fma_rn(bx, bx, fma_rn(by, by, bz * bz));
+    const double cur = best.sq;   // m^2; +inf until the first visit
+    // rounding of the exact evaluation vs. the closed form: << 1 m^2 + 1e-9 relative
+    const double want = (fmax(cur, (best.conj_j == kNoIndex) ? thr2 : 0.0) * (1.0 + 1e-9) + 1.0) * 1e-6 + 1e-9 * a0;
+    const double q1 = a0 + (a1 + a1) + a2;
+    const bool rising = a1 >= 0.0, falling = (a1 + a2) <= 0.0;
+    const bool out = rising ? (a0 > want) : (falling ? (q1 > want) : ((a0 - want) * a2 > a1 * a1));
+    return out && (fabs(a0) < INFINITY) && (fabs(a2) < INFINITY);
+}
+
 // Visit segment k (coarse epochs k and k+1; k == last is torch's clamped tail
 // segment with both ends at `last`).  kMode = KSL_SCREEN_BRUTE enumerates every
 // fine point; KSL_SCREEN_ANALYTIC evaluates only the candidates that can hold the
 // segment's minimum or first threshold crossing, and only if the segment can
-// improve on `best` at all.
+// improve on `best` at all.  Callers normally run segment_skippable first.
 // ja_tab (optional): ja_tab[k] = first_fine_of(k) for k = 0..n_coarse-1 and ja_tab[n_coarse] = n_fine,
 // precomputed once per CTA in shared memory; NULL = evaluate first_fine_of on the fly.
 template <int kMode>
 KSL_HD void segment_search(long long k, long long last, double scale, long long n_coarse, long long n_fine, double thr2,
                            const double *t0, const double *t1, const double *c0, const double *c1, Best &best,
                            const int *ja_tab = nullptr) {
-    // D(l) = A + l*B in metres; q(l) = a0 + 2 a1 l + a2 l^2
-    const double ax = (t0[0] - c0[0]) * 1e3, ay = (t0[1] - c0[1]) * 1e3, az = (t0[2] - c0[2]) * 1e3;
-    const double bx = (t1[0] - c1[0]) * 1e3 - ax, by = (t1[1] - c1[1]) * 1e3 - ay, bz = (t1[2] - c1[2]) * 1e3 - az;
-    const double a0 = ax * ax + ay * ay + az * az;
-    const double a1 = ax * bx + ay * by + az * bz;
-    const double a2 = bx * bx + by * by + bz * bz;
-    const double cur = (best.j == kNoIndex) ? INFINITY : best.sq;
-    // rounding of the exact evaluation vs. the closed form: << 1 m^2 + 1e-9 relative
-    const double slack = 1.0 + 1e-9 * fmax(a0, cur < INFINITY ? cur : 0.0);
-    if (kMode != KSL_SCREEN_BRUTE) {
-        // Division-free early exit (most segments): a lower bound of q over l in [0, 1], which contains the
-        // segment's [la, lb].  If even that cannot beat the running minimum nor the threshold (when no crossing
-        // has been found yet), no fine point of this segment matters.  NaN / inf compare false and fall through.
-        const double q1 = a0 + (a1 + a1) + a2;
-        const double want = fmax(cur, (best.conj_j == kNoIndex) ? thr2 : 0.0) + slack;
-        const bool rising = a1 >= 0.0, falling = (a1 + a2) <= 0.0;
-        const bool out = rising ? (a0 > want) : (falling ? (q1 > want) : ((a0 - want) * a2 > a1 * a1));
-        // (an infinite coordinate can still produce NaN fine points through 0 * inf: never skipped)
-        if (out && (fabs(a0) < INFINITY) && (fabs(a2) < INFINITY)) return;
-    }
     long long ja, jb;
     if (ja_tab) {
         ja = ja_tab[k];
@@ -157,9 +156,17 @@ KSL_HD void segment_search(long long k, long long last, double scale, long long 
     if (ja > jb) return;
     bool brute = (kMode == KSL_SCREEN_BRUTE);
     if (!brute) {
+        // D(l) = A + l*B in metres; q(l) = a0 + 2 a1 l + a2 l^2
+        const double ax = (t0[0] - c0[0]) * 1e3, ay = (t0[1] - c0[1]) * 1e3, az = (t0[2] - c0[2]) * 1e3;
+        const double bx = (t1[0] - c1[0]) * 1e3 - ax, by = (t1[1] - c1[1]) * 1e3 - ay, bz = (t1[2] - c1[2]) * 1e3 - az;
+        const double a0 = ax * ax + ay * ay + az * az;
+        const double a1 = ax * bx + ay * by + az * bz;
+        const double a2 = bx * bx + by * by + bz * bz;
         if (!(fabs(a0) < INFINITY) || !(fabs(a2) < INFINITY)) {
             brute = true;  // NaN / inf states: reference semantics by enumeration
         } else {
+            const double cur = best.sq;
+            const double slack = 1.0 + 1e-9 * fmax(a0, cur < INFINITY ? cur : 0.0);
             const double la = fmin(fmax((double)ja * scale - (double)k, 0.0), 1.0);
             const double lb = fmin(fmax((double)jb * scale - (double)k, 0.0), 1.0);
             const double lv = (a2 > 0.0) ? fmin(fmax(-a1 / a2, la), lb) : la;

@@ -99,6 +99,9 @@ int hc_screen(const double *consts_t, const double *epoch_t, int64_t n_t, const 
                 const bool owner = (k < last && tid < kThreads - 1) || (k == last);
                 if (!owner) continue;
                 const long long nb = (k == last) ? k : k + 1;
+                const double d0[3] = {pt[3 * k] - pc[3 * k], pt[3 * k + 1] - pc[3 * k + 1], pt[3 * k + 2] - pc[3 * k + 2]};
+                const double d1[3] = {pt[3 * nb] - pc[3 * nb], pt[3 * nb + 1] - pc[3 * nb + 1], pt[3 * nb + 2] - pc[3 * nb + 2]};
+                if (mode == 0 && ksl::segment_skippable(d0, d1, best[tid], thr2)) continue;
                 if (mode == 0)
                     ksl::segment_search<0>(k, last, scale, n_coarse, n_fine, thr2, &pt[3 * k], &pt[3 * nb], &pc[3 * k], &pc[3 * nb], best[tid], ja_tab);
                 else
