@@ -448,7 +448,6 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
 #pragma unroll
                 for (int x = 0; x < 3; ++x) d1[x] = d0[x];
             }
-#ifndef KSL_EXPERIMENT_SKIP_SEARCH
             const bool need = owner && (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable(d0, d1, best, p.thr2));
             // stage 2 (rare): the neighbour's full positions, then the exact candidate evaluation
             if (__any_sync(0xffffffffu, need)) {
@@ -466,9 +465,6 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
                     ksl::segment_search<kMode>(k, last, p.scale, p.n_coarse, p.n_fine, p.thr2, rt, t1, rc, c1, best, ja_tab);
                 }
             }
-#else   // tuning experiment only: cost of the SGP4 evaluations without the closed-form search
-            if (owner) best_visit(best, d0[0] * d1[0] + d0[1] * d1[2], k, p.thr2);
-#endif
         }
         e_t = __reduce_or_sync(0xffffffffu, e_t);
         e_c = __reduce_or_sync(0xffffffffu, e_c);

@@ -303,6 +303,49 @@ def test_screen_cta_and_warp_decompositions_agree(eng):
         assert np.array_equal(r["err"], ref["err"])
 
 
+def test_screen_full_size_properties(eng):
+    """BASELINE configs[1] at its full size (1e6 perturbed samples of the default LEO pair, the bench workload),
+    checked through size-independent properties: the warp-per-trace kernel on the full batch equals the
+    CTA-per-trace kernel and the brute-force enumeration on random subsets, the oracle on a few traces, the
+    summary counts equal a NumPy recount, and splitting the batch does not change any result."""
+    from kessler_b200 import _native as NV, workloads as W
+    t_tle, c_tle = W.pair_a()
+    states = []
+    for t in (t_tle, c_tle):
+        c, _ = eng.sgp4_init(t.elements().reshape(7, 1))
+        rv, _ = eng.sgp4_prop(c, [0.0])
+        states.append(_np(rv)[0, 0].reshape(2, 3) * 1e3)
+    n = 1000000
+    wl = W.config2_batch(n, seed=1, rank=0, state_t=states[0], state_c=states[1])
+    elt, elc = wl["elems_t"].numpy(), wl["elems_c"].numpy()
+    ept, epc = np.full(n, wl["epoch_t"]), np.full(n, wl["epoch_c"])
+    tc, nf = wl["times_coarse"], wl["n_fine"]
+    full = _screen(eng, elt, ept, elc, epc, tc, nf, 5e3, 0)
+    assert (full["err"] == 0).all() and (full["i_min"] >= 0).all() and np.isfinite(full["d_min"]).all()
+    rng = np.random.default_rng(0)
+    sub = np.sort(rng.choice(n, 3000, replace=False))
+    pick = lambda a: np.ascontiguousarray(a[:, sub])
+    cta = _screen(eng, pick(elt), ept[sub], pick(elc), epc[sub], tc, nf, 5e3, NV.SCREEN_FORCE_CTA)
+    brute = _screen(eng, pick(elt), ept[sub], pick(elc), epc[sub], tc, nf, 5e3, 1)
+    for other in (cta, brute):
+        assert np.array_equal(other["i_min"], full["i_min"][sub]) and np.array_equal(other["i_conj"], full["i_conj"][sub])
+        assert np.array_equal(other["d_min"], full["d_min"][sub])
+    few = sub[:6]
+    ref = C.screen(np.ascontiguousarray(elt[:, few]), ept[few], np.ascontiguousarray(elc[:, few]), epc[few], tc, nf, 5e3)
+    assert np.array_equal(ref["i_min"], full["i_min"][few]) and np.abs(ref["d_min"] - full["d_min"][few]).max() < 1e-3
+    # split invariance (what sharding over GPUs relies on)
+    h = n // 2
+    a = _screen(eng, np.ascontiguousarray(elt[:, :h]), ept[:h], np.ascontiguousarray(elc[:, :h]), epc[:h], tc, nf, 5e3, 0)
+    assert np.array_equal(a["i_min"], full["i_min"][:h]) and np.array_equal(a["d_min"], full["d_min"][:h])
+    # summary = NumPy recount
+    res = {k: torch.from_numpy(v).cuda() for k, v in full.items()}
+    counts, moments = eng.screen_summary(res, 70.0)
+    counts, moments = _np(counts), _np(moments)
+    assert counts[0] == n and counts[2] == (full["i_conj"] >= 0).sum() and counts[4] == (full["d_min"] < 70.0).sum()
+    assert moments[0] == n and moments[3] == full["d_min"].min()
+    assert moments[1] == pytest.approx(full["d_min"].sum(), rel=1e-12)
+
+
 def test_screen_host_and_summary(eng):
     elt, ept, elc, epc, times, _ = _golden_batch(500, 9)
     tc = np.ascontiguousarray(times[::100])
