@@ -114,19 +114,56 @@ class _Replay:
         return getattr(self._fn, k)
 
 
+def _round_decimals(x, decimals):
+    """float('{:.{d}f}'.format(v)) for every v, vectorised: rint(v * 10^d) / 10^d agrees with the correctly
+    rounded decimal formatting except when v * 10^d sits within binary rounding noise of a half-integer; those
+    (rare) entries are formatted one by one."""
+    x = np.asarray(x, dtype=np.float64)
+    scaled = x * (10.0 ** decimals)
+    out = np.rint(scaled) / (10.0 ** decimals)
+    frac = np.abs(scaled - np.floor(scaled) - 0.5)
+    # x * 10^d carries one rounding (<= 1.2e-16 relative): only entries that close to a tie can differ
+    risky = np.nonzero(~(frac > 1e-14 * np.maximum(1.0, np.abs(scaled))) | ~np.isfinite(scaled))[0]
+    for i in risky:
+        out[i] = float("{:.{d}f}".format(x[i], d=decimals))
+    return out
+
+
+def _quantize_exp_field(x):
+    """TLE 'decimal point assumed' field (B*): 5-digit mantissa in [0.1, 1) and a one-digit exponent."""
+    from .tle import _format_exp_field, _parse_exp_field
+    x = np.asarray(x, dtype=np.float64)
+    out = np.zeros_like(x)
+    nz = np.nonzero((x != 0.0) & np.isfinite(x))[0]
+    if len(nz):
+        ax = np.abs(x[nz])
+        ex = np.floor(np.log10(ax)).astype(np.int64) + 1
+        scaled = ax / np.array([10.0 ** int(e) for e in range(-300, 301)])[np.clip(ex, -300, 300) + 300] * 1e5   # as _format_exp_field
+        mant = np.rint(scaled)
+        frac = np.abs(scaled - np.floor(scaled) - 0.5)
+        # decade edges, half-way mantissas and exponents outside one digit go through the text formatter
+        risky = (frac < 1e-9) | (mant >= 100000) | (mant < 10000) | (np.abs(ex) > 8)
+        pow10 = np.array([10.0 ** e for e in range(-9, 10)])          # Python's pow, as tle._parse_exp_field uses
+        val = np.sign(x[nz]) * (mant / 1e5) * pow10[np.clip(ex, -9, 9) + 9]
+        for i in np.nonzero(risky)[0]:
+            val[i] = _parse_exp_field(_format_exp_field(x[nz][i]))
+        # (mant / 1e5) * 10^ex must equal float('0.' + digits) * 10^ex: same two roundings as the parser
+        out[nz] = val
+    return out
+
+
 def quantize_sgp4_inputs(mean_motion_rad_s, ecc, incl, raan, argp, mean_anomaly, b_star):
     """What ``TLE(dict)`` does to the SGP4 inputs, vectorised: every element is written into the TLE
     text (8.4f degrees, 7-digit eccentricity, 11.8f rev/day, 5-digit B* mantissa) and parsed back
     (tests/test_model_host.py checks this against TLE(dict) element-wise).
     Returns SGP4 element SoA [7, n] (rad/min, rad)."""
     deg = math.pi / 180.0
-    q4 = lambda x: np.array([float("{:8.4f}".format(v)) for v in np.asarray(x, dtype=np.float64) / deg]) * deg
-    rev = np.array([float("{:11.8f}".format(v)) for v in np.asarray(mean_motion_rad_s, dtype=np.float64) * 86400.0 / (2 * math.pi)])
-    e = np.array([float("0." + ("9999999" if "{:.7f}".format(v).startswith("1") else "{:.7f}".format(v)[2:9]))
-                  for v in np.asarray(ecc, dtype=np.float64)])
-    from .tle import _format_exp_field, _parse_exp_field
-    b = np.array([_parse_exp_field(_format_exp_field(v)) for v in np.asarray(b_star, dtype=np.float64)])
-    return np.stack([rev * (2 * math.pi) / 86400.0 * 60.0, e, q4(incl), q4(raan), q4(argp), q4(mean_anomaly), b])
+    q4 = lambda x: _round_decimals(np.asarray(x, dtype=np.float64) / deg, 4) * deg
+    rev = _round_decimals(np.asarray(mean_motion_rad_s, dtype=np.float64) * 86400.0 / (2 * math.pi), 8)
+    e = _round_decimals(ecc, 7)
+    e = np.where(e >= 1.0, 0.9999999, e)
+    return np.stack([rev * (2 * math.pi) / 86400.0 * 60.0, e, q4(incl), q4(raan), q4(argp), q4(mean_anomaly),
+                     _quantize_exp_field(b_star)])
 
 
 class Conjunction:
@@ -469,7 +506,7 @@ class Conjunction:
                        argument_of_perigee=np.full(n, given.argument_of_perigee), b_star=np.full(n, given.b_star))
             el = np.repeat(base[:, None], n, axis=1)
             deg = math.pi / 180.0
-            el[5] = np.array([float("{:8.4f}".format(v)) for v in ma / deg]) * deg
+            el[5] = _round_decimals(ma / deg, 4) * deg
             raw['_sites'] = ['mean_anomaly']
             return raw, el, np.full(n, given.date_mjd)
         raw = dict(mean_motion=self._sample_mixture(pr['mean_motion_prior'], n), mean_anomaly=ma,
@@ -597,7 +634,7 @@ class ConjunctionSimplified(Conjunction):
         idx = Categorical(torch.tensor(range(len(self._tles)))).sample((n,)).numpy()
         base = np.stack([t.elements() for t in self._tles], axis=1)[:, idx]
         deg = math.pi / 180.0
-        base[5] = np.array([float("{:8.4f}".format(v)) for v in ma / deg]) * deg
+        base[5] = _round_decimals(ma / deg, 4) * deg
         pick = lambda attr: np.array([getattr(t, attr) for t in self._tles], dtype=np.float64)[idx]
         raw = dict(mean_anomaly=ma, sampled_index=idx, mean_motion=pick('mean_motion'), eccentricity=pick('eccentricity'),
                    _sites=['mean_anomaly', 'sampled_index'])

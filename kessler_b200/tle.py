@@ -138,8 +138,10 @@ def _format_exp_field(x):
     if mant >= 100000:
         mant //= 10
         ex += 1
-    if mant == 0:
+    if mant == 0 or ex < -9:       # below the field's range (one exponent digit): reads back as zero
         return " 00000-0"
+    if ex > 9:                      # above it: saturate
+        mant, ex = 99999, 9
     return "{}{:05d}{}{:d}".format(sign, mant, "-" if ex <= 0 else "+", abs(ex))
 
 
