@@ -195,6 +195,19 @@ int ksl_mc_pc(const double *mean_t, const double *chol_t, double bstar_t, double
               double *moments_t, double *moments_c, unsigned long long *err_count, double *dump, int64_t n_dump,
               void *workspace, void *stream);
 
+/* ---- dsgp4.newton_method(tle, time_mjd)  (model.py:399,411), batched ---------------
+ * For each of n problems: the mean elements y = (no_kozai rad/min, e, i, raan, argp, M) whose SGP4 state at
+ * tsince = 0 (with the given B*) equals target_km[6] (km, km/s, TEME).  resid = final ||F|| (km; km/s x 1000),
+ * iters = Newton iterations used.  The caller builds the new TLE (epoch = observation time) from y. */
+int ksl_newton_elements(const double *target_km, const double *bstar, int64_t n, int max_iter, double tol, double *y,
+                        double *resid, int32_t *iters, void *stream);
+
+/* ---- util.from_cartesian_to_keplerian + util.keplerian_cartesian_partials  (util.py:187-302), batched
+ * states [n][6] (x,y,z,vx,vy,vz; units of mu) -> elements [n][6] = (a, e, i, Omega, omega, M) and
+ * jac [n][6][6], jac[i][j] = d element_i / d state_j (exact: forward-mode dual numbers, no finite
+ * differences).  NaN rows for e >= 1. */
+int ksl_kepler_partials(const double *states, int64_t n, double mu, double *elements, double *jac, void *stream);
+
 /* ---- end-to-end entry points: HOST buffers in, HOST buffers out ----------------
  * What a Kessler-side binding calls for a batch of traces.  Allocates (and caches
  * per device) its staging and scratch buffers; synchronous.

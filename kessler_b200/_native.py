@@ -15,6 +15,7 @@ _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("KSL_LIB_PATH") or os.path.join(_PKG, "lib", "libkessler_b200.so")   # env override: tuning experiments only
 SRC = os.path.join(_PKG, "csrc", "kessler_b200.cu")
 HEADERS = [os.path.join(_PKG, "csrc", "sgp4_device.cuh"), os.path.join(_PKG, "csrc", "screen_device.cuh"),
+           os.path.join(_PKG, "csrc", "kepler_device.cuh"),
            os.path.join(_ROOT, "include", "kessler_b200.h")]
 
 NCONST = 36
@@ -30,7 +31,7 @@ PAIR_ELEMENTWISE = 1
 ERR_ECC, ERR_MEANMOTION, ERR_SEMILATUS, ERR_DECAYED, ERR_DEEPSPACE = 1, 2, 4, 8, 16
 ERR_CHASER_SHIFT = 8
 
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-diag-suppress", "20091",
               "-Xcompiler", "-fPIC", "-shared"]
 
 
@@ -82,6 +83,8 @@ _SIGNATURES = {
     "ksl_mc_pc_ws": [_i64],
     "ksl_mc_pc": [_vp, _vp, _f64, _f64, _vp, _vp, _vp, _f64, _f64, _vp, ctypes.c_uint64, _i64, _i64, _f64, _f64, _vp,
                   _vp, _vp, _vp, _vp, _i64, _vp, _vp],
+    "ksl_newton_elements": [_vp, _vp, _i64, _int, _f64, _vp, _vp, _vp, _vp],
+    "ksl_kepler_partials": [_vp, _i64, _f64, _vp, _vp, _vp],
     "ksl_screen_host": [_int, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _f64, _int, _f64,
                         _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ksl_host_cache_free": [],

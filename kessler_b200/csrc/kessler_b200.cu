@@ -17,6 +17,7 @@
 
 #include "sgp4_device.cuh"
 #include "screen_device.cuh"
+#include "kepler_device.cuh"
 
 namespace {
 
@@ -865,6 +866,125 @@ __global__ void __launch_bounds__(kMcThreads) k_mc_pc(const McObject tgt, const 
 }
 
 // ------------------------------------------------------------------------------------
+// K7  mean elements from an osculating state (dsgp4.newton_method as Kessler calls it, model.py:399,411):
+// find (no_kozai, e, i, raan, argp, M) whose SGP4 state at tsince = 0 equals the target state.  One thread
+// per problem; Newton in the non-singular unknowns z = (n, e sin w, e cos w, i, raan, w + M) with a central-
+// difference Jacobian (12 SGP4 evaluations), a 6x6 elimination with partial pivoting and a halving line search
+// (6 evaluations) per iteration -- everything in registers / local memory, no host round trip per iteration.
+// K8  Kepler elements + exact Jacobian by forward-mode dual numbers (kepler_device.cuh).
+// ------------------------------------------------------------------------------------
+__device__ __noinline__ void newton_residual(const double z[6], double bstar, const double target[6], double F[6]) {
+    double el[7];
+    const double ecc = sqrt(z[1] * z[1] + z[2] * z[2]);
+    const double w = atan2(z[1], z[2]);
+    el[0] = z[0]; el[1] = ecc; el[2] = z[3]; el[3] = z[4]; el[4] = w; el[5] = z[5] - w; el[6] = bstar;
+    double c[KSL_NCONST], x[6];
+    ksl::sgp4_init(el, [&](int k, double v) { c[k] = v; });
+    ksl::sgp4_prop<true>([&](int k) { return c[k]; }, 0.0, x, x + 3);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        F[q] = x[q] - target[q];
+        F[3 + q] = (x[3 + q] - target[3 + q]) * 1.0e3;   // weigh km/s like km over ~1000 s
+    }
+}
+
+__device__ __forceinline__ double norm6(const double F[6]) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) s += F[q] * F[q];
+    return sqrt(s);
+}
+
+__global__ void __launch_bounds__(64) k_newton(const double *__restrict__ target_km, const double *__restrict__ bstar_in,
+                                               long long n, int max_iter, double tol, double mu_km,
+                                               double *__restrict__ y_out, double *__restrict__ resid, int *__restrict__ iters) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double target[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) target[q] = target_km[6 * i + q];
+    const double bstar = bstar_in[i];
+    double kep[6];
+    const bool ok = ksl::cartesian_to_keplerian<double>(target, target + 3, mu_km, kep);
+    double z[6] = {sqrt(mu_km / (kep[0] * kep[0] * kep[0])) * 60.0, kep[1] * sin(kep[4]), kep[1] * cos(kep[4]), kep[2], kep[3],
+                   kep[4] + kep[5]};
+    const double h[6] = {1e-9, 1e-8, 1e-8, 1e-8, 1e-8, 1e-8};
+    double F[6], res = INFINITY;
+    int it = 0;
+    if (ok) {
+        for (; it < max_iter; ++it) {
+            newton_residual(z, bstar, target, F);
+            res = norm6(F);
+            if (!(res >= tol) || !(res < INFINITY)) break;
+            double A[6][7];   // [J | -F]
+            for (int col = 0; col < 6; ++col) {
+                double zp[6], zm[6], Fp[6], Fm[6];
+                for (int q = 0; q < 6; ++q) { zp[q] = z[q]; zm[q] = z[q]; }
+                zp[col] += h[col];
+                zm[col] -= h[col];
+                newton_residual(zp, bstar, target, Fp);
+                newton_residual(zm, bstar, target, Fm);
+                for (int row = 0; row < 6; ++row) A[row][col] = (Fp[row] - Fm[row]) / (2.0 * h[col]);
+            }
+            for (int row = 0; row < 6; ++row) A[row][6] = -F[row];
+            bool singular = false;
+            for (int col = 0; col < 6; ++col) {   // elimination with partial pivoting
+                int piv = col;
+                for (int row = col + 1; row < 6; ++row)
+                    if (fabs(A[row][col]) > fabs(A[piv][col])) piv = row;
+                if (!(fabs(A[piv][col]) > 0.0)) { singular = true; break; }
+                if (piv != col)
+                    for (int q = col; q < 7; ++q) { const double tmp = A[col][q]; A[col][q] = A[piv][q]; A[piv][q] = tmp; }
+                for (int row = col + 1; row < 6; ++row) {
+                    const double m = A[row][col] / A[col][col];
+                    for (int q = col; q < 7; ++q) A[row][q] -= m * A[col][q];
+                }
+            }
+            if (singular) break;
+            double dz[6];
+            for (int row = 5; row >= 0; --row) {
+                double acc = A[row][6];
+                for (int q = row + 1; q < 6; ++q) acc -= A[row][q] * dz[q];
+                dz[row] = acc / A[row][row];
+            }
+            double best_norm = INFINITY, frac = 1.0, best_frac = 0.0;
+            for (int m = 0; m < 6; ++m, frac *= 0.5) {   // damped step
+                double zc[6], Fc[6];
+                for (int q = 0; q < 6; ++q) zc[q] = z[q] + frac * dz[q];
+                newton_residual(zc, bstar, target, Fc);
+                const double nn = norm6(Fc);
+                if (nn < best_norm) { best_norm = nn; best_frac = frac; }
+            }
+            if (!(best_norm < res)) { ++it; break; }   // no progress: rounding floor
+            for (int q = 0; q < 6; ++q) z[q] += best_frac * dz[q];
+        }
+        if (it == max_iter) {
+            newton_residual(z, bstar, target, F);
+            res = norm6(F);
+        }
+    }
+    const double ecc = sqrt(z[1] * z[1] + z[2] * z[2]);
+    const double w = atan2(z[1], z[2]);
+    double *y = y_out + 6 * i;
+    y[0] = z[0]; y[1] = ecc; y[2] = z[3]; y[3] = z[4]; y[4] = w; y[5] = z[5] - w;
+    if (!ok) for (int q = 0; q < 6; ++q) y[q] = NAN;
+    resid[i] = ok ? res : NAN;
+    iters[i] = it;
+}
+
+__global__ void __launch_bounds__(128) k_kepler_partials(const double *__restrict__ states, long long n, double mu,
+                                                         double *__restrict__ elements, double *__restrict__ jac) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double st[6], el[6], J[36];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) st[q] = states[6 * i + q];
+    const bool ok = ksl::kepler_elements_and_partials(st, mu, el, J);
+    for (int q = 0; q < 6; ++q) elements[6 * i + q] = ok ? el[q] : NAN;
+    for (int q = 0; q < 36; ++q) jac[36 * i + q] = ok ? J[q] : NAN;
+}
+
+// ------------------------------------------------------------------------------------
 // FP64 peak probe: 8 independent DFMA chains per thread
 // ------------------------------------------------------------------------------------
 __global__ void k_fp64_peak(long long iters, double *__restrict__ sink) {
@@ -1169,6 +1289,24 @@ int ksl_mc_pc(const double *mean_t, const double *chol_t, double bstar_t, double
     KSL_LAUNCH_CHECK();
     if (moments_c != moments_t + KSL_NMOMENT)
         KSL_CUDA(cudaMemcpyAsync(moments_c, moments_t + KSL_NMOMENT, sizeof(double) * KSL_NMOMENT, cudaMemcpyDeviceToDevice, S(stream)));
+    return KSL_OK;
+}
+
+int ksl_newton_elements(const double *target_km, const double *bstar, int64_t n, int max_iter, double tol, double *y,
+                        double *resid, int32_t *iters, void *stream) {
+    if (n < 0 || max_iter < 0 || (n > 0 && (!target_km || !bstar || !y || !resid || !iters)))
+        return fail(KSL_E_ARG, "ksl_newton_elements: bad argument");
+    if (n == 0) return KSL_OK;
+    k_newton<<<(unsigned)((n + 63) / 64), 64, 0, S(stream)>>>(target_km, bstar, n, max_iter, tol, 398600.5, y, resid, iters);
+    KSL_LAUNCH_CHECK();
+    return KSL_OK;
+}
+
+int ksl_kepler_partials(const double *states, int64_t n, double mu, double *elements, double *jac, void *stream) {
+    if (n < 0 || (n > 0 && (!states || !elements || !jac))) return fail(KSL_E_ARG, "ksl_kepler_partials: bad argument");
+    if (n == 0) return KSL_OK;
+    k_kepler_partials<<<(unsigned)((n + 127) / 128), 128, 0, S(stream)>>>(states, n, mu, elements, jac);
+    KSL_LAUNCH_CHECK();
     return KSL_OK;
 }
 

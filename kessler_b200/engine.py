@@ -198,6 +198,33 @@ def mc_pc(mean_t, chol_t, bstar_t, tsince_t, ref_t, mean_c, chol_c, bstar_c, tsi
     return dict(count=count, moments_t=moments[:N.NMOMENT], moments_c=moments[N.NMOMENT:], err_count=err_count, dump=dump)
 
 
+# --- dsgp4.newton_method / kessler.util Kepler partials, batched ---------------------------------
+def newton_elements(target_km, bstar, max_iter=50, tol=1e-12):
+    """target_km [n, 6] (km, km/s), bstar [n] -> (y [n, 6] mean elements, resid [n], iters [n] int32)."""
+    dev = _dev()
+    target_km = _cf64(target_km, dev).reshape(-1, 6)
+    n = target_km.shape[0]
+    bstar = _cf64(bstar, dev).reshape(-1)
+    assert bstar.numel() == n
+    y = torch.empty((n, 6), dtype=F64, device=dev)
+    resid = torch.empty(n, dtype=F64, device=dev)
+    iters = torch.empty(n, dtype=torch.int32, device=dev)
+    N.check(N.lib().ksl_newton_elements(ptr(target_km), ptr(bstar), n, int(max_iter), float(tol), ptr(y), ptr(resid), ptr(iters),
+                                        stream_ptr()), "ksl_newton_elements")
+    return y, resid, iters
+
+
+def kepler_partials(states, mu):
+    """states [n, 6] -> (elements [n, 6], jac [n, 6, 6])."""
+    dev = _dev()
+    states = _cf64(states, dev).reshape(-1, 6)
+    n = states.shape[0]
+    el = torch.empty((n, 6), dtype=F64, device=dev)
+    jac = torch.empty((n, 6, 6), dtype=F64, device=dev)
+    N.check(N.lib().ksl_kepler_partials(ptr(states), n, float(mu), ptr(el), ptr(jac), stream_ptr()), "ksl_kepler_partials")
+    return el, jac
+
+
 # --- end-to-end: host buffers in / out -----------------------------------------------------
 def screen_host(elems_t, epoch_t, elems_c, epoch_c, times_coarse, n_fine, thr_m, mode=N.SCREEN_ANALYTIC,
                 collision_thr_m=70.0, device=None, out=None, want_summary=True):

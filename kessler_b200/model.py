@@ -337,7 +337,9 @@ class Conjunction:
         T[0:3, 0:3] = R
         T[3:, 3:] = R
         C_xyz = np.matmul(np.matmul(T.T, np.diag(cov_matrix_diagonal_rtn)), T)
-        dtle_dx = util.keplerian_cartesian_partials(torch.tensor(np.asarray(state_xyz)), self._mu_earth)
+        # util.keplerian_cartesian_partials (six autograd passes on the CPU) -> one dual-number kernel
+        _, jac = engine.kepler_partials(np.asarray(state_xyz, dtype=np.float64).reshape(1, 6), self._mu_earth)
+        dtle_dx = jac[0].cpu().numpy()
         cov = np.matmul(np.matmul(dtle_dx, C_xyz), dtle_dx.T)
         if ~torch.all(torch.from_numpy(np.real(np.linalg.eig(cov)[0])) > 1e-11):
             cov = 0.5 * (cov + cov.T)

@@ -140,61 +140,21 @@ def newton_method(tle_0, time_mjd, max_iter=50, new_tol=1e-12, verbose=False, ta
     dsgp4's source is absent, so this is restated from its documented behaviour:
     osculating Kepler elements as the initial guess, Newton iterations on the six mean elements until
     ||F|| < new_tol, result built through ``TLE(dict)`` (hence text-quantised SGP4 inputs).  dsgp4
-    differentiates through SGP4 with autograd; here the 6x6 Jacobian is a central difference over ONE
-    batched GPU call per iteration (13 records).  PARITY UNPINNED for this function: no reference
-    fixture records a newton_method output; it is "next" scope."""
-    from . import util as kutil
+    differentiates through SGP4 with autograd; here the whole solve runs in ONE kernel launch
+    (ksl_newton_elements: Newton in non-singular unknowns, central-difference Jacobian, damped steps).
+    PARITY UNPINNED for this function in isolation (no reference fixture records a newton_method
+    output); end to end it is pinned by the golden trace's first CDM (tests/test_gpu_model.py)."""
     epoch0 = from_datetime_to_mjd(tle_0._epoch)
     if target_state is None:
         target = propagate(tle_0, (time_mjd - epoch0) * 1440.0).numpy().reshape(6)
     else:
         target = np.asarray(target_state, dtype=np.float64).reshape(6)
-    mu_km = 398600.5
-    a, e, i, Om, om, M = [float(x) for x in kutil.from_cartesian_to_keplerian(torch.tensor(target[:3]), torch.tensor(target[3:]), mu_km)]
-    # Solve in non-singular unknowns z = (n, e sin w, e cos w, i, Omega, w + M): for the near-circular
-    # orbits of the LEO population, w and M are individually ill-determined (only w + M is), and
-    # Newton in (w, M) oscillates.
-    z = np.array([math.sqrt(mu_km / a ** 3) * 60.0, e * math.sin(om), e * math.cos(om), i, Om, om + M])
-
-    def to_y(zz):
-        ecc = np.hypot(zz[1], zz[2])
-        w = np.arctan2(zz[1], zz[2])
-        return np.stack([zz[0], ecc, zz[3], zz[4], w, zz[5] - w])
-
-    scale = np.array([1.0, 1.0, 1.0, 1.0e3, 1.0e3, 1.0e3])          # weigh km/s like km over ~1000 s
-    h = np.array([1e-9, 1e-8, 1e-8, 1e-8, 1e-8, 1e-8])
-
-    def residuals(zcols):
-        st, _ = _states_at_epoch(to_y(zcols), tle_0._bstar)
-        return (st - target[None, :]) * scale[None, :]
-
-    tol, it = np.inf, 0
-    F = None
-    while it < max_iter:
-        cols = np.repeat(z[:, None], 13, axis=1)
-        for k in range(6):
-            cols[k, 1 + 2 * k] += h[k]
-            cols[k, 2 + 2 * k] -= h[k]
-        R = residuals(cols)
-        F = R[0]
-        tol = float(np.linalg.norm(F))
-        if verbose:
-            print(f"newton_method: iteration {it}, ||F|| = {tol:.3e}")
-        if not np.isfinite(tol) or tol < new_tol:
-            break
-        J = np.stack([(R[1 + 2 * k] - R[2 + 2 * k]) / (2 * h[k]) for k in range(6)], axis=1)
-        dz = np.linalg.lstsq(J, -F, rcond=None)[0]
-        # damped step: one batched evaluation of the candidates z + dz / 2^m
-        fracs = 0.5 ** np.arange(6)
-        cand = z[:, None] + dz[:, None] * fracs[None, :]
-        norms = np.linalg.norm(residuals(cand), axis=1)
-        norms = np.where(np.isfinite(norms), norms, np.inf)
-        best = int(np.argmin(norms))
-        it += 1
-        if not norms[best] < tol:          # no progress: converged to the rounding floor
-            break
-        z = cand[:, best]
-    y = to_y(z)
+    y_dev, resid, iters = engine.newton_elements(target.reshape(1, 6), [tle_0._bstar], max_iter=max_iter, tol=new_tol)
+    y = y_dev[0].cpu().numpy()
+    if verbose:
+        print(f"newton_method: {int(iters[0])} iterations, ||F|| = {float(resid[0]):.3e}")
+    if not np.all(np.isfinite(y)):
+        raise RuntimeError("newton_method: the target state is not an elliptic orbit")
     dt = from_mjd_to_datetime(time_mjd)
     d = dict(tle_0._data)
     d.update(epoch_year=dt.year, epoch_days=from_mjd_to_epoch_days_after_1_jan(time_mjd),

@@ -168,6 +168,14 @@ def keplerian_cartesian_partials(state, mu):
     return np.stack(rows)
 
 
+def keplerian_cartesian_partials_batch(states, mu):
+    """Batched counterpart on the GPU (ksl_kepler_partials, forward-mode dual numbers): states [n, 2, 3] or
+    [n, 6] -> numpy [n, 6, 6]; agrees with keplerian_cartesian_partials to rounding."""
+    from . import engine
+    _, jac = engine.kepler_partials(np.asarray(states, dtype=np.float64).reshape(-1, 6), mu)
+    return jac.cpu().numpy()
+
+
 def rotation_matrix(state):
     """util.py:304-320."""
     r, v = state[0], state[1]

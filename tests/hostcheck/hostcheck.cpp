@@ -6,6 +6,7 @@
 #include <vector>
 #include "../../kessler_b200/csrc/sgp4_device.cuh"
 #include "../../kessler_b200/csrc/screen_device.cuh"
+#include "../../kessler_b200/csrc/kepler_device.cuh"
 
 extern "C" {
 
@@ -62,6 +63,12 @@ int hc_upsample_index(int64_t j, int64_t n_in, int64_t n_out, int64_t *i0, int64
 }
 
 double hc_wrap_twopi(double x) { return ksl::wrap_twopi(x); }
+
+int hc_kepler_partials(const double *states, int64_t n, double mu, double *elements, double *jac) {
+    for (int64_t i = 0; i < n; ++i)
+        if (!ksl::kepler_elements_and_partials(states + 6 * i, mu, elements + 6 * i, jac + 36 * i)) return (int)(i + 1);
+    return 0;
+}
 
 // Host emulation of k_screen's data flow (kessler_b200.cu): kThreads "threads" walk the
 // coarse epochs in chunks of kThreads with a one-epoch overlap, each keeping its own

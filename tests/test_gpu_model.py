@@ -198,3 +198,43 @@ def test_get_conjunction_on_population(kb):
     assert len(cdms) >= 1 and int(trace.nodes["i_conj"]["value"]) > 0
     assert float(trace.nodes["d_conj"]["value"]) < 5e3
     assert cdms[0].get_object(0, "OBJECT_NAME") == trace.nodes["t_tle"]["infer"]["t_tle"].name
+
+
+def test_newton_and_partials_kernels(kb, golden, refnpz):
+    """ksl_newton_elements (batched dsgp4.newton_method) and ksl_kepler_partials (util.py:187-302, batched)."""
+    from kessler_b200 import engine
+    sgp4, util = kb["sgp4"], kb["util"]
+    # partials vs the reference's own autograd output (tests/golden/reference_functions.npz) and the host mirror
+    st = refnpz["conv_states"].reshape(-1, 6)
+    el, jac = engine.kepler_partials(st, 398600.5e9)
+    el, jac = el.cpu().numpy(), jac.cpu().numpy()
+    assert np.allclose(el, refnpz["conv_kepler"], rtol=1e-11, atol=1e-12)      # acos-based angles: cancellation near 0, pi
+    ref = refnpz["conv_partials"]
+    assert np.abs(jac - ref).max() / np.abs(ref).max() < 1e-14
+    assert (np.abs(jac - ref) / np.maximum(np.abs(ref), 1e-300)).max() < 1e-11
+    assert np.allclose(util.keplerian_cartesian_partials_batch(refnpz["conv_states"], 398600.5e9), jac, rtol=0, atol=0)
+    # Newton: population TLEs at several observation times -> solved elements reproduce the target state
+    pop = json.load(open(os.path.join(ROOT, "tests", "golden", "population.json")))
+    tles = kb["load"]([x for p in pop for x in ("0 " + p["name"], p["line1"], p["line2"])])
+    targets, bstars = [], []
+    for t in tles:
+        for dt_min in (-20000.0, -3000.0, 0.0, 1440.0):
+            rv = sgp4.propagate(t, dt_min).numpy().reshape(6)
+            if np.all(np.isfinite(rv)) and np.linalg.norm(rv[:3]) > 6400.0:
+                targets.append(rv)
+                bstars.append(t._bstar)
+    targets, bstars = np.array(targets), np.array(bstars)
+    assert len(targets) > 60
+    y, resid, iters = engine.newton_elements(targets, bstars)
+    y, resid, iters = y.cpu().numpy(), resid.cpu().numpy(), iters.cpu().numpy()
+    assert np.isfinite(y).all() and (iters <= 12).all() and resid.max() < 1e-8
+    el7 = np.concatenate([y.T, bstars[None, :]], axis=0)
+    back, _ = C.tca_states(el7, 0.0)                       # oracle SGP4 of the solved elements, metres
+    assert np.abs(back[:, :3] / 1e3 - targets[:, :3]).max() < 1e-6      # km: the north-star position tolerance
+    assert np.abs(back[:, 3:] / 1e3 - targets[:, 3:]).max() < 1e-9
+    # dsgp4-style call: new TLE at the observation epoch, text-quantised (~10 m)
+    t = tles[0]
+    new, yy = sgp4.newton_method(t, t.date_mjd + 0.3)
+    assert abs(new.date_mjd - (t.date_mjd + 0.3)) < 2e-8 and yy.shape == (6,)
+    want = sgp4.propagate(t, 0.3 * 1440.0).numpy()
+    assert np.abs(sgp4.propagate(new, 0.0).numpy() - want)[0].max() < 0.05
