@@ -208,6 +208,22 @@ int ksl_newton_elements(const double *target_km, const double *bstar, int64_t n,
  * differences).  NaN rows for e >= 1. */
 int ksl_kepler_partials(const double *states, int64_t n, double mu, double *elements, double *jac, void *stream);
 
+/* ---- batched ground segment helpers -------------------
+ * ksl_states_at_fine: `t_states[i_cdm]` of model.py:658,670 for n_items (record, fine index) pairs without
+ * materialising any trajectory: consts SoA [KSL_NCONST][n_rec]; rec[it] selects the record, epoch[it] its
+ * epoch (MJD), fine_idx[it] the index on the n_fine grid; out_m [n_items][6] metres, m/s with util.upsample's
+ * arithmetic; err [n_items] Vallado bits (may be NULL). */
+int ksl_states_at_fine(const double *consts, int64_t n_rec, const int64_t *rec, const double *epoch, const int64_t *fine_idx,
+                       int64_t n_items, const double *times_coarse, int64_t n_coarse, int64_t n_fine, double *out_m, int32_t *err,
+                       void *stream);
+/* ksl_pc_mvn_batched: model.py:424-437 for n_cdm CDMs at once.  mean [n_cdm][2][3] and chol [n_cdm][2][6]
+ * (row-major lower triangle of the 3x3 Cholesky factor) describe the Gaussian position samples of target (0)
+ * and chaser (1); n_pts samples each are drawn on the device (Philox keyed by (seed, cdm_id0 + cdm, object,
+ * point)) and counts[cdm] = #{(i, j): ||t_i - c_j|| < thr_m}.  points_ws: n_cdm*2*3*n_pts doubles (returned
+ * filled: [n_cdm][2][3][n_pts], so a test can recount on identical samples). */
+int ksl_pc_mvn_batched(const double *mean, const double *chol, int64_t n_cdm, int64_t n_pts, uint64_t seed, int64_t cdm_id0,
+                       double thr_m, unsigned long long *counts, double *points_ws, void *stream);
+
 /* ---- end-to-end entry points: HOST buffers in, HOST buffers out ----------------
  * What a Kessler-side binding calls for a batch of traces.  Allocates (and caches
  * per device) its staging and scratch buffers; synchronous.

@@ -85,6 +85,8 @@ _SIGNATURES = {
                   _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "ksl_newton_elements": [_vp, _vp, _i64, _int, _f64, _vp, _vp, _vp, _vp],
     "ksl_kepler_partials": [_vp, _i64, _f64, _vp, _vp, _vp],
+    "ksl_states_at_fine": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp],
+    "ksl_pc_mvn_batched": [_vp, _vp, _i64, _i64, ctypes.c_uint64, _i64, _f64, _vp, _vp, _vp],
     "ksl_screen_host": [_int, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _f64, _int, _f64,
                         _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ksl_host_cache_free": [],

@@ -985,6 +985,103 @@ __global__ void __launch_bounds__(128) k_kepler_partials(const double *__restric
 }
 
 // ------------------------------------------------------------------------------------
+// Batched ground segment, helpers for many events at once.
+// K9   states_at_fine: the rows `t_states[i_cdm]` that forward() hands to the observation models
+//      (model.py:658,670) for many (record, fine index) pairs: both bracketing coarse SGP4 states and the
+//      torch interpolation arithmetic of util.upsample, in metres.
+// K10  collision probability of many CDMs (model.py:424-437): Gaussian position samples of target and chaser
+//      drawn on the device (Philox keyed by (seed, CDM id, object, point)), then the all-pairs count.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_states_at_fine(const double *__restrict__ consts, long long n_rec,
+                                                        const long long *__restrict__ rec, const double *__restrict__ epoch,
+                                                        const long long *__restrict__ fine_idx, long long n_items,
+                                                        const double *__restrict__ times_coarse, long long n_coarse, double scale,
+                                                        double *__restrict__ out_m, int *__restrict__ err) {
+    const long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const long long r = rec[it];
+    int64_t i0, i1;
+    double w0, w1;
+    ksl::upsample_index(fine_idx[it], scale, n_coarse, &i0, &i1, &w0, &w1);
+    double a[6], b[6];
+    auto ld = [&](int k) { return __ldg(consts + (long long)k * n_rec + r); };
+    int e = ksl::sgp4_prop<true>(ld, (times_coarse[i0] - epoch[it]) * 1440.0, a, a + 3);
+    e |= ksl::sgp4_prop<true>(ld, (times_coarse[i1] - epoch[it]) * 1440.0, b, b + 3);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) out_m[6 * it + q] = ksl::lerp_m(w0, a[q], w1, b[q]);
+    if (err) err[it] = e;
+}
+
+// points [n_cdm][2][3][n_pts] (SoA per object): p = mean + L z, L lower-triangular 3x3 (6 numbers, row-major)
+__global__ void __launch_bounds__(256) k_mvn_points(const double *__restrict__ mean /*[n_cdm][2][3]*/,
+                                                    const double *__restrict__ chol /*[n_cdm][2][6]*/, long long n_cdm,
+                                                    long long n_pts, unsigned long long seed, long long cdm_id0,
+                                                    double *__restrict__ pts) {
+    const long long total = n_cdm * 2 * n_pts;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long cdm = idx / (2 * n_pts);
+        const long long rem = idx - cdm * 2 * n_pts;
+        const int obj = (int)(rem / n_pts);
+        const long long p = rem - (long long)obj * n_pts;
+        unsigned int w[4], w2[4];
+        const unsigned long long g = (unsigned long long)(cdm_id0 + cdm);
+        philox4x32_10((unsigned int)g, (unsigned int)(g >> 32), (unsigned int)p, 0x50630000u + (unsigned int)obj + (unsigned int)((p >> 32) << 8),
+                      (unsigned int)seed, (unsigned int)(seed >> 32), w);
+        philox4x32_10((unsigned int)g, (unsigned int)(g >> 32), (unsigned int)p, 0x50640000u + (unsigned int)obj + (unsigned int)((p >> 32) << 8),
+                      (unsigned int)seed, (unsigned int)(seed >> 32), w2);
+        double z[4], sn, cs;
+        double rad = sqrt(-2.0 * log(u53(w[0], w[1])));
+        sincospi(2.0 * u53(w[2], w[3]), &sn, &cs);
+        z[0] = rad * cs; z[1] = rad * sn;
+        rad = sqrt(-2.0 * log(u53(w2[0], w2[1])));
+        sincospi(2.0 * u53(w2[2], w2[3]), &sn, &cs);
+        z[2] = rad * cs;
+        const double *m = mean + (cdm * 2 + obj) * 3;
+        const double *L = chol + (cdm * 2 + obj) * 6;
+        double *o = pts + ((cdm * 2 + obj) * 3) * n_pts + p;
+        o[0] = m[0] + L[0] * z[0];
+        o[n_pts] = m[1] + L[1] * z[0] + L[2] * z[1];
+        o[2 * n_pts] = m[2] + L[3] * z[0] + L[4] * z[1] + L[5] * z[2];
+    }
+}
+
+// all-pairs count per CDM: grid = (target tiles, n_cdm); counts[cdm] accumulated
+__global__ void __launch_bounds__(kPcThreads) k_pc_all_pairs_batched(const double *__restrict__ pts, long long n_pts, double thr2,
+                                                                     unsigned long long *__restrict__ counts) {
+    __shared__ double sx[kPcTile], sy[kPcTile], sz[kPcTile];
+    __shared__ unsigned long long s_total;
+    const long long cdm = blockIdx.y;
+    const double *t = pts + (cdm * 2 + 0) * 3 * n_pts, *c = pts + (cdm * 2 + 1) * 3 * n_pts;
+    const long long i = (long long)blockIdx.x * kPcThreads + threadIdx.x;
+    const bool have = i < n_pts;
+    const double tx = have ? t[i] : 0.0, ty = have ? t[n_pts + i] : 0.0, tz = have ? t[2 * n_pts + i] : 0.0;
+    unsigned int local = 0;
+    if (threadIdx.x == 0) s_total = 0;
+    for (long long base = 0; base < n_pts; base += kPcTile) {
+        const int m = (int)((n_pts - base < kPcTile) ? n_pts - base : kPcTile);
+        __syncthreads();
+        for (int q = threadIdx.x; q < m; q += kPcThreads) {
+            sx[q] = c[base + q];
+            sy[q] = c[n_pts + base + q];
+            sz[q] = c[2 * n_pts + base + q];
+        }
+        __syncthreads();
+        if (have) {
+#pragma unroll 4
+            for (int q = 0; q < m; ++q) {
+                const double dx = ksl::add_rn(tx, -sx[q]), dy = ksl::add_rn(ty, -sy[q]), dz = ksl::add_rn(tz, -sz[q]);
+                local += (ksl::sqdist3(dx, dy, dz) < thr2) ? 1u : 0u;
+            }
+        }
+    }
+    unsigned long long v = local;
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_total, v);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_total) atomicAdd(counts + cdm, s_total);
+}
+
+// ------------------------------------------------------------------------------------
 // FP64 peak probe: 8 independent DFMA chains per thread
 // ------------------------------------------------------------------------------------
 __global__ void k_fp64_peak(long long iters, double *__restrict__ sink) {
@@ -1306,6 +1403,41 @@ int ksl_kepler_partials(const double *states, int64_t n, double mu, double *elem
     if (n < 0 || (n > 0 && (!states || !elements || !jac))) return fail(KSL_E_ARG, "ksl_kepler_partials: bad argument");
     if (n == 0) return KSL_OK;
     k_kepler_partials<<<(unsigned)((n + 127) / 128), 128, 0, S(stream)>>>(states, n, mu, elements, jac);
+    KSL_LAUNCH_CHECK();
+    return KSL_OK;
+}
+
+int ksl_states_at_fine(const double *consts, int64_t n_rec, const int64_t *rec, const double *epoch, const int64_t *fine_idx,
+                       int64_t n_items, const double *times_coarse, int64_t n_coarse, int64_t n_fine, double *out_m, int32_t *err,
+                       void *stream) {
+    if (n_items < 0 || n_rec <= 0 || n_coarse <= 0 || n_fine <= 0 ||
+        (n_items > 0 && (!consts || !rec || !epoch || !fine_idx || !times_coarse || !out_m)))
+        return fail(KSL_E_ARG, "ksl_states_at_fine: bad argument");
+    if (n_items == 0) return KSL_OK;
+    k_states_at_fine<<<(unsigned)((n_items + 127) / 128), 128, 0, S(stream)>>>(consts, n_rec, reinterpret_cast<const long long *>(rec), epoch,
+                                                                              reinterpret_cast<const long long *>(fine_idx), n_items,
+                                                                              times_coarse, n_coarse, up_scale(n_coarse, n_fine), out_m, err);
+    KSL_LAUNCH_CHECK();
+    return KSL_OK;
+}
+
+int ksl_pc_mvn_batched(const double *mean, const double *chol, int64_t n_cdm, int64_t n_pts, uint64_t seed, int64_t cdm_id0,
+                       double thr_m, unsigned long long *counts, double *points_ws, void *stream) {
+    if (n_cdm < 0 || n_pts <= 0 || (n_cdm > 0 && (!mean || !chol || !counts || !points_ws)))
+        return fail(KSL_E_ARG, "ksl_pc_mvn_batched: bad argument");
+    if (n_cdm == 0) return KSL_OK;
+    if (n_cdm > 65535) return fail(KSL_E_ARG, "ksl_pc_mvn_batched: at most 65535 CDMs per call");
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc) return rc;
+    const long long total = n_cdm * 2 * n_pts;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    k_mvn_points<<<(unsigned)blocks, 256, 0, S(stream)>>>(mean, chol, n_cdm, n_pts, (unsigned long long)seed, cdm_id0, points_ws);
+    KSL_LAUNCH_CHECK();
+    KSL_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (size_t)n_cdm, S(stream)));
+    dim3 grid((unsigned)((n_pts + kPcThreads - 1) / kPcThreads), (unsigned)n_cdm);
+    k_pc_all_pairs_batched<<<grid, kPcThreads, 0, S(stream)>>>(points_ws, n_pts, thr_m * thr_m, counts);
     KSL_LAUNCH_CHECK();
     return KSL_OK;
 }

@@ -225,6 +225,46 @@ def kepler_partials(states, mu):
     return el, jac
 
 
+# --- batched ground segment helpers --------------------------------------------------------------
+def states_at_fine(consts, rec, epoch, fine_idx, times_coarse, n_fine):
+    """consts [36, n_rec]; rec, epoch, fine_idx [n_items] -> (states [n_items, 6] m, err [n_items] int32)."""
+    dev = _dev()
+    consts = _cf64(consts, dev)
+    rec = torch.as_tensor(np.asarray(rec, dtype=np.int64)).to(dev)
+    fine_idx = torch.as_tensor(np.asarray(fine_idx, dtype=np.int64)).to(dev)
+    epoch = _cf64(epoch, dev).reshape(-1)
+    times_coarse = _cf64(times_coarse, dev)
+    n_items = rec.numel()
+    out = torch.empty((n_items, 6), dtype=F64, device=dev)
+    err = torch.empty(n_items, dtype=torch.int32, device=dev)
+    N.check(N.lib().ksl_states_at_fine(ptr(consts), consts.shape[1], ptr(rec), ptr(epoch), ptr(fine_idx), n_items, ptr(times_coarse),
+                                       times_coarse.numel(), int(n_fine), ptr(out), ptr(err), stream_ptr()), "ksl_states_at_fine")
+    return out, err
+
+
+def pc_mvn_batched(mean, chol, n_pts, thr_m, seed=0, cdm_id0=0, return_points=False):
+    """mean [n_cdm, 2, 3], chol [n_cdm, 2, 3, 3] (lower-triangular) -> counts int64 [n_cdm] (+ points [n_cdm,2,3,n_pts])."""
+    dev = _dev()
+    mean = _cf64(mean, dev).reshape(-1, 2, 3)
+    n_cdm = mean.shape[0]
+    chol = np.asarray(chol.cpu() if torch.is_tensor(chol) else chol, dtype=np.float64).reshape(n_cdm, 2, 3, 3)
+    tri = np.ascontiguousarray(chol[:, :, [0, 1, 1, 2, 2, 2], [0, 0, 1, 0, 1, 2]])
+    tri_d = _cf64(tri, dev)
+    counts = torch.zeros(n_cdm, dtype=torch.int64, device=dev)
+    done = 0
+    pts_all = []
+    while done < n_cdm:                       # bounded workspace: <= 4096 CDMs per launch
+        m = min(4096, n_cdm - done)
+        ws = torch.empty((m, 2, 3, int(n_pts)), dtype=F64, device=dev)
+        N.check(N.lib().ksl_pc_mvn_batched(ptr(mean[done:done + m].contiguous()), ptr(tri_d[done:done + m].contiguous()), m, int(n_pts),
+                                           int(seed), int(cdm_id0) + done, float(thr_m), ptr(counts[done:]), ptr(ws), stream_ptr()),
+                "ksl_pc_mvn_batched")
+        if return_points:
+            pts_all.append(ws)
+        done += m
+    return (counts, torch.cat(pts_all) if pts_all else None) if return_points else counts
+
+
 # --- end-to-end: host buffers in / out -----------------------------------------------------
 def screen_host(elems_t, epoch_t, elems_c, epoch_c, times_coarse, n_fine, thr_m, mode=N.SCREEN_ANALYTIC,
                 collision_thr_m=70.0, device=None, out=None, want_summary=True):

@@ -1,0 +1,245 @@
+"""Batched ground segment: CDM sequences for MANY accepted conjunctions at once.
+
+`Conjunction.forward()` (model.py:630-692 of the reference) issues the CDMs of one event in a Python
+loop: per CDM and observed object a Newton solve, six autograd passes, 100 TLE objects, a propagate, a
+rotation loop, `np.cov`, then 2 x 10^4 Gaussian samples and a 10^4 x 10^4 `cdist`.  This module does the
+same computation for all events of a `forward_batch()` at once:
+
+  truth states at the CDM times     ksl_states_at_fine      (one launch for all events)
+  osculating -> mean elements       ksl_sgp4_prop + ksl_newton_elements
+  Kepler partials                   ksl_kepler_partials
+  100-sample element clouds         ksl_sgp4_init + ksl_sgp4_prop on [items x 100] records
+  collision probability             ksl_pc_mvn_batched      (device-side draws)
+
+with the 6x6 algebra vectorised in NumPy between the launches.  The per-event semantics (CDM schedule,
+observation draws, carry-forward of un-observed objects, the ITRF/RTN conventions incl. the reference's
+quirks) are those of `Conjunction.forward()`; tests/test_gpu_events.py checks the deterministic parts
+against it event by event.  Random streams differ from the sequential path (one vectorised draw per
+stage instead of one per CDM), so the outputs are equal in distribution, not sample by sample.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import engine, util
+from . import _native as N
+from .cdm import ConjunctionDataMessage
+from .model import quantize_sgp4_inputs
+from .tle import MU_EARTH, epoch_to_datetime, from_datetime_to_mjd, from_mjd_to_datetime, from_mjd_to_epoch_days_after_1_jan
+
+
+def _rotation_matrices(states):
+    """util.rotation_matrix for states [n, 6] -> [n, 3, 3] (rows u, t, w)."""
+    r, v = states[:, :3], states[:, 3:]
+    u = r / np.linalg.norm(r, axis=1, keepdims=True)
+    w = np.cross(r, v)
+    w = w / np.linalg.norm(w, axis=1, keepdims=True)
+    t = np.cross(w, u)
+    return np.stack([u, t, w], axis=1)
+
+
+def _blockdiag2(R):
+    n = R.shape[0]
+    T = np.zeros((n, 6, 6))
+    T[:, :3, :3] = R
+    T[:, 3:, 3:] = R
+    return T
+
+
+def _teme_to_itrf(states_m, jd):
+    """util.from_TEME_to_ITRF vectorised: states [n, 6] metres, jd [n]."""
+    out = np.empty_like(states_m)
+    for k in np.unique(jd):           # few distinct TCAs per batch (one per event)
+        sel = jd == k
+        theta, theta_dot = util._theta_gmst1982(float(k))
+        c, s = math.cos(theta), math.sin(theta)
+        R = np.array([[c, s, 0.0], [-s, c, 0.0], [0.0, 0.0, 1.0]])
+        r_new = states_m[sel, :3] @ R.T
+        v_day = (states_m[sel, 3:] * 86400.0) @ R.T + np.cross(np.array([0.0, 0.0, -theta_dot]), r_new)
+        out[sel, :3], out[sel, 3:] = r_new, v_day / 86400.0
+    return out
+
+
+def obs_epoch_mjd(time_mjd):
+    """Epoch of the TLE that newton_method builds for an observation at time_mjd: year + day-of-year written
+    with 8 decimals into the TLE text, read back, truncated to the microsecond (tle.TLE semantics)."""
+    year = from_mjd_to_datetime(time_mjd).year
+    days = float("{:012.8f}".format(from_mjd_to_epoch_days_after_1_jan(time_mjd)))
+    return from_datetime_to_mjd(epoch_to_datetime(year, days))
+
+
+def generate_cdm_batch(model, batch, hits, seed=0, t_new_obs=None, c_new_obs=None, z_elements=None):
+    """Ground segment for the accepted draws `hits` (indices into `batch` = model.forward_batch(n)).
+
+    Returns a dict of arrays over events e (= hits) and CDM slots i < max_ncdm[e] (padded to the largest):
+      max_ncdm [E]; issued [E, I] bool; time_cdm [I]; state_itrf_km [E, I, 2, 6]; cov_rtn [E, I, 2, 6, 6];
+      pc [E, I]; tca_mjd [E]; plus the intermediates `items` (one row per new observation).
+    t_new_obs / c_new_obs [E, I] and z_elements [n_items, S, 6] can be injected by tests."""
+    hits = np.asarray(hits, dtype=np.int64)
+    E = len(hits)
+    times = model.time_grid()
+    time0 = model._time0
+    S = int(model._mc_samples)
+    n_pc = int(model._mc_samples * model._mc_upsample_factor)
+    time_min = batch["time_min"][hits]
+    # ---- schedule (model.py:632-638): same grid times for every event -------------------------------
+    max_ncdm = np.maximum(1, ((time_min - time0) * 24.0 / model._cdm_update_every_hours).astype(np.int64))
+    I = int(max_ncdm.max())
+    idx_cdm = np.empty(I, dtype=np.int64)
+    for i in range(I):
+        idx_cdm[i], _ = util.find_closest(times, time0 + (i * model._cdm_update_every_hours) / 24)
+    time_cdm = times[idx_cdm]
+    slot = np.arange(I)[None, :] < max_ncdm[:, None]
+    # ---- observation draws (model.py:643-650) --------------------------------------------------------
+    g = torch.Generator().manual_seed(int(seed))
+    if t_new_obs is None:
+        t_new_obs = torch.bernoulli(torch.full((E, I), float(model._t_prob_new_obs)), generator=g).numpy() > 0
+    if c_new_obs is None:
+        c_new_obs = torch.bernoulli(torch.full((E, I), float(model._c_prob_new_obs)), generator=g).numpy() > 0
+    obs = np.stack([np.asarray(t_new_obs)[:, :I], np.asarray(c_new_obs)[:, :I]], axis=2).astype(bool)          # [E, I, 2]
+    obs[:, 0, :] = True
+    obs &= slot[:, :, None]
+    ev, ci, ob = np.nonzero(obs)                                         # items: one per new observation
+    n_items = len(ev)
+    # ---- records: initialised target / chaser of every event ----------------------------------------
+    el = np.concatenate([batch["elems_t"][:, hits], batch["elems_c"][:, hits]], axis=1)      # [7, 2E]
+    ep = np.concatenate([batch["epoch_t"][hits], batch["epoch_c"][hits]])
+    consts, _ = engine.sgp4_init(el)
+    rec = ob * E + ev
+    tc = np.ascontiguousarray(times[::max(int(model._time_upsample_factor), 1)])
+    truth, _ = engine.states_at_fine(consts, rec, ep[rec], idx_cdm[ci], tc, len(times))
+    truth = truth.cpu().numpy()
+    # instruments (model.py:655-676): mean over the object's instruments of (state + bias, diagonal RTN covariance)
+    def inst(instruments):
+        bias = np.mean([np.asarray(x._instrument_characteristics["bias_xyz"], dtype=np.float64).reshape(6) for x in instruments], axis=0)
+        cov = np.mean([np.asarray(x._instrument_characteristics["covariance_rtn"], dtype=np.float64) for x in instruments], axis=0)
+        return bias, cov
+    bias_t, cov_t = inst(model._t_observing_instruments)
+    bias_c, cov_c = inst(model._c_observing_instruments)
+    state_obs = truth + np.where(ob[:, None] == 0, bias_t[None, :], bias_c[None, :])
+    cov_diag = np.where(ob[:, None] == 0, cov_t[None, :], cov_c[None, :])
+    # ---- newton_method (model.py:399,411): target = the TLE's own SGP4 state at the observation time -----
+    tsince_obs = (time_cdm[ci] - ep[rec]) * 1440.0
+    rv, _ = engine.sgp4_prop(consts[:, torch.as_tensor(rec)], tsince_obs.reshape(-1, 1), per_sample_t=True)
+    bstar = el[6, rec]
+    y, resid, _ = engine.newton_elements(rv[:, 0, :], bstar)
+    y = y.cpu().numpy()
+    wrap = lambda a: np.mod(a, 2 * np.pi)
+    raw_mm = y[:, 0] / 60.0
+    q = quantize_sgp4_inputs(raw_mm, y[:, 1], wrap(y[:, 2]), wrap(y[:, 3]), wrap(y[:, 4]), wrap(y[:, 5]), bstar)   # TLE(dict)
+    epoch_obs_by_slot = np.array([obs_epoch_mjd(t) for t in time_cdm])
+    epoch_obs = epoch_obs_by_slot[ci]
+    # ---- element covariance (model.py:461-478) -----------------------------------------------------------
+    R = _rotation_matrices(state_obs)
+    T = _blockdiag2(R)
+    C_xyz = np.einsum("nji,nj,njk->nik", T, cov_diag, T)
+    _, J = engine.kepler_partials(state_obs, model._mu_earth)
+    J = J.cpu().numpy()
+    Cov = np.einsum("nij,njk,nlk->nil", J, C_xyz, J)
+    eig_ok = np.all(np.real(np.linalg.eigvals(Cov)) > 1e-11, axis=1)
+    fix = ~eig_ok
+    Cov[fix] = 0.5 * (Cov[fix] + np.transpose(Cov[fix], (0, 2, 1))) + 1e-10 * np.eye(6)
+    mean_els = np.stack([(MU_EARTH / raw_mm ** 2) ** (1.0 / 3.0), q[1], q[2], q[3], q[4], q[5]], axis=1)
+    # ---- element clouds (model.py:497-541) ------------------------------------------------------------------
+    L = np.zeros_like(Cov)
+    chol_ok = np.ones(n_items, dtype=bool)
+    for k in range(n_items):
+        try:
+            L[k] = np.linalg.cholesky(Cov[k])
+        except np.linalg.LinAlgError:         # the reference's "Expected parameter covariance_matrix" branch
+            chol_ok[k] = False
+    if z_elements is None:
+        z_elements = torch.randn((n_items, S, 6), dtype=torch.float64, generator=g).numpy()
+    samples = mean_els[:, None, :] + np.einsum("nsj,nij->nsi", z_elements, L)
+    samples[~chol_ok] = mean_els[~chol_ok][:, None, :]
+    flat = samples.reshape(-1, 6)
+    mm = (MU_EARTH / flat[:, 0] ** 3) ** 0.5
+    el_s = quantize_sgp4_inputs(mm, np.where(flat[:, 1] < 0.0, 0.0, flat[:, 1]), flat[:, 2], flat[:, 3], flat[:, 4], flat[:, 5],
+                                np.repeat(bstar, S))
+    tsince_ca = np.repeat((time_min[ev] - epoch_obs) * 1440.0, S)
+    c_s, _ = engine.sgp4_init(el_s)
+    rv_s, _ = engine.sgp4_prop(c_s, tsince_ca.reshape(-1, 1), per_sample_t=True)
+    mc = rv_s[:, 0, :].cpu().numpy().reshape(n_items, S, 6) * 1e3
+    mean_state = mc.mean(axis=1)
+    Rm = _rotation_matrices(mean_state)
+    rtn = np.concatenate([np.einsum("nij,nsj->nsi", Rm, mc[:, :, :3]), np.einsum("nij,nsj->nsi", Rm, mc[:, :, 3:])], axis=2)
+    d = rtn - rtn.mean(axis=1, keepdims=True)
+    cov_rtn = np.einsum("nsi,nsj->nij", d, d) / (S - 1)
+    cov_rtn[~chol_ok] = np.einsum("ni,ij->nij", cov_diag[~chol_ok], np.eye(6))
+    tca_jd = util.from_mjd_to_jd(time_min)
+    state_itrf_km = _teme_to_itrf(mean_state, tca_jd[ev]) / 1e3
+    # ---- carry-forward (model.py:345-346): an un-observed object keeps the previous CDM's numbers ------------
+    st = np.full((E, I, 2, 6), np.nan)
+    cv = np.full((E, I, 2, 6, 6), np.nan)
+    st[ev, ci, ob] = state_itrf_km
+    cv[ev, ci, ob] = cov_rtn
+    for i in range(1, I):
+        keep = ~obs[:, i, :]
+        st[:, i][keep] = st[:, i - 1][keep]
+        cv[:, i][keep] = cv[:, i - 1][keep]
+    issued = obs.any(axis=2)
+    # ---- collision probability of every issued CDM (model.py:424-437) ----------------------------------------
+    e_i, c_i = np.nonzero(issued)
+    s_m = st[e_i, c_i] * 1e3                                             # [n_cdm, 2, 6] metres (ITRF, sic)
+    Rr = _rotation_matrices(s_m.reshape(-1, 6)).reshape(len(e_i), 2, 3, 3)
+    mean_rtn = np.einsum("nkij,nkj->nki", Rr, s_m[:, :, :3])
+    cov3 = cv[e_i, c_i][:, :, :3, :3]
+    L3 = np.zeros_like(cov3)
+    pc_ok = np.ones(len(e_i), dtype=bool)
+    for k in range(len(e_i)):
+        for o in range(2):
+            try:
+                L3[k, o] = np.linalg.cholesky(cov3[k, o])
+            except np.linalg.LinAlgError:
+                pc_ok[k] = False
+    counts = engine.pc_mvn_batched(mean_rtn, L3, n_pc, model._collision_threshold, seed=int(seed) + 1).cpu().numpy()
+    pc = np.full((E, I), np.nan)
+    pc[e_i, c_i] = np.where(pc_ok, counts / float(n_pc * n_pc), np.nan)
+    return dict(hits=hits, max_ncdm=max_ncdm, time_cdm=time_cdm, idx_cdm=idx_cdm, issued=issued, new_obs=obs,
+                state_itrf_km=st, cov_rtn=cv, pc=pc, tca_mjd=time_min,
+                items=dict(event=ev, slot=ci, obj=ob, truth_m=truth, state_obs_m=state_obs, newton_y=y, newton_resid=resid.cpu().numpy(),
+                           obs_elements=q, obs_epoch_mjd=epoch_obs, cov_tle=Cov, mean_state_tca_m=mean_state, cov_rtn=cov_rtn))
+
+
+def to_cdms(model, res, e, t_tle=None, c_tle=None):
+    """ConjunctionDataMessage objects of event e of a generate_cdm_batch() result (same fields as generate_cdm)."""
+    cdms = []
+    tca_jd = util.from_mjd_to_jd(res["tca_mjd"][e])
+    for i in range(int(res["max_ncdm"][e])):
+        if not res["issued"][e, i]:
+            continue
+        cdm = ConjunctionDataMessage()
+        cdm.set_header("ORIGINATOR", "KESSLER_SOFTWARE")
+        if t_tle is not None and c_tle is not None:
+            model._describe_object(cdm, 0, t_tle, True, "TARGET")
+            model._describe_object(cdm, 1, c_tle, True, "CHASER")
+        cdm.set_relative_metadata("TCA", util.from_jd_to_cdm_datetime_str(tca_jd))
+        cdm.set_header("CREATION_DATE", util.from_jd_to_cdm_datetime_str(util.from_mjd_to_jd(res["time_cdm"][i])))
+        for o in (0, 1):
+            cdm.set_state(o, res["state_itrf_km"][e, i, o].reshape(2, 3))
+            cdm.set_covariance(o, res["cov_rtn"][e, i, o])
+        cdm.set_relative_metadata("COLLISION_PROBABILITY", float(res["pc"][e, i]))
+        cdm.set_relative_metadata("COLLISION_PROBABILITY_METHOD", model._pc_method)
+        cdms.append(cdm)
+    return cdms
+
+
+def generate_events(model, n_events, batch_size=8192, seed=0, max_batches=10000):
+    """Rejection-sample conjunctions `batch_size` candidates at a time and run the batched ground segment on
+    every accepted draw.  Returns (list of generate_cdm_batch results, candidates screened)."""
+    out, screened, found = [], 0, 0
+    for b in range(max_batches):
+        batch = model.forward_batch(batch_size)
+        screened += batch_size
+        hits = np.nonzero(batch["conj"])[0]
+        if len(hits) == 0:
+            continue
+        hits = hits[:max(0, n_events - found)]
+        if "epoch_t" not in batch:
+            raise KeyError("forward_batch must return epoch_t / epoch_c")
+        out.append(generate_cdm_batch(model, batch, hits, seed=seed + 7919 * b))
+        found += len(hits)
+        if found >= n_events:
+            break
+    return out, screened

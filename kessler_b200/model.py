@@ -545,7 +545,7 @@ class Conjunction:
         keep = np.nonzero(~pre)[0]
         out = dict(prefiltered=pre, prop_error=np.zeros(n, bool), conj=np.zeros(n, bool), i_min=np.full(n, -1, np.int64),
                    d_min=np.full(n, np.nan), i_conj=np.full(n, -1, np.int64), d_conj=np.full(n, np.nan),
-                   time_min=np.full(n, np.nan), t_raw=t_raw, c_raw=c_raw, elems_t=el_t, elems_c=el_c)
+                   time_min=np.full(n, np.nan), t_raw=t_raw, c_raw=c_raw, elems_t=el_t, elems_c=el_c, epoch_t=ep_t, epoch_c=ep_c)
         if len(keep):
             r = engine.screen_host(np.ascontiguousarray(el_t[:, keep]), ep_t[keep], np.ascontiguousarray(el_c[:, keep]), ep_c[keep],
                                    tc, len(times), self._miss_dist_threshold, mode, self._collision_threshold)
