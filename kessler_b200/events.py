@@ -225,21 +225,59 @@ def to_cdms(model, res, e, t_tle=None, c_tle=None):
     return cdms
 
 
-def generate_events(model, n_events, batch_size=8192, seed=0, max_batches=10000):
-    """Rejection-sample conjunctions `batch_size` candidates at a time and run the batched ground segment on
-    every accepted draw.  Returns (list of generate_cdm_batch results, candidates screened)."""
-    out, screened, found = [], 0, 0
-    for b in range(max_batches):
-        batch = model.forward_batch(batch_size)
-        screened += batch_size
-        hits = np.nonzero(batch["conj"])[0]
-        if len(hits) == 0:
-            continue
-        hits = hits[:max(0, n_events - found)]
-        if "epoch_t" not in batch:
-            raise KeyError("forward_batch must return epoch_t / epoch_c")
-        out.append(generate_cdm_batch(model, batch, hits, seed=seed + 7919 * b))
-        found += len(hits)
+_BATCH_KEYS = ("elems_t", "elems_c", "epoch_t", "epoch_c", "time_min", "i_min", "d_min", "i_conj", "d_conj")
+
+
+def _take_hits(batch, hits):
+    """Compact copy of a forward_batch() result restricted to `hits` (what the ground segment needs)."""
+    out = {}
+    for k in _BATCH_KEYS:
+        a = batch[k]
+        out[k] = np.ascontiguousarray(a[:, hits] if a.ndim == 2 else a[hits])
+    for who in ("t_raw", "c_raw"):
+        out[who] = {k: (v[hits] if isinstance(v, np.ndarray) else v) for k, v in batch[who].items()}
+    return out
+
+
+def _concat_hits(parts):
+    out = {}
+    for k in _BATCH_KEYS:
+        out[k] = np.concatenate([p[k] for p in parts], axis=1 if parts[0][k].ndim == 2 else 0)
+    for who in ("t_raw", "c_raw"):
+        out[who] = {k: (np.concatenate([p[who][k] for p in parts]) if isinstance(v, np.ndarray) else v)
+                    for k, v in parts[0][who].items()}
+    return out
+
+
+def generate_events(model, n_events, batch_size=65536, seed=0, max_batches=100000, events_per_pass=4096):
+    """Rejection-sample conjunctions `batch_size` candidates at a time (one fused screen launch each), collect the
+    accepted draws, and run the batched ground segment on up to `events_per_pass` of them at once.  Returns
+    (list of generate_cdm_batch results -- each with its compact `batch` under key "batch" --, candidates screened)."""
+    out, screened, found, pending, n_pending, passes = [], 0, 0, [], 0, 0
+
+    def flush():
+        nonlocal pending, n_pending, passes
+        if not pending:
+            return
+        merged = _concat_hits(pending)
+        res = generate_cdm_batch(model, merged, np.arange(len(merged["time_min"])), seed=seed + 7919 * passes)
+        res["batch"] = merged
+        out.append(res)
+        pending, n_pending = [], 0
+        passes += 1
+
+    for _ in range(max_batches):
         if found >= n_events:
             break
+        batch = model.forward_batch(batch_size)
+        screened += batch_size
+        hits = np.nonzero(batch["conj"])[0][:max(0, n_events - found)]
+        if len(hits) == 0:
+            continue
+        pending.append(_take_hits(batch, hits))
+        n_pending += len(hits)
+        found += len(hits)
+        if n_pending >= events_per_pass:
+            flush()
+    flush()
     return out, screened
