@@ -224,6 +224,21 @@ int ksl_states_at_fine(const double *consts, int64_t n_rec, const int64_t *rec, 
 int ksl_pc_mvn_batched(const double *mean, const double *chol, int64_t n_cdm, int64_t n_pts, uint64_t seed, int64_t cdm_id0,
                        double thr_m, unsigned long long *counts, double *points_ws, void *stream);
 
+/* ---- prior sampling on the device  (model.py:245-319 draws + TLE(dict) quantisation) ---------
+ * A prior over the eight sampled TLE fields -- order: mean_motion [rad/s], mean_anomaly, eccentricity,
+ * inclination, argument_of_perigee, raan, mean_motion_first_derivative, b_star -- is packed on the HOST with
+ * ksl_prior_pack (one call per field) into a buffer of ksl_prior_param_bytes() bytes, copied to the device by
+ * the caller, and sampled by ksl_sample_prior.  kind: 0 uniform(lo, hi); 1 mixture of normals;
+ * 2 mixture of normals truncated to [lo, hi], sampled by inverse CDF (util.py:134-160) with cdf_a/cdf_b =
+ * Phi((lo-loc)/scale), Phi((hi-loc)/scale) per component.  Outputs (device): raw [8][n] the draws, elems
+ * [7][n] the SGP4 inputs after the TLE-text quantisation, flag [n] = 1 where a decimal rounding was within
+ * binary noise of a tie (re-quantise those on the host).  Draws depend only on (seed, sample_offset + i). */
+int64_t ksl_prior_param_bytes(void);
+int ksl_prior_pack(int field, int kind, int ncomp, double lo, double hi, const double *probs, const double *loc, const double *scale,
+                   const double *cdf_a, const double *cdf_b, void *host_params);
+int ksl_sample_prior(const void *params, uint64_t seed, int64_t sample_offset, int64_t n, double *raw, double *elems, int32_t *flag,
+                     void *stream);
+
 /* ---- end-to-end entry points: HOST buffers in, HOST buffers out ----------------
  * What a Kessler-side binding calls for a batch of traces.  Allocates (and caches
  * per device) its staging and scratch buffers; synchronous.

@@ -87,13 +87,17 @@ _SIGNATURES = {
     "ksl_kepler_partials": [_vp, _i64, _f64, _vp, _vp, _vp],
     "ksl_states_at_fine": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp],
     "ksl_pc_mvn_batched": [_vp, _vp, _i64, _i64, ctypes.c_uint64, _i64, _f64, _vp, _vp, _vp],
+    "ksl_prior_param_bytes": [],
+    "ksl_prior_pack": [_int, _int, _int, _f64, _f64, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ksl_sample_prior": [_vp, ctypes.c_uint64, _i64, _i64, _vp, _vp, _vp, _vp],
     "ksl_screen_host": [_int, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _f64, _int, _f64,
                         _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ksl_host_cache_free": [],
     "ksl_fp64_peak_kernel": [_int, _int, _i64, _vp, _vp],
 }
 _RESTYPES = {"ksl_last_error": ctypes.c_char_p, "ksl_launch_count": _i64, "ksl_find_conjunction_ws": _i64,
-             "ksl_screen_ws": _i64, "ksl_screen_summary_ws": _i64, "ksl_tca_moments_ws": _i64, "ksl_mc_pc_ws": _i64}
+             "ksl_screen_ws": _i64, "ksl_screen_summary_ws": _i64, "ksl_tca_moments_ws": _i64, "ksl_mc_pc_ws": _i64,
+             "ksl_prior_param_bytes": _i64}
 
 EXPORTS = tuple(_SIGNATURES)
 

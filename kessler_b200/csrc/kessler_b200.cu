@@ -1082,6 +1082,97 @@ __global__ void __launch_bounds__(kPcThreads) k_pc_all_pairs_batched(const doubl
 }
 
 // ------------------------------------------------------------------------------------
+// K11  prior sampling on the device: the eight TLE fields that
+// Conjunction.make_target / make_chaser draw (model.py:245-319) from the default prior's families --
+// mixtures of truncated normals by inverse CDF (util.py:134-160), a mixture of normals, uniforms --
+// followed by the TLE-text quantisation that TLE(dict) applies, so that the
+// rejection loop needs no host RNG and no H2D copy.  Draws are keyed by (seed, global index, field).
+// Entries whose decimal rounding is within binary noise of a tie (probability ~1e-13) are flagged and
+// re-quantised on the host by the text formatter.
+// ------------------------------------------------------------------------------------
+constexpr int kPriorMaxComp = 16;
+struct PriorField {
+    int kind;    // 0 uniform(lo, hi); 1 mixture of normals; 2 mixture of truncated normals on [lo, hi]
+    int ncomp;
+    double lo, hi;
+    double cum[kPriorMaxComp];     // cumulative mixture weights
+    double loc[kPriorMaxComp], scale[kPriorMaxComp];
+    double cdf_a[kPriorMaxComp], cdf_w[kPriorMaxComp];   // Phi(alpha), Phi(beta) - Phi(alpha)
+};
+// field order of `raw`: mean_motion [rad/s], mean_anomaly, eccentricity, inclination, argument_of_perigee, raan,
+// mean_motion_first_derivative, b_star
+constexpr int kPriorFields = 8;
+
+__constant__ double kPow10[19] = {1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9};
+
+__device__ __forceinline__ double round_decimals_dev(double x, double p10, bool &risky) {
+    const double scaled = x * p10;
+    const double frac = fabs(scaled - floor(scaled) - 0.5);
+    if (!(frac > 1e-14 * fmax(1.0, fabs(scaled)))) risky = true;
+    return rint(scaled) / p10;
+}
+
+__device__ __forceinline__ double quantize_exp_field_dev(double x, bool &risky) {
+    if (x == 0.0 || !(fabs(x) < INFINITY)) return 0.0;
+    const double ax = fabs(x);
+    const int ex = (int)floor(log10(ax)) + 1;
+    if (ex < -8 || ex > 8) { risky = true; return x; }
+    const double scaled = ax / kPow10[ex + 9] * 1e5;
+    const double mant = rint(scaled);
+    const double frac = fabs(scaled - floor(scaled) - 0.5);
+    if (frac < 1e-9 || mant >= 100000.0 || mant < 10000.0) risky = true;
+    return copysign(1.0, x) * (mant / 1e5) * kPow10[ex + 9];
+}
+
+__global__ void __launch_bounds__(256) k_sample_prior(const PriorField *__restrict__ prior, unsigned long long seed, long long offset,
+                                                      long long n, double *__restrict__ raw /*[8][n]*/, double *__restrict__ elems /*[7][n]*/,
+                                                      int *__restrict__ flag) {
+    __shared__ PriorField s_p[kPriorFields];
+    for (int i = threadIdx.x; i < (int)(sizeof(PriorField) * kPriorFields / sizeof(int)); i += blockDim.x)
+        reinterpret_cast<int *>(s_p)[i] = reinterpret_cast<const int *>(prior)[i];
+    __syncthreads();
+    const double deg = 3.141592653589793 / 180.0, twopi = 2.0 * 3.141592653589793;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long g = (unsigned long long)(offset + i);
+        double v[kPriorFields];
+#pragma unroll 1
+        for (int f = 0; f < kPriorFields; ++f) {
+            unsigned int w[4];
+            philox4x32_10((unsigned int)g, (unsigned int)(g >> 32), (unsigned int)f, 0x50524931u, (unsigned int)seed,
+                          (unsigned int)(seed >> 32), w);
+            const double u_comp = u53(w[0], w[1]), u_val = u53(w[2], w[3]);
+            const PriorField &p = s_p[f];
+            if (p.kind == 0) {
+                v[f] = p.lo + u_val * (p.hi - p.lo);
+            } else {
+                int c = 0;
+                while (c < p.ncomp - 1 && u_comp >= p.cum[c]) ++c;
+                if (p.kind == 1) {
+                    v[f] = p.loc[c] + p.scale[c] * normcdfinv(u_val);
+                } else {
+                    double x = p.loc[c] + p.scale[c] * normcdfinv(p.cdf_a[c] + u_val * p.cdf_w[c]);
+                    v[f] = fmin(fmax(x, p.lo), p.hi);   // the reference redraws outside the support; reachable only by rounding
+                }
+            }
+            raw[(long long)f * n + i] = v[f];
+        }
+        // TLE(dict): every SGP4 input goes through the text fields (tle.py / model.quantize_sgp4_inputs)
+        bool risky = false;
+        const double rev = round_decimals_dev(v[0] * 86400.0 / twopi, 1e8, risky);
+        double e = round_decimals_dev(v[2], 1e7, risky);
+        if (e >= 1.0) e = 0.9999999;
+        elems[0 * n + i] = rev * twopi / 86400.0 * 60.0;
+        elems[1 * n + i] = e;
+        elems[2 * n + i] = round_decimals_dev(v[3] / deg, 1e4, risky) * deg;
+        elems[3 * n + i] = round_decimals_dev(v[5] / deg, 1e4, risky) * deg;
+        elems[4 * n + i] = round_decimals_dev(v[4] / deg, 1e4, risky) * deg;
+        elems[5 * n + i] = round_decimals_dev(v[1] / deg, 1e4, risky) * deg;
+        elems[6 * n + i] = quantize_exp_field_dev(v[7], risky);
+        flag[i] = risky ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // FP64 peak probe: 8 independent DFMA chains per thread
 // ------------------------------------------------------------------------------------
 __global__ void k_fp64_peak(long long iters, double *__restrict__ sink) {
@@ -1438,6 +1529,43 @@ int ksl_pc_mvn_batched(const double *mean, const double *chol, int64_t n_cdm, in
     KSL_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (size_t)n_cdm, S(stream)));
     dim3 grid((unsigned)((n_pts + kPcThreads - 1) / kPcThreads), (unsigned)n_cdm);
     k_pc_all_pairs_batched<<<grid, kPcThreads, 0, S(stream)>>>(points_ws, n_pts, thr_m * thr_m, counts);
+    KSL_LAUNCH_CHECK();
+    return KSL_OK;
+}
+
+int64_t ksl_prior_param_bytes(void) { return (int64_t)(sizeof(PriorField) * kPriorFields); }
+
+int ksl_prior_pack(int field, int kind, int ncomp, double lo, double hi, const double *probs, const double *loc, const double *scale,
+                   const double *cdf_a, const double *cdf_b, void *host_params) {
+    if (field < 0 || field >= kPriorFields || kind < 0 || kind > 2 || ncomp < 0 || ncomp > kPriorMaxComp || !host_params ||
+        (kind > 0 && (ncomp < 1 || !probs || !loc || !scale)) || (kind == 2 && (!cdf_a || !cdf_b)))
+        return fail(KSL_E_ARG, "ksl_prior_pack: bad argument");
+    PriorField &p = reinterpret_cast<PriorField *>(host_params)[field];
+    memset(&p, 0, sizeof(p));
+    p.kind = kind; p.ncomp = ncomp; p.lo = lo; p.hi = hi;
+    double acc = 0.0, tot = 0.0;
+    for (int c = 0; c < ncomp; ++c) tot += probs[c];
+    for (int c = 0; c < ncomp; ++c) {
+        acc += probs[c] / tot;
+        p.cum[c] = acc;
+        p.loc[c] = loc[c];
+        p.scale[c] = scale[c];
+        if (kind == 2) { p.cdf_a[c] = cdf_a[c]; p.cdf_w[c] = cdf_b[c] - cdf_a[c]; }
+    }
+    return KSL_OK;
+}
+
+int ksl_sample_prior(const void *params, uint64_t seed, int64_t sample_offset, int64_t n, double *raw, double *elems, int32_t *flag,
+                     void *stream) {
+    if (n < 0 || !params || (n > 0 && (!raw || !elems || !flag))) return fail(KSL_E_ARG, "ksl_sample_prior: bad argument");
+    if (n == 0) return KSL_OK;
+    int sms = 0;
+    int rc = sm_count(&sms);
+    if (rc) return rc;
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    k_sample_prior<<<(unsigned)blocks, 256, 0, S(stream)>>>(reinterpret_cast<const PriorField *>(params), (unsigned long long)seed,
+                                                            sample_offset, n, raw, elems, flag);
     KSL_LAUNCH_CHECK();
     return KSL_OK;
 }

@@ -265,6 +265,46 @@ def pc_mvn_batched(mean, chol, n_pts, thr_m, seed=0, cdm_id0=0, return_points=Fa
     return (counts, torch.cat(pts_all) if pts_all else None) if return_points else counts
 
 
+# --- prior sampling on the device --------------------------------------------------------------------
+PRIOR_FIELDS = ("mean_motion", "mean_anomaly", "eccentricity", "inclination", "argument_of_perigee", "raan",
+                "mean_motion_first_derivative", "b_star")
+
+
+def pack_prior(fields):
+    """fields: list of 8 dicts (PRIOR_FIELDS order) with kind 0 {'lo','hi'}, kind 1 {'probs','loc','scale'} or kind 2
+    {'probs','loc','scale','lo','hi'}.  Returns the packed parameter block as a uint8 device tensor."""
+    dev = _dev()
+    nbytes = int(N.lib().ksl_prior_param_bytes())
+    host = np.zeros(nbytes, dtype=np.uint8)
+    arr = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+    for f, d in enumerate(fields):
+        kind = int(d["kind"])
+        if kind == 0:
+            N.check(N.lib().ksl_prior_pack(f, 0, 0, float(d["lo"]), float(d["hi"]), None, None, None, None, None, ptr(host)), "ksl_prior_pack")
+            continue
+        probs, loc, scale = arr(d["probs"]), arr(d["loc"]), arr(d["scale"])
+        lo, hi = float(d.get("lo", -np.inf)), float(d.get("hi", np.inf))
+        cdf_a = cdf_b = None
+        if kind == 2:
+            nrm = torch.distributions.Normal(torch.zeros((), dtype=F64), torch.ones((), dtype=F64))
+            cdf_a = arr(nrm.cdf(torch.from_numpy((lo - loc) / scale)).numpy())
+            cdf_b = arr(nrm.cdf(torch.from_numpy((hi - loc) / scale)).numpy())
+        N.check(N.lib().ksl_prior_pack(f, kind, len(probs), lo, hi, ptr(probs), ptr(loc), ptr(scale), ptr(cdf_a), ptr(cdf_b), ptr(host)),
+                "ksl_prior_pack")
+    return torch.from_numpy(host).to(dev)
+
+
+def sample_prior(params, seed, sample_offset, n):
+    """-> (raw [8, n], elems [7, n], flag [n] int32) device tensors."""
+    dev = _dev()
+    raw = torch.empty((len(PRIOR_FIELDS), int(n)), dtype=F64, device=dev)
+    elems = torch.empty((7, int(n)), dtype=F64, device=dev)
+    flag = torch.empty(int(n), dtype=torch.int32, device=dev)
+    N.check(N.lib().ksl_sample_prior(ptr(params), int(seed), int(sample_offset), int(n), ptr(raw), ptr(elems), ptr(flag), stream_ptr()),
+            "ksl_sample_prior")
+    return raw, elems, flag
+
+
 # --- end-to-end: host buffers in / out -----------------------------------------------------
 def screen_host(elems_t, epoch_t, elems_c, epoch_c, times_coarse, n_fine, thr_m, mode=N.SCREEN_ANALYTIC,
                 collision_thr_m=70.0, device=None, out=None, want_summary=True):

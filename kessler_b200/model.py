@@ -528,12 +528,71 @@ class Conjunction:
                          epoch_days=from_mjd_to_epoch_days_after_1_jan(self._time0)))
         return raw, el, np.full(n, probe.date_mjd)
 
-    def forward_batch(self, n, mode=N.SCREEN_ANALYTIC):
+    def _device_prior(self):
+        """Packed parameters of the prior for ksl_sample_prior, or None when the prior is not made of the
+        default prior's families (uniform / mixture of normals / mixture of truncated normals)."""
+        if getattr(self, "_device_prior_cache", None) is not None:
+            return self._device_prior_cache or None
+        fields = []
+        for name in engine.PRIOR_FIELDS:
+            d = self._prior_dict.get(name + "_prior")
+            if isinstance(d, Uniform):
+                fields.append(dict(kind=0, lo=float(d.low), hi=float(d.high)))
+            elif isinstance(d, MixtureSameFamily) and isinstance(d.component_distribution, util.TruncatedNormal):
+                c = d.component_distribution
+                fields.append(dict(kind=2, probs=d.mixture_distribution.probs.double().numpy(), loc=c._loc.double().numpy(),
+                                   scale=c._scale.double().numpy(), lo=float(c._low), hi=float(c._high)))
+            elif isinstance(d, MixtureSameFamily) and isinstance(d.component_distribution, Normal):
+                c = d.component_distribution
+                fields.append(dict(kind=1, probs=d.mixture_distribution.probs.double().numpy(), loc=c.loc.double().numpy(),
+                                   scale=c.scale.double().numpy()))
+            else:
+                self._device_prior_cache = False
+                return None
+        if any(f["kind"] > 0 and len(f["probs"]) > 16 for f in fields):
+            self._device_prior_cache = False
+            return None
+        self._device_prior_cache = engine.pack_prior(fields)
+        return self._device_prior_cache
+
+    def sample_elements_device(self, who, n, seed, offset=0):
+        """Device-side counterpart of sample_elements for an object drawn from the full prior: the draws, the
+        TLE-text quantisation and nothing else leave no footprint on the host.  Returns (raw dict of numpy [n] incl.
+        '_sites', elems numpy [7, n], epoch [n])."""
+        params = self._device_prior()
+        raw_d, el_d, flag = engine.sample_prior(params, seed, offset, n)
+        raw_h, el = raw_d.cpu().numpy(), el_d.cpu().numpy()
+        raw = {name: raw_h[k] for k, name in enumerate(engine.PRIOR_FIELDS)}
+        bad = np.nonzero(flag.cpu().numpy())[0]
+        if len(bad):    # decimal ties (~1e-13 of the draws): let the text formatter decide
+            el[:, bad] = quantize_sgp4_inputs(raw['mean_motion'][bad], raw['eccentricity'][bad], raw['inclination'][bad], raw['raan'][bad],
+                                              raw['argument_of_perigee'][bad], raw['mean_anomaly'][bad], raw['b_star'][bad])
+        raw['_sites'] = ['mean_motion', 'mean_anomaly', 'eccentricity', 'inclination', 'argument_of_perigee', 'raan',
+                         'mean_motion_first_derivative', 'b_star']
+        return raw, el, np.full(n, self._prior_epoch_mjd())
+
+    def _prior_epoch_mjd(self):
+        if getattr(self, "_prior_epoch_cache", None) is None:
+            probe = TLE(dict(self._STATIC_TLE_FIELDS, mean_motion=1e-3, mean_anomaly=0., eccentricity=0., inclination=0.,
+                             argument_of_perigee=0., raan=0., mean_motion_first_derivative=0., mean_motion_second_derivative=0.,
+                             b_star=0., epoch_year=from_mjd_to_datetime(self._time0).year,
+                             epoch_days=from_mjd_to_epoch_days_after_1_jan(self._time0)))
+            self._prior_epoch_cache = probe.date_mjd
+        return self._prior_epoch_cache
+
+    def forward_batch(self, n, mode=N.SCREEN_ANALYTIC, device_sampling=True):
         """n independent draws of the space segment of forward() in one fused launch.  Returns a dict of
         numpy arrays [n]: conj (the reference's `if i_conj:` truthiness), prefiltered, prop_error, i_min,
         d_min, i_conj, d_conj, time_min, plus the raw draws (`t_raw`, `c_raw`) and SGP4 inputs."""
-        t_raw, el_t, ep_t = self.sample_elements('t', n)
-        c_raw, el_c, ep_c = self.sample_elements('c', n)
+        def draw(who):
+            given = self._t_tle if who == 't' else self._c_tle
+            full_prior = given is None and type(self).sample_elements is Conjunction.sample_elements
+            if device_sampling and full_prior and self._device_prior() is not None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())      # torch.manual_seed governs reproducibility
+                return self.sample_elements_device(who, n, seed)
+            return self.sample_elements(who, n)
+        t_raw, el_t, ep_t = draw('t')
+        c_raw, el_c, ep_c = draw('c')
         sma = lambda raw: (MU_EARTH / np.maximum(raw['mean_motion'], 1e-300) ** 2) ** (1.0 / 3.0)
         a_t, a_c = sma(t_raw), sma(c_raw)
         apo = lambda a, raw: a * (1 + raw['eccentricity']) - R_EARTH

@@ -238,3 +238,53 @@ def test_newton_and_partials_kernels(kb, golden, refnpz):
     assert abs(new.date_mjd - (t.date_mjd + 0.3)) < 2e-8 and yy.shape == (6,)
     want = sgp4.propagate(t, 0.3 * 1440.0).numpy()
     assert np.abs(sgp4.propagate(new, 0.0).numpy() - want)[0].max() < 0.05
+
+
+def test_device_prior_sampling(kb):
+    """ksl_sample_prior: same distributions as the host priors (two-sample KS per field), TLE-text quantisation
+    bit-equal to the host formatter, draws keyed by the global index, and forward_batch() on top of it."""
+    from scipy import stats
+    from kessler_b200 import engine
+    M = kb["M"]
+    torch.manual_seed(21)
+    model = M.Conjunction()
+    params = model._device_prior()
+    assert params is not None
+    n = 200000
+    raw, el, flag = engine.sample_prior(params, 5, 0, n)
+    raw, el, flag = raw.cpu().numpy(), el.cpu().numpy(), flag.cpu().numpy()
+    assert flag.mean() < 1e-4
+    ok = flag == 0
+    want = M.quantize_sgp4_inputs(raw[0], raw[2], raw[3], raw[5], raw[4], raw[1], raw[7])
+    assert np.array_equal(el[:, ok], want[:, ok])                      # device quantisation == text round trip
+    pr = model._prior_dict
+    for k, name in enumerate(engine.PRIOR_FIELDS):
+        host = pr[name + "_prior"].sample((n,)).double().numpy()
+        ks = stats.ks_2samp(raw[k], host)
+        assert ks.pvalue > 1e-4, (name, ks)
+    assert (raw[0] >= 0).all() and (raw[0] <= 0.004).all() and (raw[2] >= 0).all() and (raw[2] <= 0.9).all()
+    assert (raw[3] >= 0).all() and (raw[3] <= np.pi).all()
+    a, _, _ = engine.sample_prior(params, 5, 0, 1000)
+    b, _, _ = engine.sample_prior(params, 5, 1000, 1000)
+    assert np.array_equal(np.concatenate([a.cpu().numpy(), b.cpu().numpy()], axis=1), raw[:, :2000])
+    c, _, _ = engine.sample_prior(params, 6, 0, 1000)
+    assert not np.array_equal(c.cpu().numpy(), raw[:, :1000])
+    # forward_batch on device draws: reproducible under torch.manual_seed, consistent with the oracle
+    torch.manual_seed(33)
+    b1 = model.forward_batch(20000)
+    torch.manual_seed(33)
+    b2 = model.forward_batch(20000)
+    assert np.array_equal(b1["elems_c"], b2["elems_c"]) and np.array_equal(b1["i_min"], b2["i_min"])
+    assert 0.2 < b1["prefiltered"].mean() < 0.99 and b1["prop_error"].sum() > 0
+    k = np.nonzero(~b1["prefiltered"] & ~b1["prop_error"])[0][:5]
+    times = model.time_grid()
+    ref = C.screen(b1["elems_t"][:, k].copy(), b1["epoch_t"][k], b1["elems_c"][:, k].copy(), b1["epoch_c"][k], times[::100].copy(),
+                   len(times), 5e3)
+    assert np.array_equal(ref["i_min"], b1["i_min"][k]) and np.array_equal(ref["i_conj"], b1["i_conj"][k])
+    # replay of a device draw through make_target reproduces the same SGP4 inputs
+    model._replay = model._replay_values(b1, int(k[0]))
+    t_tle, c_tle = model.make_target(), model.make_chaser()
+    model._replay = {}
+    assert np.array_equal(t_tle.elements(), b1["elems_t"][:, k[0]]) and np.array_equal(c_tle.elements(), b1["elems_c"][:, k[0]])
+    host_batch = model.forward_batch(2000, device_sampling=False)
+    assert host_batch["elems_t"].shape == (7, 2000)
