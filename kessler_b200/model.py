@@ -531,8 +531,9 @@ class Conjunction:
     def _device_prior(self):
         """Packed parameters of the prior for ksl_sample_prior, or None when the prior is not made of the
         default prior's families (uniform / mixture of normals / mixture of truncated normals)."""
-        if getattr(self, "_device_prior_cache", None) is not None:
-            return self._device_prior_cache or None
+        cached = getattr(self, "_device_prior_cache", None)
+        if cached is not None:
+            return None if cached is False else cached
         fields = []
         for name in engine.PRIOR_FIELDS:
             d = self._prior_dict.get(name + "_prior")
