@@ -225,6 +225,49 @@ def to_cdms(model, res, e, t_tle=None, c_tle=None):
     return cdms
 
 
+_RTN = ("R", "T", "N", "RDOT", "TDOT", "NDOT")
+LSTM_FEATURES = (["__CREATION_DATE", "__TCA", "MISS_DISTANCE", "RELATIVE_SPEED", "RELATIVE_POSITION_R", "RELATIVE_POSITION_T",
+                  "RELATIVE_POSITION_N", "RELATIVE_VELOCITY_R", "RELATIVE_VELOCITY_T", "RELATIVE_VELOCITY_N"] +
+                 [f"OBJECT{o}_{k}" for o in (1, 2)
+                  for k in ["X", "Y", "Z", "X_DOT", "Y_DOT", "Z_DOT"] + [f"C{_RTN[i]}_{_RTN[j]}" for i in range(6) for j in range(i + 1)]])
+
+
+def feature_tensor(res):
+    """Struct-of-arrays form of the CDM sequences of a generate_cdm_batch() result: the 64 default input features
+    of the reference's LSTMPredictor (/root/reference/kessler/nn.py:60-123) for every issued CDM, without building
+    CDM objects.  Returns (features [n_cdm, 64] float64 in LSTM_FEATURES order, event_ptr [E + 1]: the CDMs of event e
+    are rows event_ptr[e]:event_ptr[e + 1], in issue order).  `__CREATION_DATE` / `__TCA` are days since the event's
+    first CDM, through the CDM date strings (event.py:42-47)."""
+    E, I = res["issued"].shape
+    creation_str = [util.from_jd_to_cdm_datetime_str(util.from_mjd_to_jd(t)) for t in res["time_cdm"]]
+    day0 = "2000-01-01T00:00:00.000000"
+    creation_days = np.array([util.from_date_str_to_days(c, date0=day0) for c in creation_str])
+    tca_days = np.array([util.from_date_str_to_days(util.from_jd_to_cdm_datetime_str(util.from_mjd_to_jd(t)), date0=day0)
+                         for t in res["tca_mjd"]])
+    e_i, c_i = np.nonzero(res["issued"])
+    n = len(e_i)
+    first = np.array([np.nonzero(res["issued"][e])[0][0] if res["issued"][e].any() else 0 for e in range(E)])
+    feats = np.empty((n, len(LSTM_FEATURES)))
+    feats[:, 0] = creation_days[c_i] - creation_days[first[e_i]]
+    feats[:, 1] = tca_days[e_i] - creation_days[first[e_i]]
+    st = res["state_itrf_km"][e_i, c_i]                                  # [n, 2, 6] km, km/s
+    s1, s2 = st[:, 0] * 1e3, st[:, 1] * 1e3
+    rot = _rotation_matrices(s1)
+    rel_p = np.einsum("nij,nj->ni", rot, s2[:, :3] - s1[:, :3])
+    rel_v = np.einsum("nij,nj->ni", rot, s2[:, 3:] - s1[:, 3:])
+    feats[:, 2] = np.linalg.norm(s1[:, :3] - s2[:, :3], axis=1)
+    feats[:, 3] = np.linalg.norm(rel_v, axis=1)
+    feats[:, 4:7], feats[:, 7:10] = rel_p, rel_v
+    tril = np.tril_indices(6)
+    cv = res["cov_rtn"][e_i, c_i]
+    for o in (0, 1):
+        base = 10 + 27 * o
+        feats[:, base:base + 6] = st[:, o]
+        feats[:, base + 6:base + 27] = cv[:, o][:, tril[0], tril[1]]
+    ptr = np.concatenate([[0], np.cumsum(res["issued"].sum(axis=1))])
+    return feats, ptr
+
+
 _BATCH_KEYS = ("elems_t", "elems_c", "epoch_t", "epoch_c", "time_min", "i_min", "d_min", "i_conj", "d_conj")
 
 

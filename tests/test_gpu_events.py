@@ -141,3 +141,20 @@ def test_generate_events_driver(setup):
         assert np.isfinite(r["state_itrf_km"][r["issued"]]).all() and np.isfinite(r["cov_rtn"][r["issued"]]).all()
         assert ((r["pc"][r["issued"]] >= 0) & (r["pc"][r["issued"]] <= 1)).all()
         assert (np.einsum("eoii->eo", r["cov_rtn"][:, 0, :, :3, :3]) > 0).all()      # positive position variances
+
+
+def test_feature_tensor_matches_cdm_objects(setup):
+    """events.feature_tensor (SoA, no CDM objects) == the same 64 LSTM input features read from the CDM objects
+    with the reference's Event semantics for __CREATION_DATE / __TCA (event.py:42-47)."""
+    ev_mod, model, batch, hits, util = setup["events"], setup["model"], setup["batch"], setup["hits"], setup["util"]
+    res = ev_mod.generate_cdm_batch(model, batch, hits, seed=3)
+    feats, ptr = ev_mod.feature_tensor(res)
+    assert feats.shape == (int(res["issued"].sum()), 64) and len(ev_mod.LSTM_FEATURES) == 64 and ptr[-1] == len(feats)
+    for e in range(len(hits)):
+        cdms = ev_mod.to_cdms(model, res, e)
+        assert len(cdms) == ptr[e + 1] - ptr[e]
+        date0 = cdms[0]["CREATION_DATE"]
+        for row, cdm in zip(feats[ptr[e]:ptr[e + 1]], cdms):
+            want = [util.from_date_str_to_days(cdm["CREATION_DATE"], date0=date0), util.from_date_str_to_days(cdm["TCA"], date0=date0)]
+            want += [cdm[k] for k in ev_mod.LSTM_FEATURES[2:]]
+            assert np.allclose(row, np.array(want, dtype=np.float64), rtol=1e-12, atol=1e-9)
