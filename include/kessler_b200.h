@@ -219,8 +219,10 @@ int ksl_states_at_fine(const double *consts, int64_t n_rec, const int64_t *rec, 
 /* ksl_pc_mvn_batched: model.py:424-437 for n_cdm CDMs at once.  mean [n_cdm][2][3] and chol [n_cdm][2][6]
  * (row-major lower triangle of the 3x3 Cholesky factor) describe the Gaussian position samples of target (0)
  * and chaser (1); n_pts samples each are drawn on the device (Philox keyed by (seed, cdm_id0 + cdm, object,
- * point)) and counts[cdm] = #{(i, j): ||t_i - c_j|| < thr_m}.  points_ws: n_cdm*2*3*n_pts doubles (returned
- * filled: [n_cdm][2][3][n_pts], so a test can recount on identical samples). */
+ * point)) and counts[cdm] = #{(i, j): ||t_i - c_j|| < thr_m}.  points_ws: n_cdm*2*(3*n_pts + 6) doubles; the first
+ * n_cdm*2*3*n_pts are returned filled with the samples [n_cdm][2][3][n_pts] (a test can recount on identical
+ * samples), the rest holds the clouds' bounding boxes, which let CDMs whose clouds are further apart than thr_m
+ * contribute their exact 0 without a pair loop. */
 int ksl_pc_mvn_batched(const double *mean, const double *chol, int64_t n_cdm, int64_t n_pts, uint64_t seed, int64_t cdm_id0,
                        double thr_m, unsigned long long *counts, double *points_ws, void *stream);
 

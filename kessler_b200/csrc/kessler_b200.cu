@@ -1045,12 +1045,54 @@ __global__ void __launch_bounds__(256) k_mvn_points(const double *__restrict__ m
     }
 }
 
-// all-pairs count per CDM: grid = (target tiles, n_cdm); counts[cdm] accumulated
+// axis-aligned bounding box of every point cloud: bbox [n_cdm][2][6] = (min x,y,z, max x,y,z); one CTA per cloud
+__global__ void __launch_bounds__(256) k_points_bbox(const double *__restrict__ pts, long long n_pts, double *__restrict__ bbox) {
+    const double *p = pts + (long long)blockIdx.x * 3 * n_pts;
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (long long i = threadIdx.x; i < n_pts; i += blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double v = p[a * n_pts + i];
+            lo[a] = fmin(lo[a], v);
+            hi[a] = fmax(hi[a], v);
+        }
+    }
+    __shared__ double s[8][6];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        for (int d = 16; d > 0; d >>= 1) {
+            lo[a] = fmin(lo[a], __shfl_down_sync(0xffffffffu, lo[a], d));
+            hi[a] = fmax(hi[a], __shfl_down_sync(0xffffffffu, hi[a], d));
+        }
+        if ((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5][a] = lo[a]; s[threadIdx.x >> 5][3 + a] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = s[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fmin(v, s[w][threadIdx.x]) : fmax(v, s[w][threadIdx.x]);
+        bbox[(long long)blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
+// all-pairs count per CDM: grid = (target tiles, n_cdm); counts[cdm] accumulated.  A CDM whose two clouds are
+// further apart than the threshold box-to-box (most of them: the clouds sit at the two objects' own radii,
+// model.py:426-427) contributes 0 without visiting a single pair -- the count stays exact.
 __global__ void __launch_bounds__(kPcThreads) k_pc_all_pairs_batched(const double *__restrict__ pts, long long n_pts, double thr2,
+                                                                     const double *__restrict__ bbox,
                                                                      unsigned long long *__restrict__ counts) {
     __shared__ double sx[kPcTile], sy[kPcTile], sz[kPcTile];
     __shared__ unsigned long long s_total;
     const long long cdm = blockIdx.y;
+    {
+        const double *bt = bbox + (cdm * 2 + 0) * 6, *bc = bbox + (cdm * 2 + 1) * 6;
+        double gap2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double g = fmax(0.0, fmax(bt[a] - bc[3 + a], bc[a] - bt[3 + a]));
+            gap2 += g * g;
+        }
+        if (gap2 > thr2 * (1.0 + 1e-9) + 1e-6) return;   // uniform over the CTA
+    }
     const double *t = pts + (cdm * 2 + 0) * 3 * n_pts, *c = pts + (cdm * 2 + 1) * 3 * n_pts;
     const long long i = (long long)blockIdx.x * kPcThreads + threadIdx.x;
     const bool have = i < n_pts;
@@ -1517,7 +1559,7 @@ int ksl_pc_mvn_batched(const double *mean, const double *chol, int64_t n_cdm, in
     if (n_cdm < 0 || n_pts <= 0 || (n_cdm > 0 && (!mean || !chol || !counts || !points_ws)))
         return fail(KSL_E_ARG, "ksl_pc_mvn_batched: bad argument");
     if (n_cdm == 0) return KSL_OK;
-    if (n_cdm > 65535) return fail(KSL_E_ARG, "ksl_pc_mvn_batched: at most 65535 CDMs per call");
+    if (n_cdm > 32767) return fail(KSL_E_ARG, "ksl_pc_mvn_batched: at most 32767 CDMs per call");
     int sms = 0;
     int rc = sm_count(&sms);
     if (rc) return rc;
@@ -1527,8 +1569,11 @@ int ksl_pc_mvn_batched(const double *mean, const double *chol, int64_t n_cdm, in
     k_mvn_points<<<(unsigned)blocks, 256, 0, S(stream)>>>(mean, chol, n_cdm, n_pts, (unsigned long long)seed, cdm_id0, points_ws);
     KSL_LAUNCH_CHECK();
     KSL_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (size_t)n_cdm, S(stream)));
+    double *bbox = points_ws + (size_t)n_cdm * 2 * 3 * (size_t)n_pts;
+    k_points_bbox<<<(unsigned)(n_cdm * 2), 256, 0, S(stream)>>>(points_ws, n_pts, bbox);
+    KSL_LAUNCH_CHECK();
     dim3 grid((unsigned)((n_pts + kPcThreads - 1) / kPcThreads), (unsigned)n_cdm);
-    k_pc_all_pairs_batched<<<grid, kPcThreads, 0, S(stream)>>>(points_ws, n_pts, thr_m * thr_m, counts);
+    k_pc_all_pairs_batched<<<grid, kPcThreads, 0, S(stream)>>>(points_ws, n_pts, thr_m * thr_m, bbox, counts);
     KSL_LAUNCH_CHECK();
     return KSL_OK;
 }

@@ -255,9 +255,10 @@ def pc_mvn_batched(mean, chol, n_pts, thr_m, seed=0, cdm_id0=0, return_points=Fa
     pts_all = []
     while done < n_cdm:                       # bounded workspace: <= 4096 CDMs per launch
         m = min(4096, n_cdm - done)
-        ws = torch.empty((m, 2, 3, int(n_pts)), dtype=F64, device=dev)
+        ws_flat = torch.empty(m * 2 * (3 * int(n_pts) + 6), dtype=F64, device=dev)
+        ws = ws_flat[:m * 2 * 3 * int(n_pts)].view(m, 2, 3, int(n_pts))
         N.check(N.lib().ksl_pc_mvn_batched(ptr(mean[done:done + m].contiguous()), ptr(tri_d[done:done + m].contiguous()), m, int(n_pts),
-                                           int(seed), int(cdm_id0) + done, float(thr_m), ptr(counts[done:]), ptr(ws), stream_ptr()),
+                                           int(seed), int(cdm_id0) + done, float(thr_m), ptr(counts[done:]), ptr(ws_flat), stream_ptr()),
                 "ksl_pc_mvn_batched")
         if return_points:
             pts_all.append(ws)

@@ -48,17 +48,37 @@ def _blockdiag2(R):
 
 
 def _teme_to_itrf(states_m, jd):
-    """util.from_TEME_to_ITRF vectorised: states [n, 6] metres, jd [n]."""
+    """util.from_TEME_to_ITRF vectorised: states [n, 6] metres, jd [n] (same arithmetic per row)."""
+    jd = np.asarray(jd, dtype=np.float64)
+    t = (jd - 2451545.0) / 36525.0
+    g = 67310.54841 + (8640184.812866 + (0.093104 + (-6.2e-6) * t) * t) * t
+    dg = 8640184.812866 + (0.093104 * 2.0 + (-6.2e-6 * 3.0) * t) * t
+    theta = (np.mod(jd, 1.0) + np.mod(g / 86400.0, 1.0)) * (2.0 * math.pi)
+    theta_dot = (1.0 + dg / 86400.0 / 36525.0) * (2.0 * math.pi)
+    c, s = np.cos(theta), np.sin(theta)
+    x, y, z = states_m[:, 0], states_m[:, 1], states_m[:, 2]
+    vx, vy, vz = states_m[:, 3] * 86400.0, states_m[:, 4] * 86400.0, states_m[:, 5] * 86400.0
+    rx, ry = c * x + s * y, -s * x + c * y
+    # v' = R v + (0, 0, -theta_dot) x r'
+    wx, wy = theta_dot * ry, -theta_dot * rx
     out = np.empty_like(states_m)
-    for k in np.unique(jd):           # few distinct TCAs per batch (one per event)
-        sel = jd == k
-        theta, theta_dot = util._theta_gmst1982(float(k))
-        c, s = math.cos(theta), math.sin(theta)
-        R = np.array([[c, s, 0.0], [-s, c, 0.0], [0.0, 0.0, 1.0]])
-        r_new = states_m[sel, :3] @ R.T
-        v_day = (states_m[sel, 3:] * 86400.0) @ R.T + np.cross(np.array([0.0, 0.0, -theta_dot]), r_new)
-        out[sel, :3], out[sel, 3:] = r_new, v_day / 86400.0
+    out[:, 0], out[:, 1], out[:, 2] = rx, ry, z
+    out[:, 3], out[:, 4], out[:, 5] = (c * vx + s * vy + wx) / 86400.0, (-s * vx + c * vy + wy) / 86400.0, vz / 86400.0
     return out
+
+
+def _batched_cholesky(A):
+    """Cholesky factors of a stack of matrices; rows that are not positive definite get ok = False (and L = 0)."""
+    try:
+        return np.linalg.cholesky(A), np.ones(len(A), dtype=bool)
+    except np.linalg.LinAlgError:
+        L, ok = np.zeros_like(A), np.ones(len(A), dtype=bool)
+        for k in range(len(A)):
+            try:
+                L[k] = np.linalg.cholesky(A[k])
+            except np.linalg.LinAlgError:
+                ok[k] = False
+        return L, ok
 
 
 def obs_epoch_mjd(time_mjd):
@@ -142,16 +162,10 @@ def generate_cdm_batch(model, batch, hits, seed=0, t_new_obs=None, c_new_obs=Non
     Cov[fix] = 0.5 * (Cov[fix] + np.transpose(Cov[fix], (0, 2, 1))) + 1e-10 * np.eye(6)
     mean_els = np.stack([(MU_EARTH / raw_mm ** 2) ** (1.0 / 3.0), q[1], q[2], q[3], q[4], q[5]], axis=1)
     # ---- element clouds (model.py:497-541) ------------------------------------------------------------------
-    L = np.zeros_like(Cov)
-    chol_ok = np.ones(n_items, dtype=bool)
-    for k in range(n_items):
-        try:
-            L[k] = np.linalg.cholesky(Cov[k])
-        except np.linalg.LinAlgError:         # the reference's "Expected parameter covariance_matrix" branch
-            chol_ok[k] = False
+    L, chol_ok = _batched_cholesky(Cov)       # not PD: the reference's "Expected parameter covariance_matrix" branch
     if z_elements is None:
         z_elements = torch.randn((n_items, S, 6), dtype=torch.float64, generator=g).numpy()
-    samples = mean_els[:, None, :] + np.einsum("nsj,nij->nsi", z_elements, L)
+    samples = mean_els[:, None, :] + np.matmul(z_elements, np.transpose(L, (0, 2, 1)))
     samples[~chol_ok] = mean_els[~chol_ok][:, None, :]
     flat = samples.reshape(-1, 6)
     mm = (MU_EARTH / flat[:, 0] ** 3) ** 0.5
@@ -163,9 +177,10 @@ def generate_cdm_batch(model, batch, hits, seed=0, t_new_obs=None, c_new_obs=Non
     mc = rv_s[:, 0, :].cpu().numpy().reshape(n_items, S, 6) * 1e3
     mean_state = mc.mean(axis=1)
     Rm = _rotation_matrices(mean_state)
-    rtn = np.concatenate([np.einsum("nij,nsj->nsi", Rm, mc[:, :, :3]), np.einsum("nij,nsj->nsi", Rm, mc[:, :, 3:])], axis=2)
+    RmT = np.transpose(Rm, (0, 2, 1))
+    rtn = np.concatenate([np.matmul(mc[:, :, :3], RmT), np.matmul(mc[:, :, 3:], RmT)], axis=2)
     d = rtn - rtn.mean(axis=1, keepdims=True)
-    cov_rtn = np.einsum("nsi,nsj->nij", d, d) / (S - 1)
+    cov_rtn = np.matmul(np.transpose(d, (0, 2, 1)), d) / (S - 1)
     cov_rtn[~chol_ok] = np.einsum("ni,ij->nij", cov_diag[~chol_ok], np.eye(6))
     tca_jd = util.from_mjd_to_jd(time_min)
     state_itrf_km = _teme_to_itrf(mean_state, tca_jd[ev]) / 1e3
@@ -185,14 +200,8 @@ def generate_cdm_batch(model, batch, hits, seed=0, t_new_obs=None, c_new_obs=Non
     Rr = _rotation_matrices(s_m.reshape(-1, 6)).reshape(len(e_i), 2, 3, 3)
     mean_rtn = np.einsum("nkij,nkj->nki", Rr, s_m[:, :, :3])
     cov3 = cv[e_i, c_i][:, :, :3, :3]
-    L3 = np.zeros_like(cov3)
-    pc_ok = np.ones(len(e_i), dtype=bool)
-    for k in range(len(e_i)):
-        for o in range(2):
-            try:
-                L3[k, o] = np.linalg.cholesky(cov3[k, o])
-            except np.linalg.LinAlgError:
-                pc_ok[k] = False
+    L3f, ok3 = _batched_cholesky(cov3.reshape(-1, 3, 3))
+    L3, pc_ok = L3f.reshape(cov3.shape), ok3.reshape(-1, 2).all(axis=1)
     counts = engine.pc_mvn_batched(mean_rtn, L3, n_pc, model._collision_threshold, seed=int(seed) + 1).cpu().numpy()
     pc = np.full((E, I), np.nan)
     pc[e_i, c_i] = np.where(pc_ok, counts / float(n_pc * n_pc), np.nan)
