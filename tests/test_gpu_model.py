@@ -288,3 +288,39 @@ def test_device_prior_sampling(kb):
     assert np.array_equal(t_tle.elements(), b1["elems_t"][:, k[0]]) and np.array_equal(c_tle.elements(), b1["elems_c"][:, k[0]])
     host_batch = model.forward_batch(2000, device_sampling=False)
     assert host_batch["elems_t"].shape == (7, 2000)
+
+
+def test_default_prior_forward_and_batch(kb):
+    """The full-prior model (no TLE given): traced forward() runs through TLE(dict) objects built at time0, and the
+    batched front end classifies draws the same way (pre-filter / deep-space / screened)."""
+    M, ppl = kb["M"], kb["ppl"]
+    torch.manual_seed(8)
+    np.random.seed(8)
+    model = M.Conjunction()
+    kinds = {"prefiltered": 0, "prop_error": 0, "screened": 0}
+    for _ in range(12):
+        tr = ppl.poutine.trace(model.forward).get_trace()
+        assert "conj" in tr.nodes and "t_mean_motion" in tr.nodes and "c_b_star" in tr.nodes
+        if "time0" not in tr.nodes:
+            kinds["prefiltered"] += 1
+        elif "c_prop_error" not in tr.nodes:
+            kinds["prop_error"] += 1
+        else:
+            kinds["screened"] += 1
+            assert "mc_prop_error" in tr.nodes and "num_cdms" in tr.nodes
+    assert sum(kinds.values()) == 12 and kinds["prefiltered"] > 0
+    b = model.forward_batch(4096)
+    # replaying batched draws through forward() gives the same classification and, when screened, the same result
+    for k in list(np.nonzero(b["prefiltered"])[0][:2]) + list(np.nonzero(b["prop_error"])[0][:2]) + \\
+            list(np.nonzero(~b["prefiltered"] & ~b["prop_error"])[0][:3]):
+        model._replay = model._replay_values(b, int(k))
+        tr = ppl.poutine.trace(model.forward).get_trace()
+        model._replay = {}
+        if b["prefiltered"][k]:
+            assert "time0" not in tr.nodes and not bool(tr.nodes["conj"]["value"])
+        elif b["prop_error"][k]:
+            assert "time0" in tr.nodes and "c_prop_error" not in tr.nodes
+        else:
+            assert "c_prop_error" in tr.nodes and bool(tr.nodes["conj"]["value"]) == bool(b["conj"][k])
+            if b["conj"][k]:
+                assert int(tr.nodes["i_conj"]["value"]) == b["i_conj"][k]
