@@ -311,8 +311,9 @@ def test_default_prior_forward_and_batch(kb):
     assert sum(kinds.values()) == 12 and kinds["prefiltered"] > 0
     b = model.forward_batch(4096)
     # replaying batched draws through forward() gives the same classification and, when screened, the same result
-    for k in list(np.nonzero(b["prefiltered"])[0][:2]) + list(np.nonzero(b["prop_error"])[0][:2]) + \\
-            list(np.nonzero(~b["prefiltered"] & ~b["prop_error"])[0][:3]):
+    picks = (list(np.nonzero(b["prefiltered"])[0][:2]) + list(np.nonzero(b["prop_error"])[0][:2]) +
+             list(np.nonzero(~b["prefiltered"] & ~b["prop_error"])[0][:3]))
+    for k in picks:
         model._replay = model._replay_values(b, int(k))
         tr = ppl.poutine.trace(model.forward).get_trace()
         model._replay = {}
