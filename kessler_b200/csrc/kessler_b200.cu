@@ -260,7 +260,7 @@ struct ScreenParams {
 template <bool kSharedTarget, int kMode>
 __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen(const ScreenParams p) {
     extern __shared__ double s_times[];  // [min(n_coarse, kMaxGridInSmem)]
-    __shared__ double s_ct[KSL_NCONST], s_cc[KSL_NCONST];
+    __shared__ double s_ct[ksl::KSL_NFAST], s_cc[ksl::KSL_NFAST];
     __shared__ double s_pt[kScreenThreads][3], s_pc[kScreenThreads][3];
     __shared__ Best s_scratch[32];
     __shared__ double s_epoch[2];
@@ -289,8 +289,8 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen(
             s_flags[1] = p.init_err_c ? p.init_err_c[s] : 0;
         }
         __syncthreads();
-        if (tid == 0) ksl::mask_isimp_constants(s_cc, 1);
-        if (!kSharedTarget && tid == 32) ksl::mask_isimp_constants(s_ct, 1);
+        if (tid == 0) ksl::prepare_fast_record(s_cc, 1);
+        if (!kSharedTarget && tid == 32) ksl::prepare_fast_record(s_ct, 1);
         __syncthreads();
         const int ierr_t = s_flags[0], ierr_c = s_flags[1];
         if ((ierr_t | ierr_c) & KSL_ERR_DEEPSPACE) {  // dsgp4.initialize_tle raises -> prop error (model.py:584,595)
@@ -364,18 +364,18 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen(
 // per-warp slice of shared memory, and the only block-wide barrier is the one after the time
 // grid is staged.  Warps therefore drift apart and the FP64 pipe sees a mix of the FP64-dense
 // and the integer/selection phases of different warps instead of CTA-wide lock-step phases
-// (ncu, round 1: FP64 pipe 57 % active with `wait` + `barrier` on top).  Cost: one of every 32
-// epochs is evaluated twice (the chunk overlap).  Used when there are enough samples to fill
-// the machine with warps; k_screen (CTA per trace) serves small batches.
+// (ncu, round 1: FP64 pipe 57 % active with `wait` + `barrier` on top).  Used when there are
+// enough samples to fill the machine with warps; k_screen (CTA per trace) serves small batches.
 // ------------------------------------------------------------------------------------
 constexpr int kWarpsPerCta = kScreenThreads / 32;
 
-__device__ __forceinline__ double shfl_down_d(double v, int delta) { return __shfl_down_sync(0xffffffffu, v, delta); }
+__device__ __forceinline__ double shfl_up_d(double v, int delta) { return __shfl_up_sync(0xffffffffu, v, delta); }
 
 template <bool kSharedTarget, int kMode>
 __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_warp(const ScreenParams p) {
     extern __shared__ double s_times[];
-    __shared__ double s_c[kWarpsPerCta][2][KSL_NCONST];
+    __shared__ double s_c[kWarpsPerCta][2][ksl::KSL_NFAST];
+    __shared__ double s_carry_all[kWarpsPerCta][9];   // lane 31's (d, target, chaser) for the next chunk's lane 0
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool grid_in_smem = KSL_SCREEN_GRID_SMEM && p.n_coarse <= kMaxGridInSmem;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
     const int *ja_tab = ja_in_smem ? s_ja : nullptr;
     __syncthreads();
 
-    double *s_ct = s_c[warp][0], *s_cc = s_c[warp][1];
+    double *s_ct = s_c[warp][0], *s_cc = s_c[warp][1], *s_carry = s_carry_all[warp];
     const long long warps_total = (long long)gridDim.x * kWarpsPerCta;
     const long long last = p.n_coarse - 1;
     for (long long s = (long long)blockIdx.x * kWarpsPerCta + warp; s < p.n; s += warps_total) {
@@ -403,8 +403,8 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
         const double epoch_t = p.epoch_t[it], epoch_c = p.epoch_c[s];
         const int ierr_t = p.init_err_t ? p.init_err_t[it] : 0, ierr_c = p.init_err_c ? p.init_err_c[s] : 0;
         __syncwarp();
-        if (lane == 0) ksl::mask_isimp_constants(s_cc, 1);
-        if (!kSharedTarget && lane == 1) ksl::mask_isimp_constants(s_ct, 1);
+        if (lane == 0) ksl::prepare_fast_record(s_cc, 1);
+        if (!kSharedTarget && lane == 1) ksl::prepare_fast_record(s_ct, 1);
         __syncwarp();
         if ((ierr_t | ierr_c) & KSL_ERR_DEEPSPACE) {
             if (lane == 0) {
@@ -419,9 +419,12 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
         Best best;
         best_init(best);
         int e_t = 0, e_c = 0;
-        for (long long base = 0; base < last || base == 0; base += 31) {
-            const long long k = base + lane;
-            double rt[3] = {0.0, 0.0, 0.0}, rc[3] = {0.0, 0.0, 0.0};
+        // lane i of a chunk evaluates epoch k = base + i and owns the segment [k-1, k] that ENDS there; lane 0
+        // finds the left end, lane 31 of the previous chunk, in the warp's carry slot (no epoch evaluated twice)
+        double rt[3] = {0.0, 0.0, 0.0}, rc[3] = {0.0, 0.0, 0.0};
+        long long k = lane;
+        for (long long base = 0; base <= last; base += 32) {
+            k = base + lane;
             if (k <= last) {
                 const double tm = grid_in_smem ? s_times[k] : __ldg(p.times_coarse + k);
                 // both fast evaluations back to back: one straight-line block with two independent
@@ -434,38 +437,52 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
                 } else {
                     ok_t = ksl::sgp4_prop_fast([&](int q) { return s_ct[q]; }, ts_t, rt);
                 }
-                if (!ok_c) e_c |= ksl::sgp4_position_exact(s_cc, 1, ts_c, rc);
-                if (!ok_t) e_t |= ksl::sgp4_position_exact(s_ct, 1, ts_t, rt);
+                // (through a scratch array: the out-of-line call takes an address, and rc / rt must stay in registers)
+                if (!ok_c) {
+                    double rx[3];
+                    e_c |= ksl::sgp4_position_exact(s_cc, 1, ts_c, rx);
+                    rc[0] = rx[0]; rc[1] = rx[1]; rc[2] = rx[2];
+                }
+                if (!ok_t) {
+                    double rx[3];
+                    e_t |= ksl::sgp4_position_exact(s_ct, 1, ts_t, rx);
+                    rt[0] = rx[0]; rt[1] = rx[1]; rt[2] = rx[2];
+                }
             }
-            // stage 1: relative position of this epoch and of the right-hand neighbour (3 shuffles)
-            const bool owner = (k < last && lane < 31) || (k == last);
+            // stage 1: relative position at this epoch (d1) and at the left-hand neighbour (d0: 3 shuffles)
+            const bool owner = k >= 1 && k <= last;
             double d0[3], d1[3];
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
-                d0[x] = rt[x] - rc[x];
-                d1[x] = shfl_down_d(d0[x], 1);
-            }
-            if (k == last) {
-#pragma unroll
-                for (int x = 0; x < 3; ++x) d1[x] = d0[x];
+                d1[x] = rt[x] - rc[x];
+                d0[x] = shfl_up_d(d1[x], 1);
+                if (lane == 0) d0[x] = s_carry[x];
             }
             const bool need = owner && (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable(d0, d1, best, p.thr2));
             // stage 2 (rare): the neighbour's full positions, then the exact candidate evaluation
             if (__any_sync(0xffffffffu, need)) {
-                double t1[3], c1[3];
+                double t0[3], c0[3];
 #pragma unroll
                 for (int x = 0; x < 3; ++x) {
-                    t1[x] = shfl_down_d(rt[x], 1);
-                    c1[x] = shfl_down_d(rc[x], 1);
+                    t0[x] = shfl_up_d(rt[x], 1);
+                    c0[x] = shfl_up_d(rc[x], 1);
+                    if (lane == 0) { t0[x] = s_carry[3 + x]; c0[x] = s_carry[6 + x]; }
                 }
-                if (need) {
-                    if (k == last) {
-#pragma unroll
-                        for (int x = 0; x < 3; ++x) { t1[x] = rt[x]; c1[x] = rc[x]; }
-                    }
-                    ksl::segment_search<kMode>(k, last, p.scale, p.n_coarse, p.n_fine, p.thr2, rt, t1, rc, c1, best, ja_tab);
-                }
+                if (need)
+                    ksl::segment_search<kMode>(k - 1, last, p.scale, p.n_coarse, p.n_fine, p.thr2, t0, rt, c0, rc, best, ja_tab);
             }
+            __syncwarp();
+            if (lane == 31) {
+#pragma unroll
+                for (int x = 0; x < 3; ++x) { s_carry[x] = d1[x]; s_carry[3 + x] = rt[x]; s_carry[6 + x] = rc[x]; }
+            }
+            __syncwarp();
+        }
+        // torch's clamped tail segment [last, last]: both ends are the last epoch
+        if (k == last) {
+            const double dl[3] = {rt[0] - rc[0], rt[1] - rc[1], rt[2] - rc[2]};
+            if (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable(dl, dl, best, p.thr2))
+                ksl::segment_search<kMode>(last, last, p.scale, p.n_coarse, p.n_fine, p.thr2, rt, rt, rc, rc, best, ja_tab);
         }
         e_t = __reduce_or_sync(0xffffffffu, e_t);
         e_c = __reduce_or_sync(0xffffffffu, e_c);

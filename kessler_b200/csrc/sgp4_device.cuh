@@ -417,6 +417,18 @@ KSL_HD double flip_sign_if(double v, int nonzero) {
     return nonzero ? -v : v;
 #endif
 }
+KSL_HD int hi_word(double t) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(t);
+#else
+    long long b;
+    memcpy(&b, &t, 8);
+    return (int)(b >> 32);
+#endif
+}
+// |x| < bound for bound = 2^e, decided on the high word: an integer compare on the ALU pipe instead of a DSETP on
+// the FP64 pipe this code is bound by.  NaN and inf give false.
+KSL_HD bool abs_below_pow2(double x, int e) { return (hi_word(x) & 0x7fffffff) < ((1023 + e) << 20); }
 // branch-free sincos for |x| < kSinCosMaxArg (callers flag anything larger for the exact path)
 constexpr double kSinCosMaxArg = 1.0e5;
 KSL_HD void sincos_cw(double x, double &s, double &c) {
@@ -499,79 +511,147 @@ KSL_HD void rotate_tiny(double d, double &s, double &c) {
 
 constexpr double kFastMaxEl2 = 0.0144;   // e <= 0.12: series for sqrt(1 - el2) good to 6e-14 relative
 
-// returns true when the result is the one sgp4_prop would give (to rounding); false = assumptions
-// violated, nothing usable written: call sgp4_prop.  err receives the Vallado bits (0 on success).
+// |d| <= 2e-3 (the three J2 short-period angles; bounded through 1/pl^2 below): 5th / 4th-order kernels,
+// truncation d^7/5040 < 3e-23 and d^6/720 < 1e-19
+constexpr double kMicroAngle = 2.0e-3;
+KSL_HD void rotate_micro(double d, double &s, double &c) {
+    const double d2 = d * d;
+    const double ps = fma_rn(d2, kTrigTab[1], kTrigTab[0]);
+    const double sd = fma_rn(ps * d2, d, d);
+    const double cd = fma_rn(fma_rn(d2, kTrigTab[5], kTrigTab[4]), d2, 1.0);
+    const double s0 = s, c0 = c;
+    s = fma_rn(s0, cd, c0 * sd);
+    c = fma_rn(c0, cd, -(s0 * sd));
+}
+
+// sincos_cw with two reduction pieces and one polynomial term less per kernel: absolute error < 1e-11, for
+// the mean-anomaly angle whose sine / cosine only enter drag terms scaled by <~ 1e-3
+KSL_HD void sincos_cw_coarse(double x, double &s, double &c) {
+    const double t = fma_rn(x, kSinCosTab[0], kSinCosTab[1]);
+    const int q = lo_word(t);
+    const double fn = t - kSinCosTab[1];
+    double r = fma_rn(-fn, kSinCosTab[2], x);
+    r = fma_rn(-fn, kSinCosTab[3], r);
+    const double z = r * r;
+    double ps = fma_rn(z, kSinCosTab[9], kSinCosTab[8]);
+    ps = fma_rn(ps, z, kSinCosTab[7]);
+    ps = fma_rn(ps, z, kSinCosTab[6]);
+    ps = fma_rn(ps, z, kSinCosTab[5]);
+    const double ks = fma_rn(ps * z, r, r);
+    double pc = fma_rn(z, kSinCosTab[15], kSinCosTab[14]);
+    pc = fma_rn(pc, z, kSinCosTab[13]);
+    pc = fma_rn(pc, z, kSinCosTab[12]);
+    pc = fma_rn(pc, z, kSinCosTab[11]);
+    const double kc = fma_rn(z, fma_rn(pc, z, -0.5), 1.0);
+    const bool swap = (q & 1) != 0;
+    const double sv = swap ? kc : ks;
+    const double cv = swap ? ks : kc;
+    s = flip_sign_if(sv, q & 2);
+    c = flip_sign_if(cv, (q + 1) & 2);
+}
+
+// x - 2pi_d rint(x / 2pi_d) for |x| < 1e5, where 2pi_d = 6.283185307179586 is the DOUBLE the reference's `%`
+// divides by: the remainder is exact (2pi_d split into 33 + 20 bits, both products exact), i.e. what fmod
+// leaves up to a multiple of 2pi_d, in [-pi, pi], without compare or select.
+//   [0] 1/(2 pi)  [1] 1.5*2^52  [2] 2pi_d, 33 leading bits  [3] 2pi_d - [2]
+KSL_TABLE kWrapTab[4] = {1.59154943091895345608e-01, 6755399441055744.0, 6.28318530693650245667e+00,
+                         2.43083775330887874588e-10};
+KSL_HD double wrap_pm_pi(double x) {
+    const double t = fma_rn(x, kWrapTab[0], kWrapTab[1]);
+    const double fn = t - kWrapTab[1];
+    return fma_rn(-fn, kWrapTab[3], fma_rn(-fn, kWrapTab[2], x));
+}
+
+// The fast path reads a FAST RECORD: the 36 public constants followed by products sgp4_prop rebuilds at
+// every call (prepare_fast_record fills them once per record, in the kernel's shared-memory copy).
+enum {
+    KSL_F_BC4 = KSL_NCONST,   // bstar * cc4
+    KSL_F_BC5,                // bstar * cc5 (0 when isimp)
+    KSL_F_KMRT,               // 3/4 J2 con41
+    KSL_F_KX1,                // 1/4 J2 x1mth2
+    KSL_F_KSU,                // -1/8 J2 x7thm1
+    KSL_F_KNODE,              // 3/4 J2 cosio
+    KSL_F_KINC,               // 3/4 J2 cosio sinio
+    KSL_F_PAD,
+    KSL_NFAST
+};
+
+// returns true when the result is the one sgp4_prop would give (to rounding: the angle bookkeeping below is
+// algebraically the reference's with fewer intermediate roundings, ~1e-13 rad); false = assumptions violated,
+// nothing usable written: call sgp4_prop.
 template <typename Load>
-KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: MASKED constants (see below)
+KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: fast record (prepare_fast_record)
+    // Angles that grow with t (mean anomaly, mean longitude: ~1e3 rad over the window) keep the reference's
+    // own sequence of roundings -- each costs ~1e-13 rad = 1e-9 km; everything of magnitude <= 2 pi is free
+    // to use FMAs (1e-16 rad).
     const double xmdf = mad_2r(c(KSL_C_MDOT), t, c(KSL_C_MO));
-    const double argpdf = mad_2r(c(KSL_C_ARGPDOT), t, c(KSL_C_ARGPO));
-    const double nodedf = mad_2r(c(KSL_C_NODEDOT), t, c(KSL_C_NODEO));
+    const double argpdf = fma_rn(c(KSL_C_ARGPDOT), t, c(KSL_C_ARGPO));
     const double t2 = t * t;
-    double nodem = mad_2r(c(KSL_C_NODECF), t2, nodedf);
-    const double bstar = c(KSL_C_BSTAR);
-    double tempa = 1.0 - c(KSL_C_CC1) * t;
-    double tempe = (bstar * c(KSL_C_CC4)) * t;
-    double templ = c(KSL_C_T2COF) * t2;
-    // Drag / long-period block, executed unconditionally: for an `isimp` record (perigee < 220 km) the
-    // caller hands in a MASKED copy of the constants (mask_isimp_constants: omgcof = xmcof = cc5 = 0, and
-    // sgp4init already left d2..d4, t3cof..t5cof at 0), which turns every term below into an exact +0.
+    const double nodem = fma_rn(c(KSL_C_NODECF), t2, fma_rn(c(KSL_C_NODEDOT), t, c(KSL_C_NODEO)));
+    // Drag / long-period block, executed unconditionally: for an `isimp` record (perigee < 220 km)
+    // prepare_fast_record zeroes omgcof, xmcof and bstar*cc5, and sgp4init already left d2..d4,
+    // t3cof..t5cof at 0, which turns every term below into an exact +0.
     double sx, cx;
-    sincos_cw(xmdf, sx, cx);
-    const bool ok_arg = fabs(xmdf) < kSinCosMaxArg;
+    sincos_cw_coarse(xmdf, sx, cx);
     const double delmtemp = fma_rn(c(KSL_C_ETA), cx, 1.0);
     const double delm = c(KSL_C_XMCOF) * (delmtemp * delmtemp * delmtemp - c(KSL_C_DELMO));
     const double temp0 = fma_rn(c(KSL_C_OMGCOF), t, delm);
     const double mm0 = add_rn(xmdf, temp0);
-    double argpm = add_rn(argpdf, -temp0);
-    const double t3 = t2 * t, t4 = t3 * t;
-    tempa = tempa - c(KSL_C_D2) * t2 - c(KSL_C_D3) * t3 - c(KSL_C_D4) * t4;
-    double worst = fabs(temp0);   // largest small-angle argument seen, checked once at the end
-    rotate_small(temp0, sx, cx);   // sx = sin(mm); feeds a 1e-6-weighted term
-    tempe = fma_rn(bstar * c(KSL_C_CC5), sx - c(KSL_C_SINMAO), tempe);
-    templ = templ + c(KSL_C_T3COF) * t3 + t4 * fma_rn(t, c(KSL_C_T5COF), c(KSL_C_T4COF));
-    double mm = mm0;
+    const double argpm = argpdf - temp0;
+    // tempa = 1 - cc1 t - d2 t^2 - d3 t^3 - d4 t^4;  templ = t2cof t^2 + t3cof t^3 + t4cof t^4 + t5cof t^5
+    const double tempa =
+        fma_rn(-t, fma_rn(t, fma_rn(t, fma_rn(t, c(KSL_C_D4), c(KSL_C_D3)), c(KSL_C_D2)), c(KSL_C_CC1)), 1.0);
+    const double templ =
+        t2 * fma_rn(t, fma_rn(t, fma_rn(t, c(KSL_C_T5COF), c(KSL_C_T4COF)), c(KSL_C_T3COF)), c(KSL_C_T2COF));
+    // sin(mm0) = sin(xmdf + temp0), |temp0| <= 0.1, to 2e-11 (6th-order kernels): it only feeds the
+    // bstar*cc5 term of the eccentricity (bstar*cc5 < 1e-5 even for bstar = 1e-2)
+    const double q2 = temp0 * temp0;
+    const double sd0 = fma_rn(fma_rn(q2, kTrigTab[1], kTrigTab[0]) * q2, temp0, temp0);
+    const double cd0 = fma_rn(fma_rn(fma_rn(q2, kTrigTab[6], kTrigTab[5]), q2, kTrigTab[4]), q2, 1.0);
+    const double smm = fma_rn(sx, cd0, cx * sd0);
+    const double tempe = fma_rn(c(KSL_F_BC5), smm - c(KSL_C_SINMAO), c(KSL_F_BC4) * t);
     const double am = c(KSL_C_AOBASE) * tempa * tempa;
     const double em = c(KSL_C_ECCO) - tempe;
-    bool ok = ok_arg && (em >= 1.0e-6) && (em < 0.12);   // no clamp, no error 1
-    mm = mad_2r(c(KSL_C_NO), templ, mm);
+    // validity: 2^16 < kSinCosMaxArg; |temp0| < 2^-4 for the kernels above; em < 1e-6 is clamped by the reference
+    bool ok = abs_below_pow2(xmdf, 16) && abs_below_pow2(argpm, 16) && abs_below_pow2(nodem, 3) &&
+              abs_below_pow2(temp0, -4) && (em >= 1.0e-6);
+    const double mm = mad_2r(c(KSL_C_NO), templ, mm0);
     const double xlm = add_rn(add_rn(mm, argpm), nodem);
-    nodem = wrap_twopi(nodem);
-    argpm = wrap_twopi(argpm);
-    const double xlmw = wrap_twopi(xlm);
-    mm = wrap_twopi(add_rn(add_rn(xlmw, -argpm), -nodem));
+    // The reference wraps nodem, argpm, xlm and mm = xlm - argpm - nodem to [0, 2 pi) with exact remainders
+    // and rebuilds u = (mm + argpm + nodem + long-period term) - nodem from them: modulo 2pi_d that is
+    // (nodem itself stays unwrapped: |nodem| < 3 pi, where reducing by 2pi_d or by 2 pi differs by 2e-16 rad)
+    const double lm = wrap_pm_pi(xlm) - nodem;
 
     double sarg, carg;
     sincos_cw(argpm, sarg, carg);
     const double axnl = em * carg;
     double temp = rcp_1(am * fma_rn(-em, em, 1.0));            // * aycof / xlcof ~ 1e-3: 1e-12 is plenty
     const double aynl = fma_rn(em, sarg, temp * c(KSL_C_AYCOF));
-    const double xl = add_rn(add_rn(add_rn(mm, argpm), nodem), temp * c(KSL_C_XLCOF) * axnl);
-    const double u = wrap_twopi(add_rn(xl, -nodem));
+    const double u = fma_rn(temp * c(KSL_C_XLCOF), axnl, lm);  // |u| < 4 pi
 
-    // Kepler: u = E - axnl sin E + aynl cos E
+    // Kepler: u = E - axnl sin E + aynl cos E.  The steps need no individual bound checks: with el2 < 0.0144
+    // (tested below) the Newton step from E = u is below 0.12 / 0.88 = 0.137 (11th-order rotation: 7e-18), the second
+    // below e d^2 / 2(1 - e) = 1.3e-3, the third below 1e-6; anything else (non-finite input) fails the final test.
     double se, ce;
     sincos_cw(u, se, ce);
     double den = fma_rn(-se, aynl, fma_rn(-ce, axnl, 1.0));
     double rden = rcp_2(den);
     double d = (fma_rn(axnl, se, fma_rn(-aynl, ce, u)) - u) * rden;            // first step from E = u
     double eo1 = u + d;
-    worst = fmax(worst, fabs(d));
     rotate_small(d, se, ce);
     den = fma_rn(-se, aynl, fma_rn(-ce, axnl, 1.0));
     rden = fma_rn(rden, fma_rn(-den, rden, 1.0), rden);                        // follows den to ~(e d)^2
     d = (fma_rn(axnl, se, fma_rn(-aynl, ce, u)) - eo1) * rden;
     eo1 += d;
-    ok = ok && (fabs(d) <= kTinyAngle);
     rotate_tiny(d, se, ce);
     // sweeps 3 and 4: steps <= 1e-6 (e <= 0.12), first-order rotations (error d^2/2), reciprocal reused
     d = (fma_rn(axnl, se, fma_rn(-aynl, ce, u)) - eo1) * rden;
     eo1 += d;
-    ok = ok && (fabs(d) <= 1.0e-6);
     double s_prev = se;
     se = fma_rn(d, ce, se);
     ce = fma_rn(-d, s_prev, ce);
     d = (fma_rn(axnl, se, fma_rn(-aynl, ce, u)) - eo1) * rden;
-    ok = ok && (fabs(d) < 1.0e-12);                                            // the reference's convergence test
+    ok = ok && abs_below_pow2(d, -40);   // 9.1e-13: inside the reference's convergence test (1e-12)
     s_prev = se;
     se = fma_rn(d, ce, se);
     ce = fma_rn(-d, s_prev, ce);
@@ -582,7 +662,8 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: MASKED con
     ok = ok && (el2 < kFastMaxEl2);
     const double omel2 = 1.0 - el2;
     const double pl = am * omel2;
-    const double rl = am * (1.0 - ecose);
+    const double omecose = 1.0 - ecose;
+    const double rl = am * omecose;
     double bs = fma_rn(el2, kSqrtTab[5], kSqrtTab[4]);
     bs = fma_rn(bs, el2, kSqrtTab[3]);
     bs = fma_rn(bs, el2, kSqrtTab[2]);
@@ -590,46 +671,58 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: MASKED con
     bs = fma_rn(bs, el2, kSqrtTab[0]);
     const double betal = fma_rn(bs, el2, 1.0);
     temp = esine * rcp_1(1.0 + betal);                                          // enters as e * temp ~ e^2
-    const double amorl = rcp_2(1.0 - ecose);                                    // am / rl
-    double sinu = amorl * (se - aynl - axnl * temp);
-    double cosu = amorl * (ce - axnl + aynl * temp);
+    const double amorl = rcp_2(omecose);                                        // am / rl
+    const double sinu = amorl * (se - aynl - axnl * temp);
+    const double cosu = amorl * (ce - axnl + aynl * temp);
     const double sin2u = (cosu + cosu) * sinu;
     const double cos2u = fma_rn(-2.0 * sinu, sinu, 1.0);
     const double ipl = rcp_1(pl);                                               // only inside J2 terms (5e-4)
-    const double temp1 = 0.5 * kJ2 * ipl;
-    const double temp2 = temp1 * ipl;
-    const double mrt = fma_rn(rl, fma_rn(-1.5 * temp2 * betal, c(KSL_C_CON41), 1.0), 0.5 * temp1 * c(KSL_C_X1MTH2) * cos2u);
-    const double cosio = c(KSL_C_COSIO), sinio = c(KSL_C_SINIO);
-    const double dsu = -0.25 * temp2 * c(KSL_C_X7THM1) * sin2u;
-    const double dnode = 1.5 * temp2 * cosio * sin2u;
-    const double dinc = 1.5 * temp2 * cosio * sinio * cos2u;
-    ok = ok && (worst <= kSmallAngle) && (fmax(fabs(dsu), fmax(fabs(dnode), fabs(dinc))) <= kTinyAngle);
+    const double ipl2 = ipl * ipl;
+    // mrt = rl (1 - 3/2 temp2 betal con41) + 1/2 temp1 x1mth2 cos2u,  temp1 = J2/2/pl, temp2 = temp1/pl
+    const double mrt = fma_rn(rl, fma_rn(-c(KSL_F_KMRT), ipl2 * betal, 1.0), c(KSL_F_KX1) * ipl * cos2u);
+    const double ps2 = ipl2 * sin2u;
+    const double dsu = c(KSL_F_KSU) * ps2;
+    const double dnode = c(KSL_F_KNODE) * ps2;
+    const double dinc = c(KSL_F_KINC) * (ipl2 * cos2u);
+    // |dsu|, |dnode|, |dinc| <= 3/4 J2 / pl^2 (|x7thm1| <= 6, |sin|, |cos| <= 1): one test covers the three
+    ok = ok && abs_below_pow2(ipl2, 1);   // 2 < kMicroAngle / (0.75 J2) = 2.47
 
-    const double h = fma_rn(-0.5, fma_rn(sinu, sinu, cosu * cosu) - 1.0, 1.0);  // renormalise (sinu, cosu)
-    double sinsu = sinu * h, cossu = cosu * h;
-    rotate_tiny(dsu, sinsu, cossu);
+    // (sinu, cosu) has norm 1 + O(d^2) after the first-order sweeps; h renormalises it (folded into the radius)
+    const double h = fma_rn(-0.5, fma_rn(sinu, sinu, cosu * cosu) - 1.0, 1.0);
+    double sinsu = sinu, cossu = cosu;
+    rotate_micro(dsu, sinsu, cossu);
     double snod, cnod;
     sincos_cw(nodem, snod, cnod);
-    rotate_tiny(dnode, snod, cnod);
-    double sini = sinio, cosi = cosio;
-    rotate_tiny(dinc, sini, cosi);
+    rotate_micro(dnode, snod, cnod);
+    double sini = c(KSL_C_SINIO), cosi = c(KSL_C_COSIO);
+    rotate_micro(dinc, sini, cosi);
     const double xmx = -snod * cosi, xmy = cnod * cosi;
-    const double mr = mrt * kRe;
+    const double mr = mrt * kRe * h;
     r[0] = mr * fma_rn(xmx, sinsu, cnod * cossu);
     r[1] = mr * fma_rn(xmy, sinsu, snod * cossu);
     r[2] = mr * (sini * sinsu);
     // pl < 0 is impossible with el2 < 0.0144; decay (mrt < 1) and non-finite values go to the exact path
-    return ok && (mrt >= 1.0) && (fabs(mr) < 1.0e300);
+    return ok && (mrt >= 1.0) && abs_below_pow2(mr, 996);
 }
 
-// In-place masking of a private (shared-memory / local) copy of a record for sgp4_prop_fast.  The exact
-// path ignores these three constants when isimp is set, so the masked copy serves both paths.
-KSL_HD void mask_isimp_constants(double *c, int stride) {
-    if (c[(long long)KSL_C_ISIMP * stride] != 0.0) {
-        c[(long long)KSL_C_OMGCOF * stride] = 0.0;
-        c[(long long)KSL_C_XMCOF * stride] = 0.0;
-        c[(long long)KSL_C_CC5 * stride] = 0.0;
+// In-place preparation of a private (shared-memory / local) copy of a record, KSL_NFAST entries of `stride`
+// doubles, for sgp4_prop_fast.  The exact path ignores the three masked constants when isimp is set and
+// never reads beyond KSL_NCONST, so the prepared copy serves both paths.
+KSL_HD void prepare_fast_record(double *c, int stride) {
+    auto at = [&](int k) -> double & { return c[(long long)k * stride]; };
+    if (at(KSL_C_ISIMP) != 0.0) {
+        at(KSL_C_OMGCOF) = 0.0;
+        at(KSL_C_XMCOF) = 0.0;
+        at(KSL_C_CC5) = 0.0;
     }
+    at(KSL_F_BC4) = at(KSL_C_BSTAR) * at(KSL_C_CC4);
+    at(KSL_F_BC5) = at(KSL_C_BSTAR) * at(KSL_C_CC5);
+    at(KSL_F_KMRT) = 0.75 * kJ2 * at(KSL_C_CON41);
+    at(KSL_F_KX1) = 0.25 * kJ2 * at(KSL_C_X1MTH2);
+    at(KSL_F_KSU) = -0.125 * kJ2 * at(KSL_C_X7THM1);
+    at(KSL_F_KNODE) = 0.75 * kJ2 * at(KSL_C_COSIO);
+    at(KSL_F_KINC) = 0.75 * kJ2 * at(KSL_C_COSIO) * at(KSL_C_SINIO);
+    at(KSL_F_PAD) = 0.0;
 }
 
 // position at t through the fast path, falling back to the exact path when needed (c: masked record).  The exact path

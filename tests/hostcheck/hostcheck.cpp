@@ -40,9 +40,9 @@ int hc_sgp4_prop(const double *consts, int64_t n, const double *tsince, int64_t 
 int hc_sgp4_position(const double *consts, int64_t n, const double *tsince, int64_t m, double *pos, int32_t *err,
                      int32_t *fast_used) {
     for (int64_t i = 0; i < n; ++i) {
-        double cm[KSL_NCONST];
+        double cm[ksl::KSL_NFAST];
         for (int k = 0; k < KSL_NCONST; ++k) cm[k] = consts[(int64_t)k * n + i];
-        ksl::mask_isimp_constants(cm, 1);
+        ksl::prepare_fast_record(cm, 1);
         auto ld = [&](int k) { return cm[k]; };
         int e = 0;
         for (int64_t j = 0; j < m; ++j) {
@@ -90,10 +90,10 @@ int hc_screen(const double *consts_t, const double *epoch_t, int64_t n_t, const 
     for (int64_t s = 0; s < n; ++s) {
         const int64_t it = (n_t == 1) ? 0 : s;
         int et = 0, ec = 0;
-        double cmt[KSL_NCONST], cmc[KSL_NCONST];
+        double cmt[ksl::KSL_NFAST], cmc[ksl::KSL_NFAST];
         for (int q = 0; q < KSL_NCONST; ++q) { cmt[q] = consts_t[(int64_t)q * n_t + it]; cmc[q] = consts_c[(int64_t)q * n + s]; }
-        ksl::mask_isimp_constants(cmt, 1);
-        ksl::mask_isimp_constants(cmc, 1);
+        ksl::prepare_fast_record(cmt, 1);
+        ksl::prepare_fast_record(cmc, 1);
         for (int64_t k = 0; k < n_coarse; ++k) {
             et |= ksl::sgp4_position(cmt, 1, (times_coarse[k] - epoch_t[it]) * 1440.0, &pt[3 * k]);
             ec |= ksl::sgp4_position(cmc, 1, (times_coarse[k] - epoch_c[s]) * 1440.0, &pc[3 * k]);
