@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen(
                 const double *t0 = s_pt[tid], *t1 = s_pt[nb], *c0 = s_pc[tid], *c1 = s_pc[nb];
                 const double d0[3] = {t0[0] - c0[0], t0[1] - c0[1], t0[2] - c0[2]};
                 const double d1[3] = {t1[0] - c1[0], t1[1] - c1[1], t1[2] - c1[2]};
-                if (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable(d0, d1, best, p.thr2))
+                if (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable(d0, d1, best.sq, best.conj_j == ksl::kNoIndex, p.thr2))
                     ksl::segment_search<kMode>(k, last, p.scale, p.n_coarse, p.n_fine, p.thr2, t0, t1, c0, c1, best, ja_tab);
             }
             __syncthreads();
@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
     double *s_ct = s_c[warp][0], *s_cc = s_c[warp][1], *s_carry = s_carry_all[warp];
     const long long warps_total = (long long)gridDim.x * kWarpsPerCta;
     const long long last = p.n_coarse - 1;
+    long long hint = -1;   // first epoch of the pilot chunk (see below); none for a warp's first trace
     for (long long s = (long long)blockIdx.x * kWarpsPerCta + warp; s < p.n; s += warps_total) {
         const long long it = (p.n_t == 1) ? 0 : s;
         __syncwarp();
@@ -422,8 +423,15 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
         // lane i of a chunk evaluates epoch k = base + i and owns the segment [k-1, k] that ENDS there; lane 0
         // finds the left end, lane 31 of the previous chunk, in the warp's carry slot (no epoch evaluated twice)
         double rt[3] = {0.0, 0.0, 0.0}, rc[3] = {0.0, 0.0, 0.0};
+        double cutoff = INFINITY;   // warp-wide running minimum (m^2), refreshed whenever a lane visited a segment
         long long k = lane;
-        for (long long base = 0; base <= last; base += 32) {
+        // Pilot chunk (it = -1): the 32 epochs around the PREVIOUS trace's closest approach are searched first.  In a
+        // Monte Carlo batch consecutive traces are perturbations of one pair, so this seeds the warp-wide running
+        // minimum (`cutoff`) close to the final one and the skip test below then prunes nearly every other segment.  It only
+        // changes the order in which segments are visited (the pilot's epochs are evaluated again in their turn),
+        // never the result: arg-min and first crossing are order-independent (ties go to the smaller index).
+        for (long long it = (hint >= 0) ? -1 : 0, base; (base = (it < 0) ? hint : it * 32) <= last; ++it) {
+            const bool pilot = it < 0;
             k = base + lane;
             if (k <= last) {
                 const double tm = grid_in_smem ? s_times[k] : __ldg(p.times_coarse + k);
@@ -450,7 +458,7 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
                 }
             }
             // stage 1: relative position at this epoch (d1) and at the left-hand neighbour (d0: 3 shuffles)
-            const bool owner = k >= 1 && k <= last;
+            const bool owner = k >= 1 && k <= last && !(pilot && lane == 0);   // the pilot's lane 0 has no left neighbour
             double d0[3], d1[3];
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
@@ -458,7 +466,8 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
                 d0[x] = shfl_up_d(d1[x], 1);
                 if (lane == 0) d0[x] = s_carry[x];
             }
-            const bool need = owner && (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable(d0, d1, best, p.thr2));
+            const bool need = owner && (kMode == KSL_SCREEN_BRUTE ||
+                                       !ksl::segment_skippable(d0, d1, cutoff, best.conj_j == ksl::kNoIndex, p.thr2));
             // stage 2 (rare): the neighbour's full positions, then the exact candidate evaluation
             if (__any_sync(0xffffffffu, need)) {
                 double t0[3], c0[3];
@@ -470,6 +479,10 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
                 }
                 if (need)
                     ksl::segment_search<kMode>(k - 1, last, p.scale, p.n_coarse, p.n_fine, p.thr2, t0, rt, c0, rc, best, ja_tab);
+                // the smallest squared distance any lane of this trace has seen prunes every lane's later segments
+                cutoff = best.sq;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) cutoff = fmin(cutoff, __shfl_xor_sync(0xffffffffu, cutoff, d));
             }
             __syncwarp();
             if (lane == 31) {
@@ -481,7 +494,7 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
         // torch's clamped tail segment [last, last]: both ends are the last epoch
         if (k == last) {
             const double dl[3] = {rt[0] - rc[0], rt[1] - rc[1], rt[2] - rc[2]};
-            if (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable(dl, dl, best, p.thr2))
+            if (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable(dl, dl, cutoff, best.conj_j == ksl::kNoIndex, p.thr2))
                 ksl::segment_search<kMode>(last, last, p.scale, p.n_coarse, p.n_fine, p.thr2, rt, rt, rc, rc, best, ja_tab);
         }
         e_t = __reduce_or_sync(0xffffffffu, e_t);
@@ -497,6 +510,9 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
             if (kSharedTarget && p.target_err) et |= *p.target_err;
             p.err[s] = et | ((e_c | ierr_c) << KSL_ERR_CHASER_SHIFT);
         }
+        // next trace's pilot chunk: centred on the coarse segment of this trace's minimum
+        const long long j_min = __shfl_sync(0xffffffffu, best.j, 0);
+        hint = (kMode == KSL_SCREEN_BRUTE || j_min == ksl::kNoIndex) ? -1 : max(0LL, ksl::up_i0(j_min, p.scale, p.n_coarse) - 15);
     }
 }
 

@@ -120,14 +120,15 @@ KSL_HD double seg_sq(long long j, long long k, double scale, const double *t0, c
 // segment from below.  True = that bound can neither beat the running minimum nor (while no crossing has
 // been found) the threshold, so no fine point of the segment matters.  NaN / inf never skip (an infinite
 // coordinate can still produce NaN fine points through 0 * inf).
-KSL_HD bool segment_skippable(const double d0[3], const double d1[3], const Best &best, double thr2) {
+// `cur`: the running minimum (m^2) to beat -- the caller's own, or any smaller one known to belong to the same trace
+// (the warp kernel shares one across its lanes); `conj_open`: no threshold crossing found yet by this caller.
+KSL_HD bool segment_skippable(const double d0[3], const double d1[3], double cur, bool conj_open, double thr2) {
     const double bx = d1[0] - d0[0], by = d1[1] - d0[1], bz = d1[2] - d0[2];
     const double a0 = fma_rn(d0[0], d0[0], fma_rn(d0[1], d0[1], d0[2] * d0[2]));   // km^2
     const double a1 = fma_rn(d0[0], bx, fma_rn(d0[1], by, d0[2] * bz));
     const double a2 = fma_rn(bx, bx, fma_rn(by, by, bz * bz));
-    const double cur = best.sq;   // m^2; +inf until the first visit
-    // rounding of the exact evaluation vs. the closed form: << 1 m^2 + 1e-9 relative
-    const double want = (fmax(cur, (best.conj_j == kNoIndex) ? thr2 : 0.0) * (1.0 + 1e-9) + 1.0) * 1e-6 + 1e-9 * a0;
+    // cur is +inf until the first visit.  Rounding of the exact evaluation vs. the closed form: << 1 m^2 + 1e-9 relative
+    const double want = (fmax(cur, conj_open ? thr2 : 0.0) * (1.0 + 1e-9) + 1.0) * 1e-6 + 1e-9 * a0;
     const double q1 = a0 + (a1 + a1) + a2;
     const bool rising = a1 >= 0.0, falling = (a1 + a2) <= 0.0;
     const bool out = rising ? (a0 > want) : (falling ? (q1 > want) : ((a0 - want) * a2 > a1 * a1));

@@ -100,7 +100,9 @@ int hc_screen(const double *consts_t, const double *epoch_t, int64_t n_t, const 
         }
         std::vector<ksl::Best> best(kThreads);
         for (auto &b : best) ksl::best_init(b);
+        double cutoff = INFINITY;   // as k_screen_warp: the group's running minimum, refreshed after a chunk that visited
         for (long long base = 0; base < last || base == 0; base += kThreads - 1) {
+            bool visited = false;
             for (int tid = 0; tid < kThreads; ++tid) {
                 const long long k = base + tid;
                 const bool owner = (k < last && tid < kThreads - 1) || (k == last);
@@ -108,12 +110,15 @@ int hc_screen(const double *consts_t, const double *epoch_t, int64_t n_t, const 
                 const long long nb = (k == last) ? k : k + 1;
                 const double d0[3] = {pt[3 * k] - pc[3 * k], pt[3 * k + 1] - pc[3 * k + 1], pt[3 * k + 2] - pc[3 * k + 2]};
                 const double d1[3] = {pt[3 * nb] - pc[3 * nb], pt[3 * nb + 1] - pc[3 * nb + 1], pt[3 * nb + 2] - pc[3 * nb + 2]};
-                if (mode == 0 && ksl::segment_skippable(d0, d1, best[tid], thr2)) continue;
+                if (mode == 0 && ksl::segment_skippable(d0, d1, cutoff, best[tid].conj_j == ksl::kNoIndex, thr2)) continue;
+                visited = true;
                 if (mode == 0)
                     ksl::segment_search<0>(k, last, scale, n_coarse, n_fine, thr2, &pt[3 * k], &pt[3 * nb], &pc[3 * k], &pc[3 * nb], best[tid], ja_tab);
                 else
                     ksl::segment_search<1>(k, last, scale, n_coarse, n_fine, thr2, &pt[3 * k], &pt[3 * nb], &pc[3 * k], &pc[3 * nb], best[tid], ja_tab);
             }
+            if (visited)
+                for (int tid = 0; tid < kThreads; ++tid) cutoff = fmin(cutoff, best[tid].sq);
         }
         ksl::Best b = best[0];
         for (int tid = 1; tid < kThreads; ++tid) ksl::best_merge(b, best[tid]);
