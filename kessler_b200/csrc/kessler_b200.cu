@@ -371,11 +371,37 @@ constexpr int kWarpsPerCta = kScreenThreads / 32;
 
 __device__ __forceinline__ double shfl_up_d(double v, int delta) { return __shfl_up_sync(0xffffffffu, v, delta); }
 
+// Best with 32-bit indices: what k_screen_warp keeps live across its epoch loop (the launcher only picks that kernel
+// when n_fine and n_coarse fit; register pressure, not arithmetic, is what limits that loop's scheduling)
+struct BestW {
+    double sq, conj_sq;
+    int j, nan_j, conj_j;
+};
+constexpr int kNoIndexW = 0x7fffffff;
+__device__ __forceinline__ Best best_expand(const BestW &w) {
+    Best b;
+    b.sq = w.sq;
+    b.conj_sq = w.conj_sq;
+    b.j = (w.j == kNoIndexW) ? ksl::kNoIndex : (long long)w.j;
+    b.nan_j = (w.nan_j == kNoIndexW) ? ksl::kNoIndex : (long long)w.nan_j;
+    b.conj_j = (w.conj_j == kNoIndexW) ? ksl::kNoIndex : (long long)w.conj_j;
+    return b;
+}
+__device__ __forceinline__ BestW best_compact(const Best &b) {
+    BestW w;
+    w.sq = b.sq;
+    w.conj_sq = b.conj_sq;
+    w.j = (b.j == ksl::kNoIndex) ? kNoIndexW : (int)b.j;
+    w.nan_j = (b.nan_j == ksl::kNoIndex) ? kNoIndexW : (int)b.nan_j;
+    w.conj_j = (b.conj_j == ksl::kNoIndex) ? kNoIndexW : (int)b.conj_j;
+    return w;
+}
+
 template <bool kSharedTarget, int kMode>
 __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_warp(const ScreenParams p) {
     extern __shared__ double s_times[];
     __shared__ double s_c[kWarpsPerCta][2][ksl::KSL_NFAST];
-    __shared__ double s_carry_all[kWarpsPerCta][9];   // lane 31's (d, target, chaser) for the next chunk's lane 0
+    __shared__ double s_carry_all[kWarpsPerCta][8];   // lane 31's (target, chaser, float d) for the next chunk's lane 0
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool grid_in_smem = KSL_SCREEN_GRID_SMEM && p.n_coarse <= kMaxGridInSmem;
@@ -391,9 +417,10 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
     __syncthreads();
 
     double *s_ct = s_c[warp][0], *s_cc = s_c[warp][1], *s_carry = s_carry_all[warp];
+    float *s_carry_f = reinterpret_cast<float *>(s_carry + 6);
     const long long warps_total = (long long)gridDim.x * kWarpsPerCta;
-    const long long last = p.n_coarse - 1;
-    long long hint = -1;   // first epoch of the pilot chunk (see below); none for a warp's first trace
+    const int last = (int)p.n_coarse - 1;
+    int hint = -1;   // first epoch of the pilot chunk (see below); none for a warp's first trace
     for (long long s = (long long)blockIdx.x * kWarpsPerCta + warp; s < p.n; s += warps_total) {
         const long long it = (p.n_t == 1) ? 0 : s;
         __syncwarp();
@@ -417,20 +444,20 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
             }
             continue;
         }
-        Best best;
-        best_init(best);
+        BestW best = {INFINITY, 0.0, kNoIndexW, kNoIndexW, kNoIndexW};
         int e_t = 0, e_c = 0;
         // lane i of a chunk evaluates epoch k = base + i and owns the segment [k-1, k] that ENDS there; lane 0
         // finds the left end, lane 31 of the previous chunk, in the warp's carry slot (no epoch evaluated twice)
         double rt[3] = {0.0, 0.0, 0.0}, rc[3] = {0.0, 0.0, 0.0};
         double cutoff = INFINITY;   // warp-wide running minimum (m^2), refreshed whenever a lane visited a segment
-        long long k = lane;
+        float want_f = INFINITY;    // what a segment's lower bound has to exceed to be skipped (km^2), follows cutoff
+        int k = lane;
         // Pilot chunk (it = -1): the 32 epochs around the PREVIOUS trace's closest approach are searched first.  In a
         // Monte Carlo batch consecutive traces are perturbations of one pair, so this seeds the warp-wide running
         // minimum (`cutoff`) close to the final one and the skip test below then prunes nearly every other segment.  It only
         // changes the order in which segments are visited (the pilot's epochs are evaluated again in their turn),
         // never the result: arg-min and first crossing are order-independent (ties go to the smaller index).
-        for (long long it = (hint >= 0) ? -1 : 0, base; (base = (it < 0) ? hint : it * 32) <= last; ++it) {
+        for (int it = (hint >= 0) ? -1 : 0, base; (base = (it < 0) ? hint : it * 32) <= last; ++it) {
             const bool pilot = it < 0;
             k = base + lane;
             if (k <= last) {
@@ -457,17 +484,17 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
                     rt[0] = rx[0]; rt[1] = rx[1]; rt[2] = rx[2];
                 }
             }
-            // stage 1: relative position at this epoch (d1) and at the left-hand neighbour (d0: 3 shuffles)
+            // stage 1, in FP32 (conservative, see segment_skippable_f32): relative position at this epoch (d1) and
+            // at the left-hand neighbour (d0: 3 shuffles)
             const bool owner = k >= 1 && k <= last && !(pilot && lane == 0);   // the pilot's lane 0 has no left neighbour
-            double d0[3], d1[3];
+            float d0[3], d1[3];
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
-                d1[x] = rt[x] - rc[x];
-                d0[x] = shfl_up_d(d1[x], 1);
-                if (lane == 0) d0[x] = s_carry[x];
+                d1[x] = (float)(rt[x] - rc[x]);
+                d0[x] = __shfl_up_sync(0xffffffffu, d1[x], 1);
+                if (lane == 0) d0[x] = s_carry_f[x];
             }
-            const bool need = owner && (kMode == KSL_SCREEN_BRUTE ||
-                                       !ksl::segment_skippable(d0, d1, cutoff, best.conj_j == ksl::kNoIndex, p.thr2));
+            const bool need = owner && (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable_f32(d0, d1, want_f));
             // stage 2 (rare): the neighbour's full positions, then the exact candidate evaluation
             if (__any_sync(0xffffffffu, need)) {
                 double t0[3], c0[3];
@@ -475,44 +502,52 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
                 for (int x = 0; x < 3; ++x) {
                     t0[x] = shfl_up_d(rt[x], 1);
                     c0[x] = shfl_up_d(rc[x], 1);
-                    if (lane == 0) { t0[x] = s_carry[3 + x]; c0[x] = s_carry[6 + x]; }
+                    if (lane == 0) { t0[x] = s_carry[x]; c0[x] = s_carry[3 + x]; }
                 }
-                if (need)
-                    ksl::segment_search<kMode>(k - 1, last, p.scale, p.n_coarse, p.n_fine, p.thr2, t0, rt, c0, rc, best, ja_tab);
+                if (need) {
+                    Best b = best_expand(best);
+                    ksl::segment_search<kMode>(k - 1, last, p.scale, p.n_coarse, p.n_fine, p.thr2, t0, rt, c0, rc, b, ja_tab);
+                    best = best_compact(b);
+                }
                 // the smallest squared distance any lane of this trace has seen prunes every lane's later segments
                 cutoff = best.sq;
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) cutoff = fmin(cutoff, __shfl_xor_sync(0xffffffffu, cutoff, d));
+                want_f = ksl::segment_want_f32(cutoff, best.conj_j == kNoIndexW, p.thr2);
             }
             __syncwarp();
             if (lane == 31) {
 #pragma unroll
-                for (int x = 0; x < 3; ++x) { s_carry[x] = d1[x]; s_carry[3 + x] = rt[x]; s_carry[6 + x] = rc[x]; }
+                for (int x = 0; x < 3; ++x) { s_carry[x] = rt[x]; s_carry[3 + x] = rc[x]; s_carry_f[x] = d1[x]; }
             }
             __syncwarp();
         }
         // torch's clamped tail segment [last, last]: both ends are the last epoch
         if (k == last) {
             const double dl[3] = {rt[0] - rc[0], rt[1] - rc[1], rt[2] - rc[2]};
-            if (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable(dl, dl, cutoff, best.conj_j == ksl::kNoIndex, p.thr2))
-                ksl::segment_search<kMode>(last, last, p.scale, p.n_coarse, p.n_fine, p.thr2, rt, rt, rc, rc, best, ja_tab);
+            if (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable(dl, dl, cutoff, best.conj_j == kNoIndexW, p.thr2)) {
+                Best b = best_expand(best);
+                ksl::segment_search<kMode>(last, last, p.scale, p.n_coarse, p.n_fine, p.thr2, rt, rt, rc, rc, b, ja_tab);
+                best = best_compact(b);
+            }
         }
         e_t = __reduce_or_sync(0xffffffffu, e_t);
         e_c = __reduce_or_sync(0xffffffffu, e_c);
+        Best full = best_expand(best);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
-            Best o = best_shfl_down(best, d);
-            best_merge(best, o);
+            Best o = best_shfl_down(full, d);
+            best_merge(full, o);
         }
         if (lane == 0) {
-            ksl::best_result(best, p.i_min + s, p.d_min + s, p.i_conj + s, p.d_conj + s);
+            ksl::best_result(full, p.i_min + s, p.d_min + s, p.i_conj + s, p.d_conj + s);
             int et = e_t | ierr_t;
             if (kSharedTarget && p.target_err) et |= *p.target_err;
             p.err[s] = et | ((e_c | ierr_c) << KSL_ERR_CHASER_SHIFT);
         }
         // next trace's pilot chunk: centred on the coarse segment of this trace's minimum
-        const long long j_min = __shfl_sync(0xffffffffu, best.j, 0);
-        hint = (kMode == KSL_SCREEN_BRUTE || j_min == ksl::kNoIndex) ? -1 : max(0LL, ksl::up_i0(j_min, p.scale, p.n_coarse) - 15);
+        const long long j_min = __shfl_sync(0xffffffffu, full.j, 0);
+        hint = (kMode == KSL_SCREEN_BRUTE || j_min == ksl::kNoIndex) ? -1 : max(0, (int)ksl::up_i0(j_min, p.scale, p.n_coarse) - 15);
     }
 }
 
@@ -1388,8 +1423,10 @@ int ksl_screen(const double *consts_t, const double *epoch_t, const int32_t *ini
     const size_t dyn = ((KSL_SCREEN_GRID_SMEM && n_coarse <= kMaxGridInSmem) ? sizeof(double) * (size_t)n_coarse : 0) +
                        ((n_coarse <= kMaxGridInSmem && n_fine < 0x7fffffffLL) ? sizeof(int) * (size_t)(n_coarse + 2) : 0);
     // enough samples to give every resident warp its own trace -> warp-per-trace kernel, else CTA-per-trace
-    const bool per_warp = (force & KSL_SCREEN_FORCE_WARP) ||
-                          (!(force & KSL_SCREEN_FORCE_CTA) && n >= (long long)sms * KSL_SCREEN_MIN_CTAS * kWarpsPerCta);
+    // (the warp kernel keeps 32-bit epoch / fine-grid indices)
+    const bool fits32 = n_coarse < 0x7fffffffLL && n_fine < 0x7fffffffLL;
+    const bool per_warp = fits32 && ((force & KSL_SCREEN_FORCE_WARP) ||
+                                     (!(force & KSL_SCREEN_FORCE_CTA) && n >= (long long)sms * KSL_SCREEN_MIN_CTAS * kWarpsPerCta));
     long long grid = (long long)sms * KSL_SCREEN_MIN_CTAS;
     if (!per_warp && grid > n) grid = n;
 #define KSL_SCREEN_LAUNCH(SH, MD)                                                                       \

@@ -135,6 +135,27 @@ KSL_HD bool segment_skippable(const double d0[3], const double d1[3], double cur
     return out && (fabs(a0) < INFINITY) && (fabs(a2) < INFINITY);
 }
 
+// The same test in FP32, for the warp kernel's inner loop (the FP64 pipe is what that kernel is bound by; the FP32
+// pipe idles).  d0, d1: the relative positions rounded to float (km); want_km2 = segment_want(...) rounded to float.
+// Conservative: FP32 evaluation perturbs q(l) on [0, 1] by at most ~1e-6 (a0 + a2), and the margin added to the
+// target is 1e-4 (a0 + a2) -- a segment whose bound lies within that margin of the running minimum is simply visited.
+// Overflow / NaN give false.  (hostcheck: never true where the FP64 test says false with margin.)
+KSL_HD bool segment_skippable_f32(const float d0[3], const float d1[3], float want_km2) {
+    const float bx = d1[0] - d0[0], by = d1[1] - d0[1], bz = d1[2] - d0[2];
+    const float a0 = fmaf(d0[0], d0[0], fmaf(d0[1], d0[1], d0[2] * d0[2]));
+    const float a1 = fmaf(d0[0], bx, fmaf(d0[1], by, d0[2] * bz));
+    const float a2 = fmaf(bx, bx, fmaf(by, by, bz * bz));
+    const float want = fmaf(1e-4f, a0 + a2, want_km2);
+    const float q1 = a0 + (a1 + a1) + a2;
+    const bool rising = a1 >= 0.0f, falling = (a1 + a2) <= 0.0f;
+    const bool out = rising ? (a0 > want) : (falling ? (q1 > want) : ((a0 - want) * a2 > a1 * a1));
+    return out && (a0 < INFINITY) && (a2 < INFINITY);
+}
+// the target of the FP32 test: what the bound has to exceed, km^2 (cur in m^2; +inf until the first visit)
+KSL_HD float segment_want_f32(double cur, bool conj_open, double thr2) {
+    return (float)((fmax(cur, conj_open ? thr2 : 0.0) * (1.0 + 1e-9) + 1.0) * 1e-6);
+}
+
 // Visit segment k (coarse epochs k and k+1; k == last is torch's clamped tail
 // segment with both ends at `last`).  kMode = KSL_SCREEN_BRUTE enumerates every
 // fine point; KSL_SCREEN_ANALYTIC evaluates only the candidates that can hold the

@@ -458,6 +458,33 @@ KSL_HD void sincos_cw(double x, double &s, double &c) {
     c = flip_sign_if(cv, (q + 1) & 2);
 }
 
+// sincos_cw for |x| < 32 (the node, the perigee and the reduced mean longitude): two reduction pieces are enough
+// there (the third, fn * pio2_2t, is below 5e-20)
+KSL_HD void sincos_cw_near(double x, double &s, double &c) {
+    const double t = fma_rn(x, kSinCosTab[0], kSinCosTab[1]);
+    const int q = lo_word(t);
+    const double fn = t - kSinCosTab[1];
+    const double r = fma_rn(-fn, kSinCosTab[3], fma_rn(-fn, kSinCosTab[2], x));
+    const double z = r * r;
+    double ps = fma_rn(z, kSinCosTab[10], kSinCosTab[9]);
+    ps = fma_rn(ps, z, kSinCosTab[8]);
+    ps = fma_rn(ps, z, kSinCosTab[7]);
+    ps = fma_rn(ps, z, kSinCosTab[6]);
+    ps = fma_rn(ps, z, kSinCosTab[5]);
+    const double ks = fma_rn(ps * z, r, r);
+    double pc = fma_rn(z, kSinCosTab[16], kSinCosTab[15]);
+    pc = fma_rn(pc, z, kSinCosTab[14]);
+    pc = fma_rn(pc, z, kSinCosTab[13]);
+    pc = fma_rn(pc, z, kSinCosTab[12]);
+    pc = fma_rn(pc, z, kSinCosTab[11]);
+    const double kc = fma_rn(z, fma_rn(pc, z, -0.5), 1.0);
+    const bool swap = (q & 1) != 0;
+    const double sv = swap ? kc : ks;
+    const double cv = swap ? ks : kc;
+    s = flip_sign_if(sv, q & 2);
+    c = flip_sign_if(cv, (q + 1) & 2);
+}
+
 KSL_HD double rcp_seed(double b) {
 #if defined(__CUDA_ARCH__)
     double r;
@@ -476,6 +503,13 @@ KSL_HD double rcp_1(double b) {
 KSL_HD double rcp_2(double b) {
     double r = rcp_1(b);
     return fma_rn(r, fma_rn(-b, r, 1.0), r);
+}
+
+// reciprocal to full precision in three FMAs: with e = 1 - b r (|e| ~ 2^-20), r (1 + e + e^2) is off by e^3
+KSL_HD double rcp_3(double b) {
+    const double r = rcp_seed(b);
+    const double e = fma_rn(-b, r, 1.0);
+    return fma_rn(r, fma_rn(e, e, e), r);
 }
 
 // |d| <= 0.1: 11th-order kernel (truncation 2.5e-19); rotate (s, c) by d
@@ -509,15 +543,14 @@ KSL_HD void rotate_tiny(double d, double &s, double &c) {
     c = fma_rn(c0, cd, -(s0 * sd));
 }
 
-constexpr double kFastMaxEl2 = 0.0144;   // e <= 0.12: series for sqrt(1 - el2) good to 6e-14 relative
+constexpr double kFastMaxEl2 = 0.0144;   // e <= 0.12: bound behind the series for sqrt(1 - el2) and the Kepler step sizes
 
-// |d| <= 2e-3 (the three J2 short-period angles; bounded through 1/pl^2 below): 5th / 4th-order kernels,
-// truncation d^7/5040 < 3e-23 and d^6/720 < 1e-19
+// |d| <= 2e-3 (the three J2 short-period angles; bounded through 1/pl^2 below): 3rd / 4th-order kernels,
+// truncation d^5/120 < 3e-16 (1e-17 at the usual 1e-3) and d^6/720 < 1e-19
 constexpr double kMicroAngle = 2.0e-3;
 KSL_HD void rotate_micro(double d, double &s, double &c) {
     const double d2 = d * d;
-    const double ps = fma_rn(d2, kTrigTab[1], kTrigTab[0]);
-    const double sd = fma_rn(ps * d2, d, d);
+    const double sd = fma_rn(d2 * kTrigTab[0], d, d);
     const double cd = fma_rn(fma_rn(d2, kTrigTab[5], kTrigTab[4]), d2, 1.0);
     const double s0 = s, c0 = c;
     s = fma_rn(s0, cd, c0 * sd);
@@ -612,8 +645,9 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: fast recor
     const double tempe = fma_rn(c(KSL_F_BC5), smm - c(KSL_C_SINMAO), c(KSL_F_BC4) * t);
     const double am = c(KSL_C_AOBASE) * tempa * tempa;
     const double em = c(KSL_C_ECCO) - tempe;
-    // validity: 2^16 < kSinCosMaxArg; |temp0| < 2^-4 for the kernels above; em < 1e-6 is clamped by the reference
-    bool ok = abs_below_pow2(xmdf, 16) && abs_below_pow2(argpm, 16) && abs_below_pow2(nodem, 3) &&
+    // validity: 2^16 < kSinCosMaxArg; sincos_cw_near needs < 32 (and |u| < pi + 8 + 0.1); |temp0| < 2^-4 for the
+    // kernels above; em < 1e-6 is clamped by the reference
+    bool ok = abs_below_pow2(xmdf, 16) && abs_below_pow2(argpm, 5) && abs_below_pow2(nodem, 3) &&
               abs_below_pow2(temp0, -4) && (em >= 1.0e-6);
     const double mm = mad_2r(c(KSL_C_NO), templ, mm0);
     const double xlm = add_rn(add_rn(mm, argpm), nodem);
@@ -623,7 +657,7 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: fast recor
     const double lm = wrap_pm_pi(xlm) - nodem;
 
     double sarg, carg;
-    sincos_cw(argpm, sarg, carg);
+    sincos_cw_near(argpm, sarg, carg);
     const double axnl = em * carg;
     double temp = rcp_1(am * fma_rn(-em, em, 1.0));            // * aycof / xlcof ~ 1e-3: 1e-12 is plenty
     const double aynl = fma_rn(em, sarg, temp * c(KSL_C_AYCOF));
@@ -633,9 +667,9 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: fast recor
     // (tested below) the Newton step from E = u is below 0.12 / 0.88 = 0.137 (11th-order rotation: 7e-18), the second
     // below e d^2 / 2(1 - e) = 1.3e-3, the third below 1e-6; anything else (non-finite input) fails the final test.
     double se, ce;
-    sincos_cw(u, se, ce);
+    sincos_cw_near(u, se, ce);
     double den = fma_rn(-se, aynl, fma_rn(-ce, axnl, 1.0));
-    double rden = rcp_2(den);
+    double rden = rcp_3(den);
     double d = (fma_rn(axnl, se, fma_rn(-aynl, ce, u)) - u) * rden;            // first step from E = u
     double eo1 = u + d;
     rotate_small(d, se, ce);
@@ -664,14 +698,13 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: fast recor
     const double pl = am * omel2;
     const double omecose = 1.0 - ecose;
     const double rl = am * omecose;
-    double bs = fma_rn(el2, kSqrtTab[5], kSqrtTab[4]);
-    bs = fma_rn(bs, el2, kSqrtTab[3]);
-    bs = fma_rn(bs, el2, kSqrtTab[2]);
+    double bs = fma_rn(el2, kSqrtTab[4], kSqrtTab[3]);   // through x^5: 2e-13 at el2 = 0.0144, and betal only enters
+    bs = fma_rn(bs, el2, kSqrtTab[2]);                  // multiplied by e^2 or J2
     bs = fma_rn(bs, el2, kSqrtTab[1]);
     bs = fma_rn(bs, el2, kSqrtTab[0]);
     const double betal = fma_rn(bs, el2, 1.0);
     temp = esine * rcp_1(1.0 + betal);                                          // enters as e * temp ~ e^2
-    const double amorl = rcp_2(omecose);                                        // am / rl
+    const double amorl = rcp_3(omecose);                                        // am / rl
     const double sinu = amorl * (se - aynl - axnl * temp);
     const double cosu = amorl * (ce - axnl + aynl * temp);
     const double sin2u = (cosu + cosu) * sinu;
@@ -687,17 +720,16 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: fast recor
     // |dsu|, |dnode|, |dinc| <= 3/4 J2 / pl^2 (|x7thm1| <= 6, |sin|, |cos| <= 1): one test covers the three
     ok = ok && abs_below_pow2(ipl2, 1);   // 2 < kMicroAngle / (0.75 J2) = 2.47
 
-    // (sinu, cosu) has norm 1 + O(d^2) after the first-order sweeps; h renormalises it (folded into the radius)
-    const double h = fma_rn(-0.5, fma_rn(sinu, sinu, cosu * cosu) - 1.0, 1.0);
+    // (sinu, cosu) is a unit vector to d3^2 / 2 < 1e-14 (first-order rotation of the third sweep, e = 0.12)
     double sinsu = sinu, cossu = cosu;
     rotate_micro(dsu, sinsu, cossu);
     double snod, cnod;
-    sincos_cw(nodem, snod, cnod);
+    sincos_cw_near(nodem, snod, cnod);
     rotate_micro(dnode, snod, cnod);
     double sini = c(KSL_C_SINIO), cosi = c(KSL_C_COSIO);
     rotate_micro(dinc, sini, cosi);
     const double xmx = -snod * cosi, xmy = cnod * cosi;
-    const double mr = mrt * kRe * h;
+    const double mr = mrt * kRe;
     r[0] = mr * fma_rn(xmx, sinsu, cnod * cossu);
     r[1] = mr * fma_rn(xmy, sinsu, snod * cossu);
     r[2] = mr * (sini * sinsu);

@@ -75,6 +75,25 @@ int hc_kepler_partials(const double *states, int64_t n, double mu, double *eleme
 // running Best (which is what the analytic pruning sees), merged at the end.
 static int s_use_table = 1;
 int hc_set_use_table(int v) { s_use_table = v; return 0; }
+static int s_use_f32 = 1;
+int hc_set_use_f32(int v) { s_use_f32 = v; return 0; }
+
+// FP32 skip test vs the FP64 one on n segments (d0, d1: [n][3] km; cur: [n] m^2).  Returns the number of segments the
+// FP32 test would skip although the FP64 test -- with its own slack -- keeps them (must be 0), and the two skip counts.
+int64_t hc_skip_compare(const double *d0, const double *d1, const double *cur, int64_t n, double thr2, int conj_open,
+                        int64_t *skipped32, int64_t *skipped64) {
+    int64_t bad = 0, s32 = 0, s64 = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double *a = d0 + 3 * i, *b = d1 + 3 * i;
+        const float f0[3] = {(float)a[0], (float)a[1], (float)a[2]}, f1[3] = {(float)b[0], (float)b[1], (float)b[2]};
+        const bool k32 = ksl::segment_skippable_f32(f0, f1, ksl::segment_want_f32(cur[i], conj_open != 0, thr2));
+        const bool k64 = ksl::segment_skippable(a, b, cur[i], conj_open != 0, thr2);
+        s32 += k32; s64 += k64;
+        if (k32 && !k64) ++bad;
+    }
+    *skipped32 = s32; *skipped64 = s64;
+    return bad;
+}
 
 int hc_screen(const double *consts_t, const double *epoch_t, int64_t n_t, const double *consts_c, const double *epoch_c,
               int64_t n, const double *times_coarse, int64_t n_coarse, int64_t n_fine, double thr, int mode,
@@ -110,7 +129,11 @@ int hc_screen(const double *consts_t, const double *epoch_t, int64_t n_t, const 
                 const long long nb = (k == last) ? k : k + 1;
                 const double d0[3] = {pt[3 * k] - pc[3 * k], pt[3 * k + 1] - pc[3 * k + 1], pt[3 * k + 2] - pc[3 * k + 2]};
                 const double d1[3] = {pt[3 * nb] - pc[3 * nb], pt[3 * nb + 1] - pc[3 * nb + 1], pt[3 * nb + 2] - pc[3 * nb + 2]};
-                if (mode == 0 && ksl::segment_skippable(d0, d1, cutoff, best[tid].conj_j == ksl::kNoIndex, thr2)) continue;
+                // the warp kernel's FP32 form of the test (the FP64 form serves the CTA kernel and the tail segment)
+                const float f0[3] = {(float)d0[0], (float)d0[1], (float)d0[2]}, f1[3] = {(float)d1[0], (float)d1[1], (float)d1[2]};
+                if (mode == 0 && (s_use_f32 ? ksl::segment_skippable_f32(f0, f1, ksl::segment_want_f32(cutoff, best[tid].conj_j == ksl::kNoIndex, thr2))
+                                            : ksl::segment_skippable(d0, d1, cutoff, best[tid].conj_j == ksl::kNoIndex, thr2)))
+                    continue;
                 visited = true;
                 if (mode == 0)
                     ksl::segment_search<0>(k, last, scale, n_coarse, n_fine, thr2, &pt[3 * k], &pt[3 * nb], &pc[3 * k], &pc[3 * nb], best[tid], ja_tab);

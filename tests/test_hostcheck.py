@@ -113,6 +113,31 @@ def test_device_fast_path_matches_oracle(hc):
     assert dev[slow].max() < 1e-9
 
 
+def test_f32_skip_test_is_conservative(hc):
+    """segment_skippable_f32 (k_screen_warp's inner loop) may only skip what the FP64 bound skips: random segments,
+    segments whose bound sits within 1e-3 relative of the running minimum, huge and non-finite coordinates."""
+    rng = np.random.default_rng(5)
+    n = 400000
+    d0 = rng.normal(size=(n, 3)) * rng.choice([1.0, 50.0, 3000.0, 14000.0], size=(n, 1))
+    d1 = d0 + rng.normal(size=(n, 3)) * rng.choice([0.01, 1.0, 300.0, 1500.0], size=(n, 1))
+    b = d1 - d0
+    a0, a1, a2 = (d0 * d0).sum(1), (d0 * b).sum(1), (b * b).sum(1)
+    lam = np.clip(-a1 / np.maximum(a2, 1e-300), 0, 1)
+    lb = (a0 + 2 * a1 * lam + a2 * lam * lam) * 1e6                       # m^2
+    cur = lb * (1 + rng.choice([-1e-3, -1e-5, -1e-7, 0, 1e-7, 1e-5, 1e-3, 0.5, -0.5], size=n))
+    d0[:50] *= 1e200
+    d1[50:100] = np.nan
+    d0[100:150] = np.inf
+    cur[150:200] = np.inf
+    hc.hc_skip_compare.restype = ctypes.c_int64
+    for conj_open in (0, 1):
+        s32, s64 = ctypes.c_int64(), ctypes.c_int64()
+        bad = hc.hc_skip_compare(_p(np.ascontiguousarray(d0), D), _p(np.ascontiguousarray(d1), D), _p(cur, D), ctypes.c_int64(n),
+                                 ctypes.c_double(25e6), conj_open, ctypes.byref(s32), ctypes.byref(s64))
+        assert bad == 0
+        assert 0 < s32.value <= s64.value and s32.value > 0.3 * s64.value    # ... and it still prunes (7 of 9 cases sit on the boundary)
+
+
 def test_device_wrap_is_python_mod(hc):
     hc.hc_wrap_twopi.restype = ctypes.c_double
     rng = np.random.default_rng(0)
