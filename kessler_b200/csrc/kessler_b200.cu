@@ -265,8 +265,10 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen(
     __shared__ Best s_scratch[32];
     __shared__ double s_epoch[2];
     __shared__ int s_flags[2];
+    __shared__ __align__(16) double s_grid[256];   // ksl::kGridSinCos, for sincos_grid
 
     const int tid = threadIdx.x;
+    for (int q = tid; q < 256; q += kScreenThreads) s_grid[q] = ksl::kGridSinCos[q];
     const bool grid_in_smem = KSL_SCREEN_GRID_SMEM && p.n_coarse <= kMaxGridInSmem;
     int *s_ja = reinterpret_cast<int *>(s_times + (grid_in_smem ? p.n_coarse : 0));
     if (grid_in_smem)
@@ -314,12 +316,12 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen(
             if (k <= last) {
                 const double tm = grid_in_smem ? s_times[k] : p.times_coarse[k];
                 double r[3];
-                e_c |= ksl::sgp4_position(s_cc, 1, (tm - epoch_c) * 1440.0, r);
+                e_c |= ksl::sgp4_position(s_cc, 1, (tm - epoch_c) * 1440.0, r, s_grid);
                 s_pc[tid][0] = r[0]; s_pc[tid][1] = r[1]; s_pc[tid][2] = r[2];
                 if (kSharedTarget) {
                     r[0] = p.target_pos[3 * k]; r[1] = p.target_pos[3 * k + 1]; r[2] = p.target_pos[3 * k + 2];
                 } else {
-                    e_t |= ksl::sgp4_position(s_ct, 1, (tm - epoch_t) * 1440.0, r);
+                    e_t |= ksl::sgp4_position(s_ct, 1, (tm - epoch_t) * 1440.0, r, s_grid);
                 }
                 s_pt[tid][0] = r[0]; s_pt[tid][1] = r[1]; s_pt[tid][2] = r[2];
             }
@@ -401,6 +403,7 @@ template <bool kSharedTarget, int kMode>
 __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_warp(const ScreenParams p) {
     extern __shared__ double s_times[];
     __shared__ double s_c[kWarpsPerCta][2][ksl::KSL_NFAST];
+    __shared__ __align__(16) double s_grid[256];          // ksl::kGridSinCos, for sincos_grid
     __shared__ double s_carry_all[kWarpsPerCta][8];   // lane 31's (target, chaser, float d) for the next chunk's lane 0
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -414,6 +417,7 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
         for (long long k = tid; k <= p.n_coarse; k += kScreenThreads)
             s_ja[k] = (k == p.n_coarse) ? (int)p.n_fine : (int)ksl::first_fine_of(k, p.scale, p.n_coarse, p.n_fine);
     const int *ja_tab = ja_in_smem ? s_ja : nullptr;
+    for (int q = tid; q < 256; q += kScreenThreads) s_grid[q] = ksl::kGridSinCos[q];
     __syncthreads();
 
     double *s_ct = s_c[warp][0], *s_cc = s_c[warp][1], *s_carry = s_carry_all[warp];
@@ -465,12 +469,12 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
                 // both fast evaluations back to back: one straight-line block with two independent
                 // dependency chains for the scheduler; the (rare) exact fallbacks come after
                 const double ts_c = (tm - epoch_c) * 1440.0, ts_t = (tm - epoch_t) * 1440.0;
-                const bool ok_c = ksl::sgp4_prop_fast([&](int q) { return s_cc[q]; }, ts_c, rc);
+                const bool ok_c = ksl::sgp4_prop_fast([&](int q) { return s_cc[q]; }, ts_c, rc, s_grid);
                 bool ok_t = true;
                 if (kSharedTarget) {
                     rt[0] = __ldg(p.target_pos + 3 * k); rt[1] = __ldg(p.target_pos + 3 * k + 1); rt[2] = __ldg(p.target_pos + 3 * k + 2);
                 } else {
-                    ok_t = ksl::sgp4_prop_fast([&](int q) { return s_ct[q]; }, ts_t, rt);
+                    ok_t = ksl::sgp4_prop_fast([&](int q) { return s_ct[q]; }, ts_t, rt, s_grid);
                 }
                 // (through a scratch array: the out-of-line call takes an address, and rc / rt must stay in registers)
                 if (!ok_c) {

@@ -485,6 +485,106 @@ KSL_HD void sincos_cw_near(double x, double &s, double &c) {
     c = flip_sign_if(cv, (q + 1) & 2);
 }
 
+// ---- sincos on a 128-point grid ---------------------------------------------------
+// x = k (2 pi / 128) + r, |r| <= pi / 128: (sin, cos)(k 2 pi / 128) from a 2 KB table (correctly rounded; the screen
+// kernels stage it in shared memory, `grid` points there), short kernels for r (sin through r^7, cos through r^8:
+// truncation 9e-21 / 3e-18) and the angle-addition formulas in the form S + (S (cos r - 1) + C sin r), which keeps the
+// result within an ulp.  16 FP64 instructions instead of 20-21 for the fdlibm kernels on [-pi/4, pi/4], and no
+// quadrant bookkeeping at all.  Valid for |x| < 2^18: the step is split into 30 + 53 bits, so fn * step_hi is exact.
+//   [0] 128 / (2 pi)  [1] 1.5 * 2^52  [2] step_hi  [3] step_lo  [4..6] -1/6, 1/120, -1/5040  [7..9] -1/2, 1/24, -1/720
+KSL_TABLE kGridTab[10] = {2.03718327157626042379e+01, 6755399441055744.0, 4.90873851813375949860e-02, 3.10029243650168882873e-11,
+                          -1.6666666666666666e-01, 8.3333333333333332e-03, -1.9841269841269841e-04,
+                          -0.5, 4.1666666666666664e-02, -1.3888888888888889e-03};
+// interleaved (sin, cos)(2 pi k / 128), k = 0..127 (mpmath, 300 bits, rounded to nearest)
+#if defined(__CUDACC__)
+__device__ const double kGridSinCos[256] = {
+#else
+static const double kGridSinCos[256] = {
+#endif
+    0.0, 1.0, 0.049067674327418015, 0.9987954562051724,
+    0.0980171403295606, 0.9951847266721969, 0.14673047445536175, 0.989176509964781,
+    0.19509032201612828, 0.9807852804032304, 0.2429801799032639, 0.970031253194544,
+    0.2902846772544624, 0.9569403357322088, 0.33688985339222005, 0.9415440651830208,
+    0.3826834323650898, 0.9238795325112867, 0.4275550934302821, 0.9039892931234433,
+    0.47139673682599764, 0.881921264348355, 0.5141027441932218, 0.8577286100002721,
+    0.5555702330196022, 0.8314696123025452, 0.5956993044924334, 0.8032075314806449,
+    0.6343932841636455, 0.773010453362737, 0.6715589548470184, 0.7409511253549591,
+    0.7071067811865476, 0.7071067811865476, 0.7409511253549591, 0.6715589548470184,
+    0.773010453362737, 0.6343932841636455, 0.8032075314806449, 0.5956993044924334,
+    0.8314696123025452, 0.5555702330196022, 0.8577286100002721, 0.5141027441932218,
+    0.881921264348355, 0.47139673682599764, 0.9039892931234433, 0.4275550934302821,
+    0.9238795325112867, 0.3826834323650898, 0.9415440651830208, 0.33688985339222005,
+    0.9569403357322088, 0.2902846772544624, 0.970031253194544, 0.2429801799032639,
+    0.9807852804032304, 0.19509032201612828, 0.989176509964781, 0.14673047445536175,
+    0.9951847266721969, 0.0980171403295606, 0.9987954562051724, 0.049067674327418015,
+    1.0, 0.0, 0.9987954562051724, -0.049067674327418015,
+    0.9951847266721969, -0.0980171403295606, 0.989176509964781, -0.14673047445536175,
+    0.9807852804032304, -0.19509032201612828, 0.970031253194544, -0.2429801799032639,
+    0.9569403357322088, -0.2902846772544624, 0.9415440651830208, -0.33688985339222005,
+    0.9238795325112867, -0.3826834323650898, 0.9039892931234433, -0.4275550934302821,
+    0.881921264348355, -0.47139673682599764, 0.8577286100002721, -0.5141027441932218,
+    0.8314696123025452, -0.5555702330196022, 0.8032075314806449, -0.5956993044924334,
+    0.773010453362737, -0.6343932841636455, 0.7409511253549591, -0.6715589548470184,
+    0.7071067811865476, -0.7071067811865476, 0.6715589548470184, -0.7409511253549591,
+    0.6343932841636455, -0.773010453362737, 0.5956993044924334, -0.8032075314806449,
+    0.5555702330196022, -0.8314696123025452, 0.5141027441932218, -0.8577286100002721,
+    0.47139673682599764, -0.881921264348355, 0.4275550934302821, -0.9039892931234433,
+    0.3826834323650898, -0.9238795325112867, 0.33688985339222005, -0.9415440651830208,
+    0.2902846772544624, -0.9569403357322088, 0.2429801799032639, -0.970031253194544,
+    0.19509032201612828, -0.9807852804032304, 0.14673047445536175, -0.989176509964781,
+    0.0980171403295606, -0.9951847266721969, 0.049067674327418015, -0.9987954562051724,
+    0.0, -1.0, -0.049067674327418015, -0.9987954562051724,
+    -0.0980171403295606, -0.9951847266721969, -0.14673047445536175, -0.989176509964781,
+    -0.19509032201612828, -0.9807852804032304, -0.2429801799032639, -0.970031253194544,
+    -0.2902846772544624, -0.9569403357322088, -0.33688985339222005, -0.9415440651830208,
+    -0.3826834323650898, -0.9238795325112867, -0.4275550934302821, -0.9039892931234433,
+    -0.47139673682599764, -0.881921264348355, -0.5141027441932218, -0.8577286100002721,
+    -0.5555702330196022, -0.8314696123025452, -0.5956993044924334, -0.8032075314806449,
+    -0.6343932841636455, -0.773010453362737, -0.6715589548470184, -0.7409511253549591,
+    -0.7071067811865476, -0.7071067811865476, -0.7409511253549591, -0.6715589548470184,
+    -0.773010453362737, -0.6343932841636455, -0.8032075314806449, -0.5956993044924334,
+    -0.8314696123025452, -0.5555702330196022, -0.8577286100002721, -0.5141027441932218,
+    -0.881921264348355, -0.47139673682599764, -0.9039892931234433, -0.4275550934302821,
+    -0.9238795325112867, -0.3826834323650898, -0.9415440651830208, -0.33688985339222005,
+    -0.9569403357322088, -0.2902846772544624, -0.970031253194544, -0.2429801799032639,
+    -0.9807852804032304, -0.19509032201612828, -0.989176509964781, -0.14673047445536175,
+    -0.9951847266721969, -0.0980171403295606, -0.9987954562051724, -0.049067674327418015,
+    -1.0, 0.0, -0.9987954562051724, 0.049067674327418015,
+    -0.9951847266721969, 0.0980171403295606, -0.989176509964781, 0.14673047445536175,
+    -0.9807852804032304, 0.19509032201612828, -0.970031253194544, 0.2429801799032639,
+    -0.9569403357322088, 0.2902846772544624, -0.9415440651830208, 0.33688985339222005,
+    -0.9238795325112867, 0.3826834323650898, -0.9039892931234433, 0.4275550934302821,
+    -0.881921264348355, 0.47139673682599764, -0.8577286100002721, 0.5141027441932218,
+    -0.8314696123025452, 0.5555702330196022, -0.8032075314806449, 0.5956993044924334,
+    -0.773010453362737, 0.6343932841636455, -0.7409511253549591, 0.6715589548470184,
+    -0.7071067811865476, 0.7071067811865476, -0.6715589548470184, 0.7409511253549591,
+    -0.6343932841636455, 0.773010453362737, -0.5956993044924334, 0.8032075314806449,
+    -0.5555702330196022, 0.8314696123025452, -0.5141027441932218, 0.8577286100002721,
+    -0.47139673682599764, 0.881921264348355, -0.4275550934302821, 0.9039892931234433,
+    -0.3826834323650898, 0.9238795325112867, -0.33688985339222005, 0.9415440651830208,
+    -0.2902846772544624, 0.9569403357322088, -0.2429801799032639, 0.970031253194544,
+    -0.19509032201612828, 0.9807852804032304, -0.14673047445536175, 0.989176509964781,
+    -0.0980171403295606, 0.9951847266721969, -0.049067674327418015, 0.9987954562051724,
+};
+KSL_HD void sincos_grid(double x, const double *grid, double &s, double &c) {
+    const double t = fma_rn(x, kGridTab[0], kGridTab[1]);
+    const int k = lo_word(t) & 127;
+    const double fn = t - kGridTab[1];
+    const double r = fma_rn(-fn, kGridTab[3], fma_rn(-fn, kGridTab[2], x));
+    const double z = r * r;
+    const double ps = fma_rn(fma_rn(z, kGridTab[6], kGridTab[5]), z, kGridTab[4]);
+    const double sr = fma_rn(z * ps, r, r);                                        // sin r
+    const double cm1 = z * fma_rn(fma_rn(z, kGridTab[9], kGridTab[8]), z, kGridTab[7]);   // cos r - 1
+#if defined(__CUDA_ARCH__)
+    const double2 sc = *reinterpret_cast<const double2 *>(grid + 2 * k);
+    const double S = sc.x, C = sc.y;
+#else
+    const double S = grid[2 * k], C = grid[2 * k + 1];
+#endif
+    s = fma_rn(C, sr, fma_rn(S, cm1, S));
+    c = fma_rn(-S, sr, fma_rn(C, cm1, C));
+}
+
 KSL_HD double rcp_seed(double b) {
 #if defined(__CUDA_ARCH__)
     double r;
@@ -613,7 +713,7 @@ enum {
 // algebraically the reference's with fewer intermediate roundings, ~1e-13 rad); false = assumptions violated,
 // nothing usable written: call sgp4_prop.
 template <typename Load>
-KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: fast record (prepare_fast_record)
+KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3], const double *grid) {   // c: fast record (prepare_fast_record); grid: kGridSinCos or a copy
     // Angles that grow with t (mean anomaly, mean longitude: ~1e3 rad over the window) keep the reference's
     // own sequence of roundings -- each costs ~1e-13 rad = 1e-9 km; everything of magnitude <= 2 pi is free
     // to use FMAs (1e-16 rad).
@@ -625,7 +725,7 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: fast recor
     // prepare_fast_record zeroes omgcof, xmcof and bstar*cc5, and sgp4init already left d2..d4,
     // t3cof..t5cof at 0, which turns every term below into an exact +0.
     double sx, cx;
-    sincos_cw_coarse(xmdf, sx, cx);
+    sincos_grid(xmdf, grid, sx, cx);
     const double delmtemp = fma_rn(c(KSL_C_ETA), cx, 1.0);
     const double delm = c(KSL_C_XMCOF) * (delmtemp * delmtemp * delmtemp - c(KSL_C_DELMO));
     const double temp0 = fma_rn(c(KSL_C_OMGCOF), t, delm);
@@ -645,7 +745,7 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: fast recor
     const double tempe = fma_rn(c(KSL_F_BC5), smm - c(KSL_C_SINMAO), c(KSL_F_BC4) * t);
     const double am = c(KSL_C_AOBASE) * tempa * tempa;
     const double em = c(KSL_C_ECCO) - tempe;
-    // validity: 2^16 < kSinCosMaxArg; sincos_cw_near needs < 32 (and |u| < pi + 8 + 0.1); |temp0| < 2^-4 for the
+    // validity: sincos_grid needs < 2^18; |argpm| < 32 and |nodem| < 8 keep |u| < pi + 8 + 0.1; |temp0| < 2^-4 for the
     // kernels above; em < 1e-6 is clamped by the reference
     bool ok = abs_below_pow2(xmdf, 16) && abs_below_pow2(argpm, 5) && abs_below_pow2(nodem, 3) &&
               abs_below_pow2(temp0, -4) && (em >= 1.0e-6);
@@ -657,7 +757,7 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: fast recor
     const double lm = wrap_pm_pi(xlm) - nodem;
 
     double sarg, carg;
-    sincos_cw_near(argpm, sarg, carg);
+    sincos_grid(argpm, grid, sarg, carg);
     const double axnl = em * carg;
     double temp = rcp_1(am * fma_rn(-em, em, 1.0));            // * aycof / xlcof ~ 1e-3: 1e-12 is plenty
     const double aynl = fma_rn(em, sarg, temp * c(KSL_C_AYCOF));
@@ -667,7 +767,7 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: fast recor
     // (tested below) the Newton step from E = u is below 0.12 / 0.88 = 0.137 (11th-order rotation: 7e-18), the second
     // below e d^2 / 2(1 - e) = 1.3e-3, the third below 1e-6; anything else (non-finite input) fails the final test.
     double se, ce;
-    sincos_cw_near(u, se, ce);
+    sincos_grid(u, grid, se, ce);
     double den = fma_rn(-se, aynl, fma_rn(-ce, axnl, 1.0));
     double rden = rcp_3(den);
     double d = (fma_rn(axnl, se, fma_rn(-aynl, ce, u)) - u) * rden;            // first step from E = u
@@ -724,7 +824,7 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3]) {   // c: fast recor
     double sinsu = sinu, cossu = cosu;
     rotate_micro(dsu, sinsu, cossu);
     double snod, cnod;
-    sincos_cw_near(nodem, snod, cnod);
+    sincos_grid(nodem, grid, snod, cnod);
     rotate_micro(dnode, snod, cnod);
     double sini = c(KSL_C_SINIO), cosi = c(KSL_C_COSIO);
     rotate_micro(dinc, sini, cosi);
@@ -766,8 +866,8 @@ __device__ __noinline__ int sgp4_position_exact(const double *c, int stride, dou
 }
 #endif
 // c: pointer to constant 0 of the record, `stride` doubles between consecutive constants
-KSL_HD int sgp4_position(const double *c, int stride, double t, double r[3]) {
-    if (sgp4_prop_fast([&](int k) { return c[(long long)k * stride]; }, t, r)) return 0;
+KSL_HD int sgp4_position(const double *c, int stride, double t, double r[3], const double *grid) {
+    if (sgp4_prop_fast([&](int k) { return c[(long long)k * stride]; }, t, r, grid)) return 0;
 #if defined(__CUDA_ARCH__)
     return sgp4_position_exact(c, stride, t, r);
 #else

@@ -48,8 +48,8 @@ int hc_sgp4_position(const double *consts, int64_t n, const double *tsince, int6
         for (int64_t j = 0; j < m; ++j) {
             double *o = pos + (i * m + j) * 3;
             double tmp[3];
-            fast_used[i * m + j] = ksl::sgp4_prop_fast(ld, tsince[j], tmp) ? 1 : 0;
-            e |= ksl::sgp4_position(cm, 1, tsince[j], o);
+            fast_used[i * m + j] = ksl::sgp4_prop_fast(ld, tsince[j], tmp, ksl::kGridSinCos) ? 1 : 0;
+            e |= ksl::sgp4_position(cm, 1, tsince[j], o, ksl::kGridSinCos);
         }
         err[i] |= e;
     }
@@ -114,8 +114,8 @@ int hc_screen(const double *consts_t, const double *epoch_t, int64_t n_t, const 
         ksl::prepare_fast_record(cmt, 1);
         ksl::prepare_fast_record(cmc, 1);
         for (int64_t k = 0; k < n_coarse; ++k) {
-            et |= ksl::sgp4_position(cmt, 1, (times_coarse[k] - epoch_t[it]) * 1440.0, &pt[3 * k]);
-            ec |= ksl::sgp4_position(cmc, 1, (times_coarse[k] - epoch_c[s]) * 1440.0, &pc[3 * k]);
+            et |= ksl::sgp4_position(cmt, 1, (times_coarse[k] - epoch_t[it]) * 1440.0, &pt[3 * k], ksl::kGridSinCos);
+            ec |= ksl::sgp4_position(cmc, 1, (times_coarse[k] - epoch_c[s]) * 1440.0, &pc[3 * k], ksl::kGridSinCos);
         }
         std::vector<ksl::Best> best(kThreads);
         for (auto &b : best) ksl::best_init(b);
