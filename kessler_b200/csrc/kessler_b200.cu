@@ -265,10 +265,10 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen(
     __shared__ Best s_scratch[32];
     __shared__ double s_epoch[2];
     __shared__ int s_flags[2];
-    __shared__ __align__(16) double s_grid[256];   // ksl::kGridSinCos, for sincos_grid
+    __shared__ __align__(16) double s_grid[2 * ksl::kGridPoints];   // ksl::kGridSinCos, for sincos_grid
 
     const int tid = threadIdx.x;
-    for (int q = tid; q < 256; q += kScreenThreads) s_grid[q] = ksl::kGridSinCos[q];
+    for (int q = tid; q < 2 * ksl::kGridPoints; q += kScreenThreads) s_grid[q] = ksl::kGridSinCos[q];
     const bool grid_in_smem = KSL_SCREEN_GRID_SMEM && p.n_coarse <= kMaxGridInSmem;
     int *s_ja = reinterpret_cast<int *>(s_times + (grid_in_smem ? p.n_coarse : 0));
     if (grid_in_smem)
@@ -403,7 +403,7 @@ template <bool kSharedTarget, int kMode>
 __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_warp(const ScreenParams p) {
     extern __shared__ double s_times[];
     __shared__ double s_c[kWarpsPerCta][2][ksl::KSL_NFAST];
-    __shared__ __align__(16) double s_grid[256];          // ksl::kGridSinCos, for sincos_grid
+    __shared__ __align__(16) double s_grid[2 * ksl::kGridPoints];          // ksl::kGridSinCos, for sincos_grid
     __shared__ double s_carry_all[kWarpsPerCta][8];   // lane 31's (target, chaser, float d) for the next chunk's lane 0
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
         for (long long k = tid; k <= p.n_coarse; k += kScreenThreads)
             s_ja[k] = (k == p.n_coarse) ? (int)p.n_fine : (int)ksl::first_fine_of(k, p.scale, p.n_coarse, p.n_fine);
     const int *ja_tab = ja_in_smem ? s_ja : nullptr;
-    for (int q = tid; q < 256; q += kScreenThreads) s_grid[q] = ksl::kGridSinCos[q];
+    for (int q = tid; q < 2 * ksl::kGridPoints; q += kScreenThreads) s_grid[q] = ksl::kGridSinCos[q];
     __syncthreads();
 
     double *s_ct = s_c[warp][0], *s_cc = s_c[warp][1], *s_carry = s_carry_all[warp];
