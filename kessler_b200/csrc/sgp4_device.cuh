@@ -776,13 +776,39 @@ KSL_HD void sincos_grid(double x, const double *grid, double &s, double &c) {
     c = fma_rn(-S, sr, fma_rn(C, cm1, C));
 }
 
+// the grid point nearest to x: (S, C) = (sin, cos)(x - r) straight from the table, |r| <= pi / 512
+KSL_HD double grid_point(double x, const double *grid, double &S, double &C) {
+    const double t = fma_rn(x, kGridTab[0], kGridTab[1]);
+    const int k = lo_word(t) & (kGridPoints - 1);
+    const double fn = t - kGridTab[1];
+#if defined(__CUDA_ARCH__)
+    const double2 sc = *reinterpret_cast<const double2 *>(grid + 2 * k);
+    S = sc.x;
+    C = sc.y;
+#else
+    S = grid[2 * k];
+    C = grid[2 * k + 1];
+#endif
+    return fma_rn(-fn, kGridTab[3], fma_rn(-fn, kGridTab[2], x));
+}
+
 KSL_HD double rcp_seed(double b) {
 #if defined(__CUDA_ARCH__)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     return r;
 #else
-    return 1.0 / b;
+    // the hardware seed works on the high words only: same accuracy class (~2^-20) for the host build
+    long long bits;
+    memcpy(&bits, &b, 8);
+    bits &= ~0xffffffffLL;
+    double bt;
+    memcpy(&bt, &bits, 8);
+    double r = 1.0 / bt;
+    memcpy(&bits, &r, 8);
+    bits &= ~0xffffffffLL;
+    memcpy(&r, &bits, 8);
+    return r;
 #endif
 }
 // reciprocal good to ~1e-12 relative (one Newton step on the ~2^-20 seed)
@@ -927,11 +953,11 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3], const double *grid) 
         fma_rn(-t, fma_rn(t, fma_rn(t, fma_rn(t, c(KSL_C_D4), c(KSL_C_D3)), c(KSL_C_D2)), c(KSL_C_CC1)), 1.0);
     const double templ =
         t2 * fma_rn(t, fma_rn(t, fma_rn(t, c(KSL_C_T5COF), c(KSL_C_T4COF)), c(KSL_C_T3COF)), c(KSL_C_T2COF));
-    // sin(mm0) = sin(xmdf + temp0), |temp0| <= 0.1, to 2e-11 (6th-order kernels): it only feeds the
-    // bstar*cc5 term of the eccentricity (bstar*cc5 < 1e-5 even for bstar = 1e-2)
+    // sin(mm0) = sin(xmdf + temp0), |temp0| < 2^-4, to 1e-8 (sin through d^3, cos through d^4): it only feeds the
+    // bstar*cc5 term of the eccentricity, and bstar*cc5 < 1e-5 even for bstar = 1e-2
     const double q2 = temp0 * temp0;
-    const double sd0 = fma_rn(fma_rn(q2, kTrigTab[1], kTrigTab[0]) * q2, temp0, temp0);
-    const double cd0 = fma_rn(fma_rn(fma_rn(q2, kTrigTab[6], kTrigTab[5]), q2, kTrigTab[4]), q2, 1.0);
+    const double sd0 = fma_rn(q2 * kTrigTab[0], temp0, temp0);
+    const double cd0 = fma_rn(fma_rn(q2, kTrigTab[5], kTrigTab[4]), q2, 1.0);
     const double smm = fma_rn(sx, cd0, cx * sd0);
     const double tempe = fma_rn(c(KSL_F_BC5), smm - c(KSL_C_SINMAO), c(KSL_F_BC4) * t);
     const double am = c(KSL_C_AOBASE) * tempa * tempa;
@@ -954,31 +980,34 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3], const double *grid) 
     const double aynl = fma_rn(em, sarg, temp * c(KSL_C_AYCOF));
     const double u = fma_rn(temp * c(KSL_C_XLCOF), axnl, lm);  // |u| < 4 pi
 
-    // Kepler: u = E - axnl sin E + aynl cos E.  The steps need no individual bound checks: with el2 < 0.0144
-    // (tested below) the Newton step from E = u is below 0.12 / 0.88 = 0.137 (11th-order rotation: 7e-18), the second
-    // below e d^2 / 2(1 - e) = 1.3e-3, the third below 1e-6; anything else (non-finite input) fails the final test.
+    // Kepler: u = E - axnl sin E + aynl cos E, solved for g = u - E in three sweeps, starting from the grid point E0
+    // nearest to u: (sin, cos)(E0) come straight from the table and g0 = u - E0 is the reduction's remainder
+    // (|g0| <= pi / 512).  With f = -(g + esine), f' = 1 - ecose, f'' = esine, the first step is Halley's,
+    // d = dN (1 - dN q / 2) with the Newton step dN = (g + esine) / (1 - ecose) and q = esine / (1 - ecose): it leaves
+    // 2e-5 at e = 0.12 (Newton: 9e-4),
+    // the Newton step that follows 5e-11 (its reciprocal is good to 7e-6), and the third step, with the same
+    // reciprocal, 1e-15.  No individual bound checks: with el2 < 0.0144 (tested below) |d1| < 0.15 (11th-order
+    // rotation: 2e-17) and |d2| < 3e-5 (rotate_micro); anything else (non-finite input) fails the test on the last
+    // step, |d3| < 2^-30 (then the remaining error is < 1e-5 |d3|).
     double se, ce;
-    sincos_grid(u, grid, se, ce);
+    double g = grid_point(u, grid, se, ce);
     double den = fma_rn(-se, aynl, fma_rn(-ce, axnl, 1.0));
-    double rden = rcp_3(den);
-    double d = (fma_rn(axnl, se, fma_rn(-aynl, ce, u)) - u) * rden;            // first step from E = u
-    double eo1 = u + d;
+    double rden = rcp_seed(den);                                               // ~2^-20: plenty for a step that leaves 2e-5
+    const double qn = fma_rn(axnl, se, -(aynl * ce)) * rden;                   // esine / (1 - ecose) = f'' / f'
+    const double dn = fma_rn(g, rden, qn);
+    double d = fma_rn(dn * qn * -0.5, dn, dn);
+    g -= d;
     rotate_small(d, se, ce);
     den = fma_rn(-se, aynl, fma_rn(-ce, axnl, 1.0));
-    rden = fma_rn(rden, fma_rn(-den, rden, 1.0), rden);                        // follows den to ~(e d)^2
-    d = (fma_rn(axnl, se, fma_rn(-aynl, ce, u)) - eo1) * rden;
-    eo1 += d;
-    rotate_tiny(d, se, ce);
-    // sweeps 3 and 4: steps <= 1e-6 (e <= 0.12), first-order rotations (error d^2/2), reciprocal reused
-    d = (fma_rn(axnl, se, fma_rn(-aynl, ce, u)) - eo1) * rden;
-    eo1 += d;
-    double s_prev = se;
-    se = fma_rn(d, ce, se);
-    ce = fma_rn(-d, s_prev, ce);
-    d = (fma_rn(axnl, se, fma_rn(-aynl, ce, u)) - eo1) * rden;
-    ok = ok && abs_below_pow2(d, -40);   // 9.1e-13: inside the reference's convergence test (1e-12)
-    s_prev = se;
-    se = fma_rn(d, ce, se);
+    const double er = fma_rn(-den, rden, 1.0);                                 // |er| < 0.02: the step changed den by e d
+    rden = fma_rn(rden, fma_rn(er, er, er), rden);                             // cubic: 1 / den to 7e-6
+    d = fma_rn(axnl, se, fma_rn(-aynl, ce, g)) * rden;
+    g -= d;
+    rotate_micro(d, se, ce);
+    d = fma_rn(axnl, se, fma_rn(-aynl, ce, g)) * rden;
+    ok = ok && abs_below_pow2(d, -30);
+    const double s_prev = se;
+    se = fma_rn(d, ce, se);                                                    // first-order rotation: d^2 / 2 < 5e-19
     ce = fma_rn(-d, s_prev, ce);
 
     const double ecose = fma_rn(axnl, ce, aynl * se);
@@ -995,7 +1024,9 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3], const double *grid) 
     bs = fma_rn(bs, el2, kSqrtTab[0]);
     const double betal = fma_rn(bs, el2, 1.0);
     temp = esine * rcp_1(1.0 + betal);                                          // enters as e * temp ~ e^2
-    const double amorl = rcp_3(omecose);                                        // am / rl
+    // am / rl = 1 / (1 - ecose): rden is that reciprocal one sweep earlier, good to 7e-6 -> cubic refinement, 3e-16
+    const double ea = fma_rn(-omecose, rden, 1.0);
+    const double amorl = fma_rn(rden, fma_rn(ea, ea, ea), rden);
     const double sinu = amorl * (se - aynl - axnl * temp);
     const double cosu = amorl * (ce - axnl + aynl * temp);
     const double sin2u = (cosu + cosu) * sinu;
@@ -1020,9 +1051,10 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3], const double *grid) 
     rotate_micro(dinc, sini, cosi);
     const double xmx = -snod * cosi, xmy = cnod * cosi;
     const double mr = mrt * kRe;
-    r[0] = mr * fma_rn(xmx, sinsu, cnod * cossu);
-    r[1] = mr * fma_rn(xmy, sinsu, snod * cossu);
-    r[2] = mr * (sini * sinsu);
+    const double rs = mr * sinsu, rcs = mr * cossu;
+    r[0] = fma_rn(xmx, rs, cnod * rcs);
+    r[1] = fma_rn(xmy, rs, snod * rcs);
+    r[2] = sini * rs;
     // pl < 0 is impossible with el2 < 0.0144; decay (mrt < 1) and non-finite values go to the exact path
     return ok && (mrt >= 1.0) && abs_below_pow2(mr, 996);
 }

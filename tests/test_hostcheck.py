@@ -111,6 +111,12 @@ def test_device_fast_path_matches_oracle(hc):
     assert dev[fast].max() < 1e-8 and np.median(dev[fast]) < 2e-11        # km
     slow = (used == 0) & good[:, None]                                       # fallback = the exact path
     assert dev[slow].max() < 1e-9
+    # the three-sweep Kepler solve at the top of its validity range (e <= 0.12), and low-drag records only: accepted,
+    # and as accurate as everywhere else
+    hi_e = good & (el[1] > 0.05) & (el[1] < 0.115) & (np.abs(el[6]) < 1e-3)
+    assert hi_e.sum() >= 10
+    assert fast[hi_e].mean() > 0.95
+    assert dev[hi_e][fast[hi_e]].max() < 1e-8 and np.median(dev[hi_e][fast[hi_e]]) < 2e-11
 
 
 def test_f32_skip_test_is_conservative(hc):
