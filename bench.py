@@ -31,7 +31,7 @@ UNIT = "traces/s"
 N_COARSE, N_FINE, UPSAMPLE = 6000, 600000, 100
 EVALS_PER_TRACE = 2 * N_COARSE
 FLOP_PER_EVAL = 940.0          # canonical algorithmic FP64 flop per SGP4 evaluation
-EXECUTED_FLOP_PER_EVAL = 449.0  # ncu, profiles/r01g_k_screen_warp_sass_opcode_mix.csv: 2 x 169.5 DFMA + 79.3 DMUL + 30.5 DADD
+EXECUTED_FLOP_PER_EVAL = 354.0  # ncu, profiles/r01i_k_screen_warp_sass_opcode_mix.csv: 2 x 125.2 DFMA + 77.3 DMUL + 26.4 DADD
 FLOP_PER_INIT = 600.0
 BYTES_PER_TRACE = 2 * 7 * 8 + 32  # algorithmic bytes: 2x7 doubles in, 4 values out
 THR_M, COLLISION_M = 5e3, 70.0
@@ -293,19 +293,19 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     traffic, pipe_pct = None, None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of k_screen_warp from the committed ncu --set full capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01g_k_screen_warp_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01i_k_screen_warp_traffic.json")))
         traffic = tr["dram_bytes_total"] * (n / tr["traces_per_launch"])
         pipe_pct = tr.get("sm__pipe_fp64_cycles_active_pct")
     except Exception:
         pass
     roofline = {"bound": "fp64", "kernel": "k_screen_warp (fused SGP4 x2 + closed-form TCA search, one warp per trace)", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": traffic,
-                "traffic_source": "profiles/r01g_k_screen_warp_traffic.json (ncu --set full at 1e6 traces/launch; scaled by n if --samples differs)",
+                "traffic_source": "profiles/r01i_k_screen_warp_traffic.json (ncu --set full at 1e6 traces/launch; scaled by n if --samples differs)",
                 "peak_source": "measured in this run: dependent-free DFMA probe (ksl_fp64_peak_kernel); MEASURED_PEAKS.json has no FP64 entry",
                 "flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": n * EVALS_PER_TRACE, "launch_ms": scr_s * 1e3,
                 # frac is ALGORITHMIC flop (the reference algorithm's 940 flop / evaluation) over the
                 # measured peak, so it exceeds 1 once the kernel needs fewer operations than that count; what the
-                # hardware actually ran is in the keys below (committed ncu capture, profiles/r01g_*)
+                # hardware actually ran is in the keys below (committed ncu capture, profiles/r01i_*)
                 "executed_flop_per_eval": EXECUTED_FLOP_PER_EVAL,
                 "executed_frac": n * EVALS_PER_TRACE * EXECUTED_FLOP_PER_EVAL / scr_s / 1e12 / peak_tf,
                 "fp64_pipe_active_pct_ncu": pipe_pct,
