@@ -368,10 +368,11 @@ KSL_HD int sgp4_prop(Load &&c, double t, double r[3], double v[3]) {
 // sincos, six small-angle fallbacks, 64-bit literals materialised through UMOV pairs):
 //   * no data-dependent branch: every assumption is accumulated into one flag and the
 //     caller re-runs the exact sgp4_prop when it is violated (`return false`);
-//   * reciprocals from rcp.approx + Newton steps sized to the precision each use needs
+//   * sin / cos from a 512-point table in shared memory + two-term kernels (sincos_grid), no quadrant logic;
+//   * reciprocals from rcp.approx + one Newton or one cubic step, sized to the precision each use needs
 //     (J2 / long-period terms carry 1e-3 factors), no IEEE-division slow path;
-//   * Kepler's equation: four quasi-Newton sweeps with ONE reciprocal (refined by an FMA pair in
-//     the second, reused afterwards); same root (|last step| < 1e-12 is checked);
+//   * Kepler's equation in three sweeps from the table point nearest to u (Halley, Newton, one more step with
+//     the same reciprocal); same root as the reference's loop (the last step is checked);
 //   * sqrt(1 - el2) from its series (el2 = e^2 <~ 1e-2);
 //   * polynomial coefficients live in constant memory.
 // Position only (the closest-approach search never reads the velocity).
@@ -389,18 +390,6 @@ KSL_TABLE kTrigTab[10] = {-1.6666666666666666e-01, 8.3333333333333332e-03, -1.98
                           -2.7557319223985888e-07, 0.0};
 // sqrt(1 - x) = 1 - x/2 - x^2/8 - x^3/16 - 5x^4/128 - 7x^5/256 - 21x^6/1024
 KSL_TABLE kSqrtTab[6] = {-0.5, -0.125, -0.0625, -0.0390625, -0.02734375, -0.0205078125};
-// full-range sincos (|x| < 1e5): Cody-Waite reduction by pi/2 in three pieces (33 + 33 + 53 bits) and the
-// fdlibm minimax kernels on [-pi/4, pi/4] (K. C. Ng, 1993; < 1 ulp)
-//   [0] 2/pi  [1] 1.5*2^52  [2] pio2_1  [3] pio2_2  [4] pio2_2t
-//   [5..10]  S1..S6    [11..16] C1..C6
-KSL_TABLE kSinCosTab[18] = {
-    6.36619772367581382433e-01, 6755399441055744.0, 1.57079632673412561417e+00, 6.07710050630396597660e-11,
-    2.02226624879595063154e-21,
-    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, 2.75573137070700676789e-06,
-    -2.50507602534068634195e-08, 1.58969099521155010221e-10,
-    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07,
-    2.08757232129817482790e-09, -1.13596475577881948265e-11, 0.0};
-
 KSL_HD int lo_word(double t) {
 #if defined(__CUDA_ARCH__)
     return __double2loint(t);
@@ -408,13 +397,6 @@ KSL_HD int lo_word(double t) {
     long long b;
     memcpy(&b, &t, 8);
     return (int)(b & 0xffffffffLL);
-#endif
-}
-KSL_HD double flip_sign_if(double v, int nonzero) {
-#if defined(__CUDA_ARCH__)
-    return __hiloint2double(__double2hiint(v) ^ (nonzero ? 0x80000000 : 0), __double2loint(v));
-#else
-    return nonzero ? -v : v;
 #endif
 }
 KSL_HD int hi_word(double t) {
@@ -429,62 +411,6 @@ KSL_HD int hi_word(double t) {
 // |x| < bound for bound = 2^e, decided on the high word: an integer compare on the ALU pipe instead of a DSETP on
 // the FP64 pipe this code is bound by.  NaN and inf give false.
 KSL_HD bool abs_below_pow2(double x, int e) { return (hi_word(x) & 0x7fffffff) < ((1023 + e) << 20); }
-// branch-free sincos for |x| < kSinCosMaxArg (callers flag anything larger for the exact path)
-constexpr double kSinCosMaxArg = 1.0e5;
-KSL_HD void sincos_cw(double x, double &s, double &c) {
-    const double t = fma_rn(x, kSinCosTab[0], kSinCosTab[1]);   // 1.5*2^52 + rint(x * 2/pi)
-    const int q = lo_word(t);
-    const double fn = t - kSinCosTab[1];
-    double r = fma_rn(-fn, kSinCosTab[2], x);
-    r = fma_rn(-fn, kSinCosTab[3], r);
-    r = fma_rn(-fn, kSinCosTab[4], r);
-    const double z = r * r;
-    double ps = fma_rn(z, kSinCosTab[10], kSinCosTab[9]);
-    ps = fma_rn(ps, z, kSinCosTab[8]);
-    ps = fma_rn(ps, z, kSinCosTab[7]);
-    ps = fma_rn(ps, z, kSinCosTab[6]);
-    ps = fma_rn(ps, z, kSinCosTab[5]);
-    const double ks = fma_rn(ps * z, r, r);
-    double pc = fma_rn(z, kSinCosTab[16], kSinCosTab[15]);
-    pc = fma_rn(pc, z, kSinCosTab[14]);
-    pc = fma_rn(pc, z, kSinCosTab[13]);
-    pc = fma_rn(pc, z, kSinCosTab[12]);
-    pc = fma_rn(pc, z, kSinCosTab[11]);
-    const double kc = fma_rn(z, fma_rn(pc, z, -0.5), 1.0);
-    const bool swap = (q & 1) != 0;
-    const double sv = swap ? kc : ks;
-    const double cv = swap ? ks : kc;
-    s = flip_sign_if(sv, q & 2);
-    c = flip_sign_if(cv, (q + 1) & 2);
-}
-
-// sincos_cw for |x| < 32 (the node, the perigee and the reduced mean longitude): two reduction pieces are enough
-// there (the third, fn * pio2_2t, is below 5e-20)
-KSL_HD void sincos_cw_near(double x, double &s, double &c) {
-    const double t = fma_rn(x, kSinCosTab[0], kSinCosTab[1]);
-    const int q = lo_word(t);
-    const double fn = t - kSinCosTab[1];
-    const double r = fma_rn(-fn, kSinCosTab[3], fma_rn(-fn, kSinCosTab[2], x));
-    const double z = r * r;
-    double ps = fma_rn(z, kSinCosTab[10], kSinCosTab[9]);
-    ps = fma_rn(ps, z, kSinCosTab[8]);
-    ps = fma_rn(ps, z, kSinCosTab[7]);
-    ps = fma_rn(ps, z, kSinCosTab[6]);
-    ps = fma_rn(ps, z, kSinCosTab[5]);
-    const double ks = fma_rn(ps * z, r, r);
-    double pc = fma_rn(z, kSinCosTab[16], kSinCosTab[15]);
-    pc = fma_rn(pc, z, kSinCosTab[14]);
-    pc = fma_rn(pc, z, kSinCosTab[13]);
-    pc = fma_rn(pc, z, kSinCosTab[12]);
-    pc = fma_rn(pc, z, kSinCosTab[11]);
-    const double kc = fma_rn(z, fma_rn(pc, z, -0.5), 1.0);
-    const bool swap = (q & 1) != 0;
-    const double sv = swap ? kc : ks;
-    const double cv = swap ? ks : kc;
-    s = flip_sign_if(sv, q & 2);
-    c = flip_sign_if(cv, (q + 1) & 2);
-}
-
 // ---- sincos on a 512-point grid ---------------------------------------------------
 // x = k (2 pi / 512) + r, |r| <= pi / 512: (sin, cos)(k 2 pi / 512) from an 8 KB table (correctly rounded; the screen
 // kernels stage it in shared memory, `grid` points there), two-term kernels for r (sin through r^5, cos through r^4:
@@ -495,7 +421,7 @@ KSL_HD void sincos_cw_near(double x, double &s, double &c) {
 constexpr int kGridPoints = 512;
 KSL_TABLE kGridTab[8] = {8.14873308630504169514e+01, 6755399441055744.0, 1.22718462953343987465e-02, 7.75073109125422207182e-12,
                          -1.6666666666666666e-01, 8.3333333333333332e-03, -0.5, 4.1666666666666664e-02};
-// interleaved (sin, cos)(2 pi k / 512), k = 0..511 (mpmath, 300 bits, rounded to nearest)
+// interleaved (sin, cos)(2 pi k / 512), k = 0..511 (tools/make_sincos_grid.py: mpmath, 300 bits, rounded to nearest)
 #if defined(__CUDACC__)
 __device__ const double kGridSinCos[2 * kGridPoints] = {
 #else
@@ -816,19 +742,6 @@ KSL_HD double rcp_1(double b) {
     double r = rcp_seed(b);
     return fma_rn(r, fma_rn(-b, r, 1.0), r);
 }
-// reciprocal good to ~1 ulp
-KSL_HD double rcp_2(double b) {
-    double r = rcp_1(b);
-    return fma_rn(r, fma_rn(-b, r, 1.0), r);
-}
-
-// reciprocal to full precision in three FMAs: with e = 1 - b r (|e| ~ 2^-20), r (1 + e + e^2) is off by e^3
-KSL_HD double rcp_3(double b) {
-    const double r = rcp_seed(b);
-    const double e = fma_rn(-b, r, 1.0);
-    return fma_rn(r, fma_rn(e, e, e), r);
-}
-
 // |d| <= 0.1: 11th-order kernel (truncation 2.5e-19); rotate (s, c) by d
 KSL_HD void rotate_small(double d, double &s, double &c) {
     const double d2 = d * d;
@@ -845,21 +758,6 @@ KSL_HD void rotate_small(double d, double &s, double &c) {
     s = fma_rn(s0, cd, c0 * sd);
     c = fma_rn(c0, cd, -(s0 * sd));
 }
-// |d| <= 0.01: 7th-order kernel (truncation d^8/40320 = 2.5e-21)
-constexpr double kTinyAngle = 0.01;
-KSL_HD void rotate_tiny(double d, double &s, double &c) {
-    const double d2 = d * d;
-    double ps = fma_rn(d2, kTrigTab[2], kTrigTab[1]);
-    ps = fma_rn(ps, d2, kTrigTab[0]);
-    const double sd = fma_rn(ps * d2, d, d);
-    double pc = fma_rn(d2, kTrigTab[6], kTrigTab[5]);
-    pc = fma_rn(pc, d2, kTrigTab[4]);
-    const double cd = fma_rn(pc, d2, 1.0);
-    const double s0 = s, c0 = c;
-    s = fma_rn(s0, cd, c0 * sd);
-    c = fma_rn(c0, cd, -(s0 * sd));
-}
-
 constexpr double kFastMaxEl2 = 0.0144;   // e <= 0.12: bound behind the series for sqrt(1 - el2) and the Kepler step sizes
 
 // |d| <= 2e-3 (the three J2 short-period angles; bounded through 1/pl^2 below): 3rd / 4th-order kernels,
@@ -872,32 +770,6 @@ KSL_HD void rotate_micro(double d, double &s, double &c) {
     const double s0 = s, c0 = c;
     s = fma_rn(s0, cd, c0 * sd);
     c = fma_rn(c0, cd, -(s0 * sd));
-}
-
-// sincos_cw with two reduction pieces and one polynomial term less per kernel: absolute error < 1e-11, for
-// the mean-anomaly angle whose sine / cosine only enter drag terms scaled by <~ 1e-3
-KSL_HD void sincos_cw_coarse(double x, double &s, double &c) {
-    const double t = fma_rn(x, kSinCosTab[0], kSinCosTab[1]);
-    const int q = lo_word(t);
-    const double fn = t - kSinCosTab[1];
-    double r = fma_rn(-fn, kSinCosTab[2], x);
-    r = fma_rn(-fn, kSinCosTab[3], r);
-    const double z = r * r;
-    double ps = fma_rn(z, kSinCosTab[9], kSinCosTab[8]);
-    ps = fma_rn(ps, z, kSinCosTab[7]);
-    ps = fma_rn(ps, z, kSinCosTab[6]);
-    ps = fma_rn(ps, z, kSinCosTab[5]);
-    const double ks = fma_rn(ps * z, r, r);
-    double pc = fma_rn(z, kSinCosTab[15], kSinCosTab[14]);
-    pc = fma_rn(pc, z, kSinCosTab[13]);
-    pc = fma_rn(pc, z, kSinCosTab[12]);
-    pc = fma_rn(pc, z, kSinCosTab[11]);
-    const double kc = fma_rn(z, fma_rn(pc, z, -0.5), 1.0);
-    const bool swap = (q & 1) != 0;
-    const double sv = swap ? kc : ks;
-    const double cv = swap ? ks : kc;
-    s = flip_sign_if(sv, q & 2);
-    c = flip_sign_if(cv, (q + 1) & 2);
 }
 
 // x - 2pi_d rint(x / 2pi_d) for |x| < 1e5, where 2pi_d = 6.283185307179586 is the DOUBLE the reference's `%`

@@ -6,6 +6,7 @@ tests (-m gpu) repeat the comparison through the C ABI on the real kernels."""
 import ctypes
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -142,6 +143,22 @@ def test_f32_skip_test_is_conservative(hc):
                                  ctypes.c_double(25e6), conj_open, ctypes.byref(s32), ctypes.byref(s64))
         assert bad == 0
         assert 0 < s32.value <= s64.value and s32.value > 0.3 * s64.value    # ... and it still prunes (7 of 9 cases sit on the boundary)
+
+
+def test_sincos_grid_table_is_the_generated_one():
+    """kGridSinCos in sgp4_device.cuh == the output of tools/make_sincos_grid.py (correctly rounded with mpmath), and
+    its entries are sin / cos of the grid angles (libm on the rounded angle agrees to the angle's rounding, 1e-15)."""
+    import re
+    src = open(os.path.join(ROOT, "kessler_b200", "csrc", "sgp4_device.cuh")).read()
+    a = src.index("kGridSinCos[2 * kGridPoints] = {", src.index("#else", src.index("interleaved (sin, cos)")))
+    vals = np.array([float(x) for x in re.findall(r"-?\d+\.\d+(?:e-?\d+)?", src[a:src.index("};", a)])])
+    assert vals.shape == (1024,)
+    ang = 2 * np.pi * np.arange(512) / 512
+    assert np.abs(vals[0::2] - np.sin(ang)).max() < 1e-15 and np.abs(vals[1::2] - np.cos(ang)).max() < 1e-15
+    pytest.importorskip("mpmath")
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "tools", "make_sincos_grid.py")]).decode().splitlines()[2:]
+    gen = np.array([float(x) for line in out for x in re.findall(r"-?\d+\.\d+(?:e-?\d+)?", line)])
+    assert np.array_equal(vals, gen)
 
 
 def test_device_wrap_is_python_mod(hc):
