@@ -317,6 +317,33 @@ def test_screen_cta_and_warp_decompositions_agree(eng):
         assert np.array_equal(r["err"], ref["err"])
 
 
+def test_screen_unrelated_pairs_warp_kernel(eng):
+    """Catalog-vs-catalog pairs through the warp kernel: consecutive traces of a warp have nothing to do with each
+    other (the pilot chunk is then a useless but harmless hint), lanes fall back to the exact SGP4 path at different
+    epochs, some objects are refused, decay or go non-finite -- indices, distances and flags are the oracle's."""
+    from kessler_b200 import _native as NV
+    _, ept, _, _, s = common.golden_pair()
+    n = 192
+    elt, elc = common.synthetic_catalog(n, seed=11), common.synthetic_catalog(n, seed=12, include_edge=False)
+    rng = np.random.default_rng(8)
+    ept_a, epc_a = ept + rng.uniform(-3, 3, n), ept + rng.uniform(-3, 3, n)
+    times = K.time_grid(s["time0"], 7.0, 6e4)
+    tc = np.ascontiguousarray(times[::100])
+    ref = C.screen(elt, ept_a, elc, epc_a, tc, len(times), 2e5)
+    for force in (NV.SCREEN_FORCE_WARP, NV.SCREEN_FORCE_CTA, NV.SCREEN_FORCE_WARP | 1):
+        r = _screen(eng, elt, ept_a, elc, epc_a, tc, len(times), 2e5, force)
+        assert np.array_equal(r["err"], ref["err"]), force
+        assert np.array_equal(r["i_min"], ref["i_min"]) and np.array_equal(r["i_conj"], ref["i_conj"]), force
+        fin = np.isfinite(ref["d_min"])
+        assert np.array_equal(np.isnan(r["d_min"]), np.isnan(ref["d_min"]))
+        clean = fin & (ref["err"] == 0)
+        assert np.abs(r["d_min"][clean] - ref["d_min"][clean]).max() < 1e-3
+        # flagged traces (decayed, eccentricity out of range ...) still carry numbers, some of them astronomically
+        # large and ill-conditioned (eccentricity >= 1): the same numbers to the conditioning of that garbage
+        assert np.allclose(r["d_min"][fin], ref["d_min"][fin], rtol=1e-4, atol=1e-3)
+    assert (ref["err"] != 0).sum() >= 10 and (ref["err"] == 0).sum() >= 100
+
+
 def test_screen_full_size_properties(eng):
     """BASELINE configs[1] at its full size (1e6 perturbed samples of the default LEO pair, the bench workload),
     checked through size-independent properties: the warp-per-trace kernel on the full batch equals the
