@@ -3,10 +3,11 @@
 //
 // Nothing on this path is a dense contraction, so there is no tensor-core / TMA
 // code here on purpose: every kernel is FP64-vector-pipe bound (SGP4) or tiny.
-// What is B200-specific is the shape: persistent grids sized from the SM count,
-// one CTA per trace with the per-trace SGP4 constants and the time grid staged in
-// shared memory (broadcast LDS operands feed the DFMA pipe), warp-shuffle
-// arg-min reductions, and a register budget chosen for 2 CTAs x 256 threads per SM.
+// What is B200-specific is the shape: persistent grids sized from the SM count
+// (one 512-thread CTA per SM, 16 warps at <= 128 registers), one warp per trace with
+// the per-trace SGP4 constants, the time grid and a sincos table staged in shared
+// memory (broadcast LDS operands feed the DFMA pipe), neighbour epochs and arg-min
+// reductions by warp shuffle, the FP32 pipe used for the conservative pruning test.
 #include <cuda_runtime.h>
 
 #include <atomic>
