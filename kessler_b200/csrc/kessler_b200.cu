@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kPropThreads) k_sgp4_prop(const double *__rest
         const long long j = idx - i * m;
         const double t = per_sample_t ? tsince[idx] : tsince[j];
         double r[3], v[3];
-        e = ksl::sgp4_prop<true>([&](int k) { return __ldg(consts + (long long)k * n + i); }, t, r, v);
+        e = ksl::sgp4_state([&](int k) { return __ldg(consts + (long long)k * n + i); }, t, r, v, ksl::kGridSinCos);
         double *st = &stage[warp][lane * 6];
         st[0] = r[0]; st[1] = r[1]; st[2] = r[2];
         st[3] = v[0]; st[4] = v[1]; st[5] = v[2];
@@ -563,7 +563,12 @@ __global__ void __launch_bounds__(128) k_target_positions(const double *__restri
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_coarse) return;
     double r[3], v[3];
-    const int e = ksl::sgp4_prop<false>([&](int q) { return __ldg(consts + q); }, (times[k] - epoch[0]) * 1440.0, r, v);
+    // the same fast path as the per-sample targets of k_screen*, so that both forms of a batch see identical positions
+    auto ld = [&](int q) { return __ldg(consts + q); };
+    const ksl::FastView<decltype(ld)> view{ld, ld(KSL_C_ISIMP) != 0.0};
+    const double ts = (times[k] - epoch[0]) * 1440.0;
+    int e = 0;
+    if (!ksl::sgp4_prop_fast(view, ts, r, ksl::kGridSinCos)) e = ksl::sgp4_prop<false>(ld, ts, r, v);
     pos[3 * k] = r[0]; pos[3 * k + 1] = r[1]; pos[3 * k + 2] = r[2];
     if (e) atomicOr(err, e);
 }
@@ -575,7 +580,7 @@ __global__ void __launch_bounds__(128) k_prop_times(const double *__restrict__ c
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_sub) return;
     double r[3], v[3];
-    const int e = ksl::sgp4_prop<true>([&](int q) { return __ldg(consts + q); }, (times[k] - epoch_mjd) * 1440.0, r, v);
+    const int e = ksl::sgp4_state([&](int q) { return __ldg(consts + q); }, (times[k] - epoch_mjd) * 1440.0, r, v, ksl::kGridSinCos);
     double *o = rv + 6 * k;
     o[0] = r[0]; o[1] = r[1]; o[2] = r[2]; o[3] = v[0]; o[4] = v[1]; o[5] = v[2];
     if (e && err) atomicOr(err, e);
@@ -670,7 +675,7 @@ __global__ void __launch_bounds__(kTcaThreads) k_tca_moments(const double *__res
 #pragma unroll
         for (int k = 0; k < 7; ++k) el[k] = elems[k * n + i];
         int e = ksl::sgp4_init(el, [&](int k, double v) { c[k] = v; });
-        e |= ksl::sgp4_prop<true>([&](int k) { return c[k]; }, tsince, x, x + 3);
+        e |= ksl::sgp4_state([&](int k) { return c[k]; }, tsince, x, x + 3, ksl::kGridSinCos);
 #pragma unroll
         for (int q = 0; q < 6; ++q) x[q] *= 1e3;  // model.py:541: *1e3 -> metres
         if (states) {
@@ -850,7 +855,7 @@ __device__ __forceinline__ int mc_state(const McObject &o, const double z[6], do
     for (int r = 0; r < 7; ++r) el_out[r] = el[r];
     double c[KSL_NCONST];
     int e = ksl::sgp4_init(el, [&](int k, double v) { c[k] = v; });
-    e |= ksl::sgp4_prop<true>([&](int k) { return c[k]; }, o.tsince, x, x + 3);
+    e |= ksl::sgp4_state([&](int k) { return c[k]; }, o.tsince, x, x + 3, ksl::kGridSinCos);
 #pragma unroll
     for (int r = 0; r < 6; ++r) x[r] *= 1e3;
     return e;
@@ -1078,8 +1083,8 @@ __global__ void __launch_bounds__(128) k_states_at_fine(const double *__restrict
     ksl::upsample_index(fine_idx[it], scale, n_coarse, &i0, &i1, &w0, &w1);
     double a[6], b[6];
     auto ld = [&](int k) { return __ldg(consts + (long long)k * n_rec + r); };
-    int e = ksl::sgp4_prop<true>(ld, (times_coarse[i0] - epoch[it]) * 1440.0, a, a + 3);
-    e |= ksl::sgp4_prop<true>(ld, (times_coarse[i1] - epoch[it]) * 1440.0, b, b + 3);
+    int e = ksl::sgp4_state(ld, (times_coarse[i0] - epoch[it]) * 1440.0, a, a + 3, ksl::kGridSinCos);
+    e |= ksl::sgp4_state(ld, (times_coarse[i1] - epoch[it]) * 1440.0, b, b + 3, ksl::kGridSinCos);
 #pragma unroll
     for (int q = 0; q < 6; ++q) out_m[6 * it + q] = ksl::lerp_m(w0, a[q], w1, b[q]);
     if (err) err[it] = e;

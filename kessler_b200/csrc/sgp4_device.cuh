@@ -388,8 +388,8 @@ KSL_HD int sgp4_prop(Load &&c, double t, double r[3], double v[3]) {
 KSL_TABLE kTrigTab[10] = {-1.6666666666666666e-01, 8.3333333333333332e-03, -1.9841269841269841e-04, 2.7557319223985893e-06,
                           -0.5, 4.1666666666666664e-02, -1.3888888888888889e-03, 2.4801587301587302e-05,
                           -2.7557319223985888e-07, 0.0};
-// sqrt(1 - x) = 1 - x/2 - x^2/8 - x^3/16 - 5x^4/128 - 7x^5/256 - 21x^6/1024
-KSL_TABLE kSqrtTab[6] = {-0.5, -0.125, -0.0625, -0.0390625, -0.02734375, -0.0205078125};
+// sqrt(1 - x) = 1 - x/2 - x^2/8 - x^3/16 - 5x^4/128 - 7x^5/256 - 21x^6/1024 - 33x^7/2048
+KSL_TABLE kSqrtTab[8] = {-0.5, -0.125, -0.0625, -0.0390625, -0.02734375, -0.0205078125, -0.01611328125, 0.0};
 KSL_HD int lo_word(double t) {
 #if defined(__CUDA_ARCH__)
     return __double2loint(t);
@@ -737,6 +737,24 @@ KSL_HD double rcp_seed(double b) {
     return r;
 #endif
 }
+KSL_HD double rsqrt_seed(double b) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    return r;
+#else
+    long long bits;   // high words only, as the hardware seed (see rcp_seed)
+    memcpy(&bits, &b, 8);
+    bits &= ~0xffffffffLL;
+    double bt;
+    memcpy(&bt, &bits, 8);
+    double r = 1.0 / sqrt(bt);
+    memcpy(&bits, &r, 8);
+    bits &= ~0xffffffffLL;
+    memcpy(&r, &bits, 8);
+    return r;
+#endif
+}
 // reciprocal good to ~1e-12 relative (one Newton step on the ~2^-20 seed)
 KSL_HD double rcp_1(double b) {
     double r = rcp_seed(b);
@@ -801,8 +819,9 @@ enum {
 // returns true when the result is the one sgp4_prop would give (to rounding: the angle bookkeeping below is
 // algebraically the reference's with fewer intermediate roundings, ~1e-13 rad); false = assumptions violated,
 // nothing usable written: call sgp4_prop.
-template <typename Load>
-KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3], const double *grid) {   // c: fast record (prepare_fast_record); grid: kGridSinCos or a copy
+// c: fast record (prepare_fast_record); grid: kGridSinCos or a copy of it; v (km/s) is written when kVel.
+template <bool kVel, typename Load>
+KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], const double *grid) {
     // Angles that grow with t (mean anomaly, mean longitude: ~1e3 rad over the window) keep the reference's
     // own sequence of roundings -- each costs ~1e-13 rad = 1e-9 km; everything of magnitude <= 2 pi is free
     // to use FMAs (1e-16 rad).
@@ -914,7 +933,7 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3], const double *grid) 
     // |dsu|, |dnode|, |dinc| <= 3/4 J2 / pl^2 (|x7thm1| <= 6, |sin|, |cos| <= 1): one test covers the three
     ok = ok && abs_below_pow2(ipl2, 1);   // 2 < kMicroAngle / (0.75 J2) = 2.47
 
-    // (sinu, cosu) is a unit vector to d3^2 / 2 < 1e-14 (first-order rotation of the third sweep, e = 0.12)
+    // (sinu, cosu) is a unit vector to rounding (the last, first-order rotation is by < 1e-9)
     double sinsu = sinu, cossu = cosu;
     rotate_micro(dsu, sinsu, cossu);
     double snod, cnod;
@@ -927,8 +946,37 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3], const double *grid) 
     r[0] = fma_rn(xmx, rs, cnod * rcs);
     r[1] = fma_rn(xmy, rs, snod * rcs);
     r[2] = sini * rs;
+    if (kVel) {
+        // sqrt(am) / rl = (am / rl) am^-1/2 and sqrt(pl) / rl = sqrt(1 - el2) (am / rl) am^-1/2: one reciprocal square
+        // root (seed + one cubic step: with e = 1 - am r^2, r (1 + e/2 + 3 e^2/8) is off by 5/16 e^3), no square root
+        const double r0 = rsqrt_seed(am);
+        const double er0 = fma_rn(-(am * r0), r0, 1.0);
+        const double rsa = fma_rn(r0, fma_rn(0.375, er0, 0.5) * er0, r0);
+        const double w = amorl * rsa;
+        double bf = fma_rn(el2, kSqrtTab[6], kSqrtTab[5]);   // sqrt(1 - el2) to 3e-17: the two terms betal leaves out
+        bf = fma_rn(bf, el2, kSqrtTab[4]);
+        bf = fma_rn(bf, el2, kSqrtTab[3]);
+        bf = fma_rn(bf, el2, kSqrtTab[2]);
+        bf = fma_rn(bf, el2, kSqrtTab[1]);
+        bf = fma_rn(bf, el2, kSqrtTab[0]);
+        const double rvdotl = w * fma_rn(bf, el2, 1.0);
+        const double k1 = (0.5 * kJ2) * ipl * (rsa * rsa * rsa);           // temp1 nm / xke
+        const double mvt = fma_rn(-k1 * c(KSL_C_X1MTH2), sin2u, w * esine);
+        const double rvdot = fma_rn(k1, fma_rn(c(KSL_C_X1MTH2), cos2u, 1.5 * c(KSL_C_CON41)), rvdotl);
+        const double ms = mvt * kVkmPerSec, rv = rvdot * kVkmPerSec;
+        const double ux = fma_rn(xmx, sinsu, cnod * cossu), uy = fma_rn(xmy, sinsu, snod * cossu), uz = sini * sinsu;
+        v[0] = fma_rn(ms, ux, rv * fma_rn(xmx, cossu, -(cnod * sinsu)));
+        v[1] = fma_rn(ms, uy, rv * fma_rn(xmy, cossu, -(snod * sinsu)));
+        v[2] = fma_rn(ms, uz, rv * (sini * cossu));
+        ok = ok && abs_below_pow2(w, 10);   // am = 0 or non-finite
+    }
     // pl < 0 is impossible with el2 < 0.0144; decay (mrt < 1) and non-finite values go to the exact path
     return ok && (mrt >= 1.0) && abs_below_pow2(mr, 996);
+}
+template <typename Load>
+KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3], const double *grid) {
+    double v[3];
+    return sgp4_prop_fast_rv<false>(c, t, r, v, grid);
 }
 
 // In-place preparation of a private (shared-memory / local) copy of a record, KSL_NFAST entries of `stride`
@@ -949,6 +997,49 @@ KSL_HD void prepare_fast_record(double *c, int stride) {
     at(KSL_F_KNODE) = 0.75 * kJ2 * at(KSL_C_COSIO);
     at(KSL_F_KINC) = 0.75 * kJ2 * at(KSL_C_COSIO) * at(KSL_C_SINIO);
     at(KSL_F_PAD) = 0.0;
+}
+
+// A record that lives only as its 36 public constants (global memory, registers) seen as a fast record: the derived
+// entries are formed on the fly (one multiplication each, what sgp4_prop does anyway) and the three constants the
+// exact path ignores under isimp read as zero.  k is a literal at every call site, so the switch folds away.
+template <typename Base>
+struct FastView {
+    Base base;
+    bool isimp;
+    KSL_HD double operator()(int k) const {
+        switch (k) {
+            case KSL_C_OMGCOF: case KSL_C_XMCOF: case KSL_C_CC5: return isimp ? 0.0 : base(k);
+            case KSL_F_BC4: return base(KSL_C_BSTAR) * base(KSL_C_CC4);
+            case KSL_F_BC5: return isimp ? 0.0 : base(KSL_C_BSTAR) * base(KSL_C_CC5);
+            case KSL_F_KMRT: return (0.75 * kJ2) * base(KSL_C_CON41);
+            case KSL_F_KX1: return (0.25 * kJ2) * base(KSL_C_X1MTH2);
+            case KSL_F_KSU: return (-0.125 * kJ2) * base(KSL_C_X7THM1);
+            case KSL_F_KNODE: return (0.75 * kJ2) * base(KSL_C_COSIO);
+            case KSL_F_KINC: return (0.75 * kJ2) * base(KSL_C_COSIO) * base(KSL_C_SINIO);
+            default: return base(k);
+        }
+    }
+};
+// full state at t from the 36 constants behind `base`: fast path, exact path when it declines.  Returns the error bits.
+// (the exact path is kept out of line on the device so that its registers do not count against the callers' hot path)
+template <typename Base>
+#if defined(__CUDACC__)
+__device__ __noinline__
+#else
+inline
+#endif
+int sgp4_state_exact(const Base &base, double t, double *r, double *v) {
+    return sgp4_prop<true>(base, t, r, v);
+}
+template <typename Base>
+KSL_HD int sgp4_state(Base base, double t, double r[3], double v[3], const double *grid) {
+    const FastView<Base> view{base, base(KSL_C_ISIMP) != 0.0};
+    if (sgp4_prop_fast_rv<true>(view, t, r, v, grid)) return 0;
+    double rx[3], vx[3];   // scratch: the out-of-line call takes addresses, r / v should stay in registers
+    const int e = sgp4_state_exact(base, t, rx, vx);
+    r[0] = rx[0]; r[1] = rx[1]; r[2] = rx[2];
+    v[0] = vx[0]; v[1] = vx[1]; v[2] = vx[2];
+    return e;
 }
 
 // position at t through the fast path, falling back to the exact path when needed (c: masked record).  The exact path

@@ -36,6 +36,23 @@ int hc_sgp4_prop(const double *consts, int64_t n, const double *tsince, int64_t 
     return 0;
 }
 
+// full state through sgp4_state (fast path with velocity over a FastView of the 36 constants, exact fallback)
+int hc_sgp4_state(const double *consts, int64_t n, const double *tsince, int64_t m, double *rv, int32_t *err, int32_t *fast_used) {
+    for (int64_t i = 0; i < n; ++i) {
+        int e = 0;
+        auto ld = [&](int k) { return consts[(int64_t)k * n + i]; };
+        for (int64_t j = 0; j < m; ++j) {
+            double *o = rv + (i * m + j) * 6;
+            double tr[3], tv[3];
+            const ksl::FastView<decltype(ld)> view{ld, ld(KSL_C_ISIMP) != 0.0};
+            fast_used[i * m + j] = ksl::sgp4_prop_fast_rv<true>(view, tsince[j], tr, tv, ksl::kGridSinCos) ? 1 : 0;
+            e |= ksl::sgp4_state(ld, tsince[j], o, o + 3, ksl::kGridSinCos);
+        }
+        if (err) err[i] |= e;
+    }
+    return 0;
+}
+
 // position through the fast path; fast_used[i*m + j] = 1 when the branch-free path accepted the epoch
 int hc_sgp4_position(const double *consts, int64_t n, const double *tsince, int64_t m, double *pos, int32_t *err,
                      int32_t *fast_used) {

@@ -120,6 +120,29 @@ def test_device_fast_path_matches_oracle(hc):
     assert dev[hi_e][fast[hi_e]].max() < 1e-8 and np.median(dev[hi_e][fast[hi_e]]) < 2e-11
 
 
+def test_device_fast_state_matches_oracle(hc):
+    """sgp4_state (K2 / K4 / K6 / K9: fast path with velocity over the 36 public constants, exact fallback)."""
+    el, _ = common.population_elems()
+    el = np.concatenate([el, common.synthetic_catalog(600)], axis=1)
+    c1, e1 = C.sgp4_init(el)
+    ts = np.linspace(-2.0e4, 2.0e4, 201)
+    rv1, ea = C.sgp4_prop(c1, ts)
+    n, m = c1.shape[1], len(ts)
+    rv, err, used = np.zeros((n, m, 6)), np.zeros(n, np.int32), np.zeros((n, m), np.int32)
+    hc.hc_sgp4_state(_p(np.ascontiguousarray(c1), D), ctypes.c_int64(n), _p(ts, D), ctypes.c_int64(m), _p(rv, D), _p(err, I32),
+                     _p(used, I32))
+    good = (e1 == 0) & (ea == 0)
+    assert (err == ea)[e1 == 0].all()
+    fast = (used == 1) & good[:, None]
+    assert fast.sum() > 0.9 * good.sum() * m
+    dp = np.abs(rv[..., :3] - rv1[..., :3]).max(-1)
+    dv = np.abs(rv[..., 3:] - rv1[..., 3:]).max(-1)
+    assert dp[fast].max() < 1e-8 and np.median(dp[fast]) < 2e-11          # km
+    assert dv[fast].max() < 1e-11 and np.median(dv[fast]) < 3e-14         # km/s (one ulp of a 1e3 rad angle: 2e-12)
+    slow = (used == 0) & good[:, None]
+    assert dp[slow].max() < 1e-9 and dv[slow].max() < 1e-12
+
+
 def test_f32_skip_test_is_conservative(hc):
     """segment_skippable_f32 (k_screen_warp's inner loop) may only skip what the FP64 bound skips: random segments,
     segments whose bound sits within 1e-3 relative of the running minimum, huge and non-finite coordinates."""
