@@ -112,6 +112,78 @@ KSL_HD void rotate_by(double d, double a_plus_d, double *s, double *c) {
     }
 }
 
+// ---- tables, bit helpers, sincos on a grid ---------------------------------------------
+// Tables are deliberately NOT const on the device: ptxas folds const initialisers into 64-bit immediates that cost two
+// UMOV issue slots per use; a mutable __constant__ array is read with uniform LDCU loads.
+#if defined(__CUDACC__)
+#define KSL_TABLE __constant__ double
+#else
+#define KSL_TABLE static const double
+#endif
+KSL_HD int lo_word(double t) {
+#if defined(__CUDA_ARCH__)
+    return __double2loint(t);
+#else
+    long long b;
+    memcpy(&b, &t, 8);
+    return (int)(b & 0xffffffffLL);
+#endif
+}
+KSL_HD int hi_word(double t) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(t);
+#else
+    long long b;
+    memcpy(&b, &t, 8);
+    return (int)(b >> 32);
+#endif
+}
+// |x| < bound for bound = 2^e, decided on the high word: an integer compare on the ALU pipe instead of a DSETP on
+// the FP64 pipe this code is bound by.  NaN and inf give false.
+KSL_HD bool abs_below_pow2(double x, int e) { return (hi_word(x) & 0x7fffffff) < ((1023 + e) << 20); }
+// ---- sincos on a 512-point grid ---------------------------------------------------
+// x = k (2 pi / 512) + r, |r| <= pi / 512: (sin, cos)(k 2 pi / 512) from an 8 KB table (correctly rounded; the screen
+// kernels stage it in shared memory, `grid` points there), two-term kernels for r (sin through r^5, cos through r^4:
+// truncation 7e-20 / 8e-17) and the angle-addition formulas in the form S + (S (cos r - 1) + C sin r), which keeps the
+// result within an ulp.  14 FP64 instructions instead of 20-21 for the fdlibm kernels on [-pi/4, pi/4], and no
+// quadrant bookkeeping at all.  Valid for |x| < 2^18: the step is split into 28 + 53 bits, so fn * step_hi is exact.
+//   [0] 512 / (2 pi)  [1] 1.5 * 2^52  [2] step_hi  [3] step_lo  [4..5] -1/6, 1/120  [6..7] -1/2, 1/24
+#include "sincos_grid_table.cuh"   // kGridPoints, kGridTab, kGridSinCos
+KSL_HD void sincos_grid(double x, const double *grid, double &s, double &c) {
+    const double t = fma_rn(x, kGridTab[0], kGridTab[1]);
+    const int k = lo_word(t) & (kGridPoints - 1);
+    const double fn = t - kGridTab[1];
+    const double r = fma_rn(-fn, kGridTab[3], fma_rn(-fn, kGridTab[2], x));
+    const double z = r * r;
+    const double sr = fma_rn(z * fma_rn(z, kGridTab[5], kGridTab[4]), r, r);   // sin r
+    const double cm1 = z * fma_rn(z, kGridTab[7], kGridTab[6]);               // cos r - 1
+#if defined(__CUDA_ARCH__)
+    const double2 sc = *reinterpret_cast<const double2 *>(grid + 2 * k);
+    const double S = sc.x, C = sc.y;
+#else
+    const double S = grid[2 * k], C = grid[2 * k + 1];
+#endif
+    s = fma_rn(C, sr, fma_rn(S, cm1, S));
+    c = fma_rn(-S, sr, fma_rn(C, cm1, C));
+}
+
+// the grid point nearest to x: (S, C) = (sin, cos)(x - r) straight from the table, |r| <= pi / 512
+KSL_HD double grid_point(double x, const double *grid, double &S, double &C) {
+    const double t = fma_rn(x, kGridTab[0], kGridTab[1]);
+    const int k = lo_word(t) & (kGridPoints - 1);
+    const double fn = t - kGridTab[1];
+#if defined(__CUDA_ARCH__)
+    const double2 sc = *reinterpret_cast<const double2 *>(grid + 2 * k);
+    S = sc.x;
+    C = sc.y;
+#else
+    S = grid[2 * k];
+    C = grid[2 * k + 1];
+#endif
+    return fma_rn(-fn, kGridTab[3], fma_rn(-fn, kGridTab[2], x));
+}
+
+
 // ---- sgp4init -----------------------------------------------------------------
 // el = {no_kozai, ecco, inclo, nodeo, argpo, mo, bstar}; c[KSL_NCONST] with stride
 // `cs` between consecutive constants (1 for a private record, n for SoA).
@@ -379,345 +451,12 @@ KSL_HD int sgp4_prop(Load &&c, double t, double r[3], double v[3]) {
 // Tables are deliberately NOT const on the device: ptxas folds const initialisers into 64-bit
 // immediates that cost two UMOV issue slots per use; a mutable __constant__ array is read with
 // uniform LDCU loads (one slot per 64 or 128 bits) that the compiler can also keep resident.
-#if defined(__CUDACC__)
-#define KSL_TABLE __constant__ double
-#else
-#define KSL_TABLE static const double
-#endif
 // sin(d) = d + d^3 (S0 + S1 d^2 + S2 d^4 + S3 d^6);  cos(d) = 1 + d^2 (C0 + C1 d^2 + ... + C4 d^8)
 KSL_TABLE kTrigTab[10] = {-1.6666666666666666e-01, 8.3333333333333332e-03, -1.9841269841269841e-04, 2.7557319223985893e-06,
                           -0.5, 4.1666666666666664e-02, -1.3888888888888889e-03, 2.4801587301587302e-05,
                           -2.7557319223985888e-07, 0.0};
 // sqrt(1 - x) = 1 - x/2 - x^2/8 - x^3/16 - 5x^4/128 - 7x^5/256 - 21x^6/1024 - 33x^7/2048
 KSL_TABLE kSqrtTab[8] = {-0.5, -0.125, -0.0625, -0.0390625, -0.02734375, -0.0205078125, -0.01611328125, 0.0};
-KSL_HD int lo_word(double t) {
-#if defined(__CUDA_ARCH__)
-    return __double2loint(t);
-#else
-    long long b;
-    memcpy(&b, &t, 8);
-    return (int)(b & 0xffffffffLL);
-#endif
-}
-KSL_HD int hi_word(double t) {
-#if defined(__CUDA_ARCH__)
-    return __double2hiint(t);
-#else
-    long long b;
-    memcpy(&b, &t, 8);
-    return (int)(b >> 32);
-#endif
-}
-// |x| < bound for bound = 2^e, decided on the high word: an integer compare on the ALU pipe instead of a DSETP on
-// the FP64 pipe this code is bound by.  NaN and inf give false.
-KSL_HD bool abs_below_pow2(double x, int e) { return (hi_word(x) & 0x7fffffff) < ((1023 + e) << 20); }
-// ---- sincos on a 512-point grid ---------------------------------------------------
-// x = k (2 pi / 512) + r, |r| <= pi / 512: (sin, cos)(k 2 pi / 512) from an 8 KB table (correctly rounded; the screen
-// kernels stage it in shared memory, `grid` points there), two-term kernels for r (sin through r^5, cos through r^4:
-// truncation 7e-20 / 8e-17) and the angle-addition formulas in the form S + (S (cos r - 1) + C sin r), which keeps the
-// result within an ulp.  14 FP64 instructions instead of 20-21 for the fdlibm kernels on [-pi/4, pi/4], and no
-// quadrant bookkeeping at all.  Valid for |x| < 2^18: the step is split into 28 + 53 bits, so fn * step_hi is exact.
-//   [0] 512 / (2 pi)  [1] 1.5 * 2^52  [2] step_hi  [3] step_lo  [4..5] -1/6, 1/120  [6..7] -1/2, 1/24
-constexpr int kGridPoints = 512;
-KSL_TABLE kGridTab[8] = {8.14873308630504169514e+01, 6755399441055744.0, 1.22718462953343987465e-02, 7.75073109125422207182e-12,
-                         -1.6666666666666666e-01, 8.3333333333333332e-03, -0.5, 4.1666666666666664e-02};
-// interleaved (sin, cos)(2 pi k / 512), k = 0..511 (tools/make_sincos_grid.py: mpmath, 300 bits, rounded to nearest)
-#if defined(__CUDACC__)
-__device__ const double kGridSinCos[2 * kGridPoints] = {
-#else
-static const double kGridSinCos[2 * kGridPoints] = {
-#endif
-    0.0, 1.0, 0.012271538285719925, 0.9999247018391445,
-    0.024541228522912288, 0.9996988186962042, 0.03680722294135883, 0.9993223845883495,
-    0.049067674327418015, 0.9987954562051724, 0.06132073630220858, 0.9981181129001492,
-    0.07356456359966743, 0.9972904566786902, 0.0857973123444399, 0.996312612182778,
-    0.0980171403295606, 0.9951847266721969, 0.11022220729388306, 0.9939069700023561,
-    0.1224106751992162, 0.99247953459871, 0.1345807085071262, 0.99090263542778,
-    0.14673047445536175, 0.989176509964781, 0.15885814333386145, 0.9873014181578584,
-    0.17096188876030122, 0.9852776423889412, 0.18303988795514095, 0.9831054874312163,
-    0.19509032201612828, 0.9807852804032304, 0.20711137619221856, 0.9783173707196277,
-    0.2191012401568698, 0.9757021300385286, 0.2310581082806711, 0.9729399522055602,
-    0.2429801799032639, 0.970031253194544, 0.25486565960451457, 0.9669764710448521,
-    0.26671275747489837, 0.9637760657954398, 0.2785196893850531, 0.9604305194155658,
-    0.2902846772544624, 0.9569403357322088, 0.3020059493192281, 0.9533060403541939,
-    0.31368174039889146, 0.9495281805930367, 0.3253102921622629, 0.9456073253805213,
-    0.33688985339222005, 0.9415440651830208, 0.34841868024943456, 0.937339011912575,
-    0.35989503653498817, 0.9329927988347388, 0.37131719395183754, 0.9285060804732156,
-    0.3826834323650898, 0.9238795325112867, 0.3939920400610481, 0.9191138516900578,
-    0.40524131400498986, 0.9142097557035307, 0.4164295600976372, 0.9091679830905224,
-    0.4275550934302821, 0.9039892931234433, 0.43861623853852766, 0.8986744656939538,
-    0.4496113296546066, 0.8932243011955153, 0.46053871095824, 0.8876396204028539,
-    0.47139673682599764, 0.881921264348355, 0.4821837720791228, 0.8760700941954066,
-    0.49289819222978404, 0.8700869911087115, 0.5035383837257176, 0.8639728561215867,
-    0.5141027441932218, 0.8577286100002721, 0.524589682678469, 0.8513551931052652,
-    0.5349976198870973, 0.8448535652497071, 0.5453249884220465, 0.8382247055548381,
-    0.5555702330196022, 0.8314696123025452, 0.5657318107836132, 0.8245893027850253,
-    0.5758081914178453, 0.8175848131515837, 0.5857978574564389, 0.8104571982525948,
-    0.5956993044924334, 0.8032075314806449, 0.6055110414043255, 0.7958369046088836,
-    0.6152315905806268, 0.7883464276266062, 0.6248594881423863, 0.7807372285720945,
-    0.6343932841636455, 0.773010453362737, 0.6438315428897915, 0.765167265622459,
-    0.6531728429537768, 0.7572088465064846, 0.6624157775901718, 0.7491363945234594,
-    0.6715589548470184, 0.7409511253549591, 0.680600997795453, 0.7326542716724128,
-    0.6895405447370669, 0.7242470829514669, 0.6983762494089728, 0.7157308252838187,
-    0.7071067811865476, 0.7071067811865476, 0.7157308252838187, 0.6983762494089728,
-    0.7242470829514669, 0.6895405447370669, 0.7326542716724128, 0.680600997795453,
-    0.7409511253549591, 0.6715589548470184, 0.7491363945234594, 0.6624157775901718,
-    0.7572088465064846, 0.6531728429537768, 0.765167265622459, 0.6438315428897915,
-    0.773010453362737, 0.6343932841636455, 0.7807372285720945, 0.6248594881423863,
-    0.7883464276266062, 0.6152315905806268, 0.7958369046088836, 0.6055110414043255,
-    0.8032075314806449, 0.5956993044924334, 0.8104571982525948, 0.5857978574564389,
-    0.8175848131515837, 0.5758081914178453, 0.8245893027850253, 0.5657318107836132,
-    0.8314696123025452, 0.5555702330196022, 0.8382247055548381, 0.5453249884220465,
-    0.8448535652497071, 0.5349976198870973, 0.8513551931052652, 0.524589682678469,
-    0.8577286100002721, 0.5141027441932218, 0.8639728561215867, 0.5035383837257176,
-    0.8700869911087115, 0.49289819222978404, 0.8760700941954066, 0.4821837720791228,
-    0.881921264348355, 0.47139673682599764, 0.8876396204028539, 0.46053871095824,
-    0.8932243011955153, 0.4496113296546066, 0.8986744656939538, 0.43861623853852766,
-    0.9039892931234433, 0.4275550934302821, 0.9091679830905224, 0.4164295600976372,
-    0.9142097557035307, 0.40524131400498986, 0.9191138516900578, 0.3939920400610481,
-    0.9238795325112867, 0.3826834323650898, 0.9285060804732156, 0.37131719395183754,
-    0.9329927988347388, 0.35989503653498817, 0.937339011912575, 0.34841868024943456,
-    0.9415440651830208, 0.33688985339222005, 0.9456073253805213, 0.3253102921622629,
-    0.9495281805930367, 0.31368174039889146, 0.9533060403541939, 0.3020059493192281,
-    0.9569403357322088, 0.2902846772544624, 0.9604305194155658, 0.2785196893850531,
-    0.9637760657954398, 0.26671275747489837, 0.9669764710448521, 0.25486565960451457,
-    0.970031253194544, 0.2429801799032639, 0.9729399522055602, 0.2310581082806711,
-    0.9757021300385286, 0.2191012401568698, 0.9783173707196277, 0.20711137619221856,
-    0.9807852804032304, 0.19509032201612828, 0.9831054874312163, 0.18303988795514095,
-    0.9852776423889412, 0.17096188876030122, 0.9873014181578584, 0.15885814333386145,
-    0.989176509964781, 0.14673047445536175, 0.99090263542778, 0.1345807085071262,
-    0.99247953459871, 0.1224106751992162, 0.9939069700023561, 0.11022220729388306,
-    0.9951847266721969, 0.0980171403295606, 0.996312612182778, 0.0857973123444399,
-    0.9972904566786902, 0.07356456359966743, 0.9981181129001492, 0.06132073630220858,
-    0.9987954562051724, 0.049067674327418015, 0.9993223845883495, 0.03680722294135883,
-    0.9996988186962042, 0.024541228522912288, 0.9999247018391445, 0.012271538285719925,
-    1.0, 0.0, 0.9999247018391445, -0.012271538285719925,
-    0.9996988186962042, -0.024541228522912288, 0.9993223845883495, -0.03680722294135883,
-    0.9987954562051724, -0.049067674327418015, 0.9981181129001492, -0.06132073630220858,
-    0.9972904566786902, -0.07356456359966743, 0.996312612182778, -0.0857973123444399,
-    0.9951847266721969, -0.0980171403295606, 0.9939069700023561, -0.11022220729388306,
-    0.99247953459871, -0.1224106751992162, 0.99090263542778, -0.1345807085071262,
-    0.989176509964781, -0.14673047445536175, 0.9873014181578584, -0.15885814333386145,
-    0.9852776423889412, -0.17096188876030122, 0.9831054874312163, -0.18303988795514095,
-    0.9807852804032304, -0.19509032201612828, 0.9783173707196277, -0.20711137619221856,
-    0.9757021300385286, -0.2191012401568698, 0.9729399522055602, -0.2310581082806711,
-    0.970031253194544, -0.2429801799032639, 0.9669764710448521, -0.25486565960451457,
-    0.9637760657954398, -0.26671275747489837, 0.9604305194155658, -0.2785196893850531,
-    0.9569403357322088, -0.2902846772544624, 0.9533060403541939, -0.3020059493192281,
-    0.9495281805930367, -0.31368174039889146, 0.9456073253805213, -0.3253102921622629,
-    0.9415440651830208, -0.33688985339222005, 0.937339011912575, -0.34841868024943456,
-    0.9329927988347388, -0.35989503653498817, 0.9285060804732156, -0.37131719395183754,
-    0.9238795325112867, -0.3826834323650898, 0.9191138516900578, -0.3939920400610481,
-    0.9142097557035307, -0.40524131400498986, 0.9091679830905224, -0.4164295600976372,
-    0.9039892931234433, -0.4275550934302821, 0.8986744656939538, -0.43861623853852766,
-    0.8932243011955153, -0.4496113296546066, 0.8876396204028539, -0.46053871095824,
-    0.881921264348355, -0.47139673682599764, 0.8760700941954066, -0.4821837720791228,
-    0.8700869911087115, -0.49289819222978404, 0.8639728561215867, -0.5035383837257176,
-    0.8577286100002721, -0.5141027441932218, 0.8513551931052652, -0.524589682678469,
-    0.8448535652497071, -0.5349976198870973, 0.8382247055548381, -0.5453249884220465,
-    0.8314696123025452, -0.5555702330196022, 0.8245893027850253, -0.5657318107836132,
-    0.8175848131515837, -0.5758081914178453, 0.8104571982525948, -0.5857978574564389,
-    0.8032075314806449, -0.5956993044924334, 0.7958369046088836, -0.6055110414043255,
-    0.7883464276266062, -0.6152315905806268, 0.7807372285720945, -0.6248594881423863,
-    0.773010453362737, -0.6343932841636455, 0.765167265622459, -0.6438315428897915,
-    0.7572088465064846, -0.6531728429537768, 0.7491363945234594, -0.6624157775901718,
-    0.7409511253549591, -0.6715589548470184, 0.7326542716724128, -0.680600997795453,
-    0.7242470829514669, -0.6895405447370669, 0.7157308252838187, -0.6983762494089728,
-    0.7071067811865476, -0.7071067811865476, 0.6983762494089728, -0.7157308252838187,
-    0.6895405447370669, -0.7242470829514669, 0.680600997795453, -0.7326542716724128,
-    0.6715589548470184, -0.7409511253549591, 0.6624157775901718, -0.7491363945234594,
-    0.6531728429537768, -0.7572088465064846, 0.6438315428897915, -0.765167265622459,
-    0.6343932841636455, -0.773010453362737, 0.6248594881423863, -0.7807372285720945,
-    0.6152315905806268, -0.7883464276266062, 0.6055110414043255, -0.7958369046088836,
-    0.5956993044924334, -0.8032075314806449, 0.5857978574564389, -0.8104571982525948,
-    0.5758081914178453, -0.8175848131515837, 0.5657318107836132, -0.8245893027850253,
-    0.5555702330196022, -0.8314696123025452, 0.5453249884220465, -0.8382247055548381,
-    0.5349976198870973, -0.8448535652497071, 0.524589682678469, -0.8513551931052652,
-    0.5141027441932218, -0.8577286100002721, 0.5035383837257176, -0.8639728561215867,
-    0.49289819222978404, -0.8700869911087115, 0.4821837720791228, -0.8760700941954066,
-    0.47139673682599764, -0.881921264348355, 0.46053871095824, -0.8876396204028539,
-    0.4496113296546066, -0.8932243011955153, 0.43861623853852766, -0.8986744656939538,
-    0.4275550934302821, -0.9039892931234433, 0.4164295600976372, -0.9091679830905224,
-    0.40524131400498986, -0.9142097557035307, 0.3939920400610481, -0.9191138516900578,
-    0.3826834323650898, -0.9238795325112867, 0.37131719395183754, -0.9285060804732156,
-    0.35989503653498817, -0.9329927988347388, 0.34841868024943456, -0.937339011912575,
-    0.33688985339222005, -0.9415440651830208, 0.3253102921622629, -0.9456073253805213,
-    0.31368174039889146, -0.9495281805930367, 0.3020059493192281, -0.9533060403541939,
-    0.2902846772544624, -0.9569403357322088, 0.2785196893850531, -0.9604305194155658,
-    0.26671275747489837, -0.9637760657954398, 0.25486565960451457, -0.9669764710448521,
-    0.2429801799032639, -0.970031253194544, 0.2310581082806711, -0.9729399522055602,
-    0.2191012401568698, -0.9757021300385286, 0.20711137619221856, -0.9783173707196277,
-    0.19509032201612828, -0.9807852804032304, 0.18303988795514095, -0.9831054874312163,
-    0.17096188876030122, -0.9852776423889412, 0.15885814333386145, -0.9873014181578584,
-    0.14673047445536175, -0.989176509964781, 0.1345807085071262, -0.99090263542778,
-    0.1224106751992162, -0.99247953459871, 0.11022220729388306, -0.9939069700023561,
-    0.0980171403295606, -0.9951847266721969, 0.0857973123444399, -0.996312612182778,
-    0.07356456359966743, -0.9972904566786902, 0.06132073630220858, -0.9981181129001492,
-    0.049067674327418015, -0.9987954562051724, 0.03680722294135883, -0.9993223845883495,
-    0.024541228522912288, -0.9996988186962042, 0.012271538285719925, -0.9999247018391445,
-    0.0, -1.0, -0.012271538285719925, -0.9999247018391445,
-    -0.024541228522912288, -0.9996988186962042, -0.03680722294135883, -0.9993223845883495,
-    -0.049067674327418015, -0.9987954562051724, -0.06132073630220858, -0.9981181129001492,
-    -0.07356456359966743, -0.9972904566786902, -0.0857973123444399, -0.996312612182778,
-    -0.0980171403295606, -0.9951847266721969, -0.11022220729388306, -0.9939069700023561,
-    -0.1224106751992162, -0.99247953459871, -0.1345807085071262, -0.99090263542778,
-    -0.14673047445536175, -0.989176509964781, -0.15885814333386145, -0.9873014181578584,
-    -0.17096188876030122, -0.9852776423889412, -0.18303988795514095, -0.9831054874312163,
-    -0.19509032201612828, -0.9807852804032304, -0.20711137619221856, -0.9783173707196277,
-    -0.2191012401568698, -0.9757021300385286, -0.2310581082806711, -0.9729399522055602,
-    -0.2429801799032639, -0.970031253194544, -0.25486565960451457, -0.9669764710448521,
-    -0.26671275747489837, -0.9637760657954398, -0.2785196893850531, -0.9604305194155658,
-    -0.2902846772544624, -0.9569403357322088, -0.3020059493192281, -0.9533060403541939,
-    -0.31368174039889146, -0.9495281805930367, -0.3253102921622629, -0.9456073253805213,
-    -0.33688985339222005, -0.9415440651830208, -0.34841868024943456, -0.937339011912575,
-    -0.35989503653498817, -0.9329927988347388, -0.37131719395183754, -0.9285060804732156,
-    -0.3826834323650898, -0.9238795325112867, -0.3939920400610481, -0.9191138516900578,
-    -0.40524131400498986, -0.9142097557035307, -0.4164295600976372, -0.9091679830905224,
-    -0.4275550934302821, -0.9039892931234433, -0.43861623853852766, -0.8986744656939538,
-    -0.4496113296546066, -0.8932243011955153, -0.46053871095824, -0.8876396204028539,
-    -0.47139673682599764, -0.881921264348355, -0.4821837720791228, -0.8760700941954066,
-    -0.49289819222978404, -0.8700869911087115, -0.5035383837257176, -0.8639728561215867,
-    -0.5141027441932218, -0.8577286100002721, -0.524589682678469, -0.8513551931052652,
-    -0.5349976198870973, -0.8448535652497071, -0.5453249884220465, -0.8382247055548381,
-    -0.5555702330196022, -0.8314696123025452, -0.5657318107836132, -0.8245893027850253,
-    -0.5758081914178453, -0.8175848131515837, -0.5857978574564389, -0.8104571982525948,
-    -0.5956993044924334, -0.8032075314806449, -0.6055110414043255, -0.7958369046088836,
-    -0.6152315905806268, -0.7883464276266062, -0.6248594881423863, -0.7807372285720945,
-    -0.6343932841636455, -0.773010453362737, -0.6438315428897915, -0.765167265622459,
-    -0.6531728429537768, -0.7572088465064846, -0.6624157775901718, -0.7491363945234594,
-    -0.6715589548470184, -0.7409511253549591, -0.680600997795453, -0.7326542716724128,
-    -0.6895405447370669, -0.7242470829514669, -0.6983762494089728, -0.7157308252838187,
-    -0.7071067811865476, -0.7071067811865476, -0.7157308252838187, -0.6983762494089728,
-    -0.7242470829514669, -0.6895405447370669, -0.7326542716724128, -0.680600997795453,
-    -0.7409511253549591, -0.6715589548470184, -0.7491363945234594, -0.6624157775901718,
-    -0.7572088465064846, -0.6531728429537768, -0.765167265622459, -0.6438315428897915,
-    -0.773010453362737, -0.6343932841636455, -0.7807372285720945, -0.6248594881423863,
-    -0.7883464276266062, -0.6152315905806268, -0.7958369046088836, -0.6055110414043255,
-    -0.8032075314806449, -0.5956993044924334, -0.8104571982525948, -0.5857978574564389,
-    -0.8175848131515837, -0.5758081914178453, -0.8245893027850253, -0.5657318107836132,
-    -0.8314696123025452, -0.5555702330196022, -0.8382247055548381, -0.5453249884220465,
-    -0.8448535652497071, -0.5349976198870973, -0.8513551931052652, -0.524589682678469,
-    -0.8577286100002721, -0.5141027441932218, -0.8639728561215867, -0.5035383837257176,
-    -0.8700869911087115, -0.49289819222978404, -0.8760700941954066, -0.4821837720791228,
-    -0.881921264348355, -0.47139673682599764, -0.8876396204028539, -0.46053871095824,
-    -0.8932243011955153, -0.4496113296546066, -0.8986744656939538, -0.43861623853852766,
-    -0.9039892931234433, -0.4275550934302821, -0.9091679830905224, -0.4164295600976372,
-    -0.9142097557035307, -0.40524131400498986, -0.9191138516900578, -0.3939920400610481,
-    -0.9238795325112867, -0.3826834323650898, -0.9285060804732156, -0.37131719395183754,
-    -0.9329927988347388, -0.35989503653498817, -0.937339011912575, -0.34841868024943456,
-    -0.9415440651830208, -0.33688985339222005, -0.9456073253805213, -0.3253102921622629,
-    -0.9495281805930367, -0.31368174039889146, -0.9533060403541939, -0.3020059493192281,
-    -0.9569403357322088, -0.2902846772544624, -0.9604305194155658, -0.2785196893850531,
-    -0.9637760657954398, -0.26671275747489837, -0.9669764710448521, -0.25486565960451457,
-    -0.970031253194544, -0.2429801799032639, -0.9729399522055602, -0.2310581082806711,
-    -0.9757021300385286, -0.2191012401568698, -0.9783173707196277, -0.20711137619221856,
-    -0.9807852804032304, -0.19509032201612828, -0.9831054874312163, -0.18303988795514095,
-    -0.9852776423889412, -0.17096188876030122, -0.9873014181578584, -0.15885814333386145,
-    -0.989176509964781, -0.14673047445536175, -0.99090263542778, -0.1345807085071262,
-    -0.99247953459871, -0.1224106751992162, -0.9939069700023561, -0.11022220729388306,
-    -0.9951847266721969, -0.0980171403295606, -0.996312612182778, -0.0857973123444399,
-    -0.9972904566786902, -0.07356456359966743, -0.9981181129001492, -0.06132073630220858,
-    -0.9987954562051724, -0.049067674327418015, -0.9993223845883495, -0.03680722294135883,
-    -0.9996988186962042, -0.024541228522912288, -0.9999247018391445, -0.012271538285719925,
-    -1.0, 0.0, -0.9999247018391445, 0.012271538285719925,
-    -0.9996988186962042, 0.024541228522912288, -0.9993223845883495, 0.03680722294135883,
-    -0.9987954562051724, 0.049067674327418015, -0.9981181129001492, 0.06132073630220858,
-    -0.9972904566786902, 0.07356456359966743, -0.996312612182778, 0.0857973123444399,
-    -0.9951847266721969, 0.0980171403295606, -0.9939069700023561, 0.11022220729388306,
-    -0.99247953459871, 0.1224106751992162, -0.99090263542778, 0.1345807085071262,
-    -0.989176509964781, 0.14673047445536175, -0.9873014181578584, 0.15885814333386145,
-    -0.9852776423889412, 0.17096188876030122, -0.9831054874312163, 0.18303988795514095,
-    -0.9807852804032304, 0.19509032201612828, -0.9783173707196277, 0.20711137619221856,
-    -0.9757021300385286, 0.2191012401568698, -0.9729399522055602, 0.2310581082806711,
-    -0.970031253194544, 0.2429801799032639, -0.9669764710448521, 0.25486565960451457,
-    -0.9637760657954398, 0.26671275747489837, -0.9604305194155658, 0.2785196893850531,
-    -0.9569403357322088, 0.2902846772544624, -0.9533060403541939, 0.3020059493192281,
-    -0.9495281805930367, 0.31368174039889146, -0.9456073253805213, 0.3253102921622629,
-    -0.9415440651830208, 0.33688985339222005, -0.937339011912575, 0.34841868024943456,
-    -0.9329927988347388, 0.35989503653498817, -0.9285060804732156, 0.37131719395183754,
-    -0.9238795325112867, 0.3826834323650898, -0.9191138516900578, 0.3939920400610481,
-    -0.9142097557035307, 0.40524131400498986, -0.9091679830905224, 0.4164295600976372,
-    -0.9039892931234433, 0.4275550934302821, -0.8986744656939538, 0.43861623853852766,
-    -0.8932243011955153, 0.4496113296546066, -0.8876396204028539, 0.46053871095824,
-    -0.881921264348355, 0.47139673682599764, -0.8760700941954066, 0.4821837720791228,
-    -0.8700869911087115, 0.49289819222978404, -0.8639728561215867, 0.5035383837257176,
-    -0.8577286100002721, 0.5141027441932218, -0.8513551931052652, 0.524589682678469,
-    -0.8448535652497071, 0.5349976198870973, -0.8382247055548381, 0.5453249884220465,
-    -0.8314696123025452, 0.5555702330196022, -0.8245893027850253, 0.5657318107836132,
-    -0.8175848131515837, 0.5758081914178453, -0.8104571982525948, 0.5857978574564389,
-    -0.8032075314806449, 0.5956993044924334, -0.7958369046088836, 0.6055110414043255,
-    -0.7883464276266062, 0.6152315905806268, -0.7807372285720945, 0.6248594881423863,
-    -0.773010453362737, 0.6343932841636455, -0.765167265622459, 0.6438315428897915,
-    -0.7572088465064846, 0.6531728429537768, -0.7491363945234594, 0.6624157775901718,
-    -0.7409511253549591, 0.6715589548470184, -0.7326542716724128, 0.680600997795453,
-    -0.7242470829514669, 0.6895405447370669, -0.7157308252838187, 0.6983762494089728,
-    -0.7071067811865476, 0.7071067811865476, -0.6983762494089728, 0.7157308252838187,
-    -0.6895405447370669, 0.7242470829514669, -0.680600997795453, 0.7326542716724128,
-    -0.6715589548470184, 0.7409511253549591, -0.6624157775901718, 0.7491363945234594,
-    -0.6531728429537768, 0.7572088465064846, -0.6438315428897915, 0.765167265622459,
-    -0.6343932841636455, 0.773010453362737, -0.6248594881423863, 0.7807372285720945,
-    -0.6152315905806268, 0.7883464276266062, -0.6055110414043255, 0.7958369046088836,
-    -0.5956993044924334, 0.8032075314806449, -0.5857978574564389, 0.8104571982525948,
-    -0.5758081914178453, 0.8175848131515837, -0.5657318107836132, 0.8245893027850253,
-    -0.5555702330196022, 0.8314696123025452, -0.5453249884220465, 0.8382247055548381,
-    -0.5349976198870973, 0.8448535652497071, -0.524589682678469, 0.8513551931052652,
-    -0.5141027441932218, 0.8577286100002721, -0.5035383837257176, 0.8639728561215867,
-    -0.49289819222978404, 0.8700869911087115, -0.4821837720791228, 0.8760700941954066,
-    -0.47139673682599764, 0.881921264348355, -0.46053871095824, 0.8876396204028539,
-    -0.4496113296546066, 0.8932243011955153, -0.43861623853852766, 0.8986744656939538,
-    -0.4275550934302821, 0.9039892931234433, -0.4164295600976372, 0.9091679830905224,
-    -0.40524131400498986, 0.9142097557035307, -0.3939920400610481, 0.9191138516900578,
-    -0.3826834323650898, 0.9238795325112867, -0.37131719395183754, 0.9285060804732156,
-    -0.35989503653498817, 0.9329927988347388, -0.34841868024943456, 0.937339011912575,
-    -0.33688985339222005, 0.9415440651830208, -0.3253102921622629, 0.9456073253805213,
-    -0.31368174039889146, 0.9495281805930367, -0.3020059493192281, 0.9533060403541939,
-    -0.2902846772544624, 0.9569403357322088, -0.2785196893850531, 0.9604305194155658,
-    -0.26671275747489837, 0.9637760657954398, -0.25486565960451457, 0.9669764710448521,
-    -0.2429801799032639, 0.970031253194544, -0.2310581082806711, 0.9729399522055602,
-    -0.2191012401568698, 0.9757021300385286, -0.20711137619221856, 0.9783173707196277,
-    -0.19509032201612828, 0.9807852804032304, -0.18303988795514095, 0.9831054874312163,
-    -0.17096188876030122, 0.9852776423889412, -0.15885814333386145, 0.9873014181578584,
-    -0.14673047445536175, 0.989176509964781, -0.1345807085071262, 0.99090263542778,
-    -0.1224106751992162, 0.99247953459871, -0.11022220729388306, 0.9939069700023561,
-    -0.0980171403295606, 0.9951847266721969, -0.0857973123444399, 0.996312612182778,
-    -0.07356456359966743, 0.9972904566786902, -0.06132073630220858, 0.9981181129001492,
-    -0.049067674327418015, 0.9987954562051724, -0.03680722294135883, 0.9993223845883495,
-    -0.024541228522912288, 0.9996988186962042, -0.012271538285719925, 0.9999247018391445,
-};
-KSL_HD void sincos_grid(double x, const double *grid, double &s, double &c) {
-    const double t = fma_rn(x, kGridTab[0], kGridTab[1]);
-    const int k = lo_word(t) & (kGridPoints - 1);
-    const double fn = t - kGridTab[1];
-    const double r = fma_rn(-fn, kGridTab[3], fma_rn(-fn, kGridTab[2], x));
-    const double z = r * r;
-    const double sr = fma_rn(z * fma_rn(z, kGridTab[5], kGridTab[4]), r, r);   // sin r
-    const double cm1 = z * fma_rn(z, kGridTab[7], kGridTab[6]);               // cos r - 1
-#if defined(__CUDA_ARCH__)
-    const double2 sc = *reinterpret_cast<const double2 *>(grid + 2 * k);
-    const double S = sc.x, C = sc.y;
-#else
-    const double S = grid[2 * k], C = grid[2 * k + 1];
-#endif
-    s = fma_rn(C, sr, fma_rn(S, cm1, S));
-    c = fma_rn(-S, sr, fma_rn(C, cm1, C));
-}
-
-// the grid point nearest to x: (S, C) = (sin, cos)(x - r) straight from the table, |r| <= pi / 512
-KSL_HD double grid_point(double x, const double *grid, double &S, double &C) {
-    const double t = fma_rn(x, kGridTab[0], kGridTab[1]);
-    const int k = lo_word(t) & (kGridPoints - 1);
-    const double fn = t - kGridTab[1];
-#if defined(__CUDA_ARCH__)
-    const double2 sc = *reinterpret_cast<const double2 *>(grid + 2 * k);
-    S = sc.x;
-    C = sc.y;
-#else
-    S = grid[2 * k];
-    C = grid[2 * k + 1];
-#endif
-    return fma_rn(-fn, kGridTab[3], fma_rn(-fn, kGridTab[2], x));
-}
-
 KSL_HD double rcp_seed(double b) {
 #if defined(__CUDA_ARCH__)
     double r;
