@@ -103,7 +103,11 @@ int ksl_sgp4_init(const double *elems, int64_t n, double *consts, int32_t *err, 
  * (util.py:571,576; model.py:541).  tsince is [m] shared by all n records
  * (per_sample_t = 0) or [n][m] (per_sample_t = 1).  rv_km [n][m][6] = x,y,z km,
  * vx,vy,vz km/s.  err[n] is OR-ed with the bits raised at any epoch (caller zeroes
- * or passes the array ksl_sgp4_init filled). */
+ * or passes the array ksl_sgp4_init filled).
+ * Numerical contract of every SGP4 evaluation behind this ABI: Vallado's near-earth
+ * algorithm as dsgp4 computes it; with identical constants the state agrees with
+ * that algorithm to 4e-12 km / 1e-14 km/s typically and 1e-8 km / 1e-11 km/s at
+ * worst (tests/test_hostcheck.py; the tolerance of record is 1e-6 km). */
 int ksl_sgp4_prop(const double *consts, int64_t n, const double *tsince, int64_t m, int per_sample_t,
                   double *rv_km, int32_t *err, void *stream);
 
@@ -137,7 +141,10 @@ int ksl_find_conjunction(const double *tr0, const double *tr1, int64_t n, int64_
  *   init_err_t [n_t] / init_err_c [n]: err arrays from ksl_sgp4_init (NULL = none);
  *   a deep-space record makes the trace a propagation error: i_min = -1.
  * Outputs (device, [n]): i_min, d_min [m], i_conj (-1 = None), d_conj [m] (NaN = None),
- * err (target bits 0..7, chaser bits 8..15).
+ * err (target bits 0..7, chaser bits 8..15).  The indices are those of the reference's
+ * enumeration of all n_fine points (first index on ties, NaN counts as the minimum),
+ * whichever search mode is used; samples are independent (any split or order of the
+ * batch gives the same per-sample results).
  * workspace: ksl_screen_ws(n_t, n, n_coarse) bytes of device memory. */
 int64_t ksl_screen_ws(int64_t n_t, int64_t n, int64_t n_coarse);
 int ksl_screen(const double *consts_t, const double *epoch_t, const int32_t *init_err_t, int64_t n_t,
