@@ -1435,7 +1435,7 @@ int ksl_screen(const double *consts_t, const double *epoch_t, const int32_t *ini
     // enough samples to give (three quarters of) the resident warps their own trace -> warp-per-trace kernel, else
     // CTA-per-trace (measured crossover on B200: ~1700 of 2368 warps; one warp needs 0.7 ms for a default trace, a CTA 0.18 ms)
     // (the warp kernel keeps 32-bit epoch / fine-grid indices)
-    const bool fits32 = n_coarse < 0x7fffffffLL && n_fine < 0x7fffffffLL;
+    const bool fits32 = n_coarse < 0x40000000LL && n_fine < 0x7fffffffLL;   // (chunk bases advance by 32 in an int)
     const bool per_warp = fits32 && ((force & KSL_SCREEN_FORCE_WARP) ||
                                      (!(force & KSL_SCREEN_FORCE_CTA) && 4 * n >= 3LL * sms * KSL_SCREEN_MIN_CTAS * kWarpsPerCta));
     long long grid = (long long)sms * KSL_SCREEN_MIN_CTAS;
