@@ -671,11 +671,10 @@ __global__ void __launch_bounds__(kTcaThreads) k_tca_moments(const double *__res
     for (int q = 0; q < 6; ++q) rf[q] = ref[q];
     unsigned long long nerr = 0;
     for (long long i = (long long)blockIdx.x * kTcaThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kTcaThreads) {
-        double el[7], c[KSL_NCONST], x[6];
+        double el[7], x[6];
 #pragma unroll
         for (int k = 0; k < 7; ++k) el[k] = elems[k * n + i];
-        int e = ksl::sgp4_init(el, [&](int k, double v) { c[k] = v; });
-        e |= ksl::sgp4_state([&](int k) { return c[k]; }, tsince, x, x + 3, ksl::kGridSinCos);
+        int e = ksl::sgp4_init_state(el, tsince, x, x + 3, ksl::kGridSinCos);
 #pragma unroll
         for (int q = 0; q < 6; ++q) x[q] *= 1e3;  // model.py:541: *1e3 -> metres
         if (states) {
@@ -853,9 +852,7 @@ __device__ __forceinline__ int mc_state(const McObject &o, const double z[6], do
     el[6] = o.bstar;
 #pragma unroll
     for (int r = 0; r < 7; ++r) el_out[r] = el[r];
-    double c[KSL_NCONST];
-    int e = ksl::sgp4_init(el, [&](int k, double v) { c[k] = v; });
-    e |= ksl::sgp4_state([&](int k) { return c[k]; }, o.tsince, x, x + 3, ksl::kGridSinCos);
+    const int e = ksl::sgp4_init_state(el, o.tsince, x, x + 3, ksl::kGridSinCos);
 #pragma unroll
     for (int r = 0; r < 6; ++r) x[r] *= 1e3;
     return e;

@@ -781,6 +781,34 @@ KSL_HD int sgp4_state(Base base, double t, double r[3], double v[3], const doubl
     return e;
 }
 
+// sgp4init + full state for one element set (the Monte Carlo kernels: one record per sample, used once).  The record
+// stays in registers: the fast path reads it through a FastView, and when it declines, an out-of-line routine redoes
+// init + the exact path from the 7 elements, so nothing ever takes the record's address.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+int sgp4_init_state_exact(const double *el, double t, double *r, double *v) {
+    double c[KSL_NCONST];
+    int e = sgp4_init(el, [&](int k, double val) { c[k] = val; });
+    e |= sgp4_prop<true>([&](int k) { return c[k]; }, t, r, v);
+    return e;
+}
+KSL_HD int sgp4_init_state(const double el[7], double t, double r[3], double v[3], const double *grid) {
+    double c[KSL_NCONST];
+    const int e = sgp4_init(el, [&](int k, double val) { c[k] = val; });
+    auto ld = [&](int k) { return c[k]; };
+    const FastView<decltype(ld)> view{ld, c[KSL_C_ISIMP] != 0.0};
+    if (sgp4_prop_fast_rv<true>(view, t, r, v, grid)) return e;
+    double elx[7], rx[3], vx[3];
+    for (int k = 0; k < 7; ++k) elx[k] = el[k];
+    const int e2 = sgp4_init_state_exact(elx, t, rx, vx);
+    r[0] = rx[0]; r[1] = rx[1]; r[2] = rx[2];
+    v[0] = vx[0]; v[1] = vx[1]; v[2] = vx[2];
+    return e2;
+}
+
 // position at t through the fast path, falling back to the exact path when needed (c: masked record).  The exact path
 // is kept out of line on the device so that its registers do not count against the hot path.
 #if defined(__CUDACC__)
