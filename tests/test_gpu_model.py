@@ -325,3 +325,34 @@ def test_default_prior_forward_and_batch(kb):
             assert "c_prop_error" in tr.nodes and bool(tr.nodes["conj"]["value"]) == bool(b["conj"][k])
             if b["conj"][k]:
                 assert int(tr.nodes["i_conj"]["value"]) == b["i_conj"][k]
+
+
+def test_config0_thousand_prior_traces_of_the_default_pair(kb):
+    """BASELINE configs[0]: Conjunction prior sampling, 1 000 traces of the default LEO pair (tests/test_model.py:20-26
+    of the reference) over the 7-day window.  With both TLEs given the prior draws only the mean anomalies
+    (model.py:269,308), quantised by the TLE text (1e-4 deg); every trace's space segment is checked against the C
+    oracle's exhaustive enumeration of the 600 000 fine points on the very same quantised elements."""
+    from kessler_b200 import workloads as W
+    M = kb["M"]
+    t_tle, c_tle = W.pair_a()
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = M.Conjunction(t_tle=t_tle, c_tle=c_tle, time0=t_tle.date_mjd - 3.5)
+    n = 1000
+    b = model.forward_batch(n)
+    assert not b["prefiltered"].any() and not b["prop_error"].any()
+    # the draws: uniform mean anomalies on the text grid, everything else the given TLE's
+    for raw, el, tle in ((b["t_raw"], b["elems_t"], t_tle), (b["c_raw"], b["elems_c"], c_tle)):
+        m = np.asarray(raw["mean_anomaly"])
+        assert m.min() >= 0.0 and m.max() < 2 * np.pi and 2.8 < m.mean() < 3.5
+        deg = np.rad2deg(el[5])
+        assert np.abs(deg * 1e4 - np.round(deg * 1e4)).max() < 1e-6
+        assert np.all(el[1] == tle._ecco) and np.all(el[2] == tle._inclo) and np.all(el[6] == tle._bstar)
+    times = model.time_grid()
+    tc = np.ascontiguousarray(times[::100])
+    ref = C.screen(np.ascontiguousarray(b["elems_t"]), b["epoch_t"], np.ascontiguousarray(b["elems_c"]), b["epoch_c"], tc, len(times),
+                   5000.0)
+    assert np.array_equal(b["i_min"], ref["i_min"]) and np.array_equal(b["i_conj"], ref["i_conj"])
+    assert np.abs(b["d_min"] - ref["d_min"]).max() < 1e-3                         # metres (tolerance of record: 1 m)
+    assert np.array_equal(b["conj"], ref["i_conj"] > 0)
+    assert np.array_equal(b["time_min"], times[ref["i_min"]])                     # TCA: same fine-grid epoch, bit for bit
