@@ -1707,7 +1707,8 @@ namespace {
 struct HostCache {
     char *arena = nullptr;
     size_t cap = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
 };
 HostCache g_cache[64];
 std::mutex g_cache_mu;
@@ -1733,6 +1734,9 @@ extern "C" int ksl_host_cache_free(void) {
         cudaSetDevice(d);
         if (g_cache[d].arena) cudaFree(g_cache[d].arena);
         if (g_cache[d].stream) cudaStreamDestroy(g_cache[d].stream);
+        if (g_cache[d].stream2) cudaStreamDestroy(g_cache[d].stream2);
+        if (g_cache[d].ev_ready) cudaEventDestroy(g_cache[d].ev_ready);
+        if (g_cache[d].ev_done) cudaEventDestroy(g_cache[d].ev_done);
         g_cache[d] = HostCache();
     }
     cudaSetDevice(cur);
@@ -1753,13 +1757,26 @@ extern "C" int ksl_screen_host(int device, const double *elems_t, const double *
     std::lock_guard<std::mutex> lk(g_cache_mu);
     KSL_CUDA(cudaSetDevice(device));
     HostCache &hc = g_cache[device];
-    if (!hc.stream) KSL_CUDA(cudaStreamCreateWithFlags(&hc.stream, cudaStreamNonBlocking));
-    const size_t un = (size_t)n, unt = (size_t)n_t, unc = (size_t)n_coarse;
+    if (!hc.stream) {
+        KSL_CUDA(cudaStreamCreateWithFlags(&hc.stream, cudaStreamNonBlocking));
+        KSL_CUDA(cudaStreamCreateWithFlags(&hc.stream2, cudaStreamNonBlocking));
+        KSL_CUDA(cudaEventCreateWithFlags(&hc.ev_ready, cudaEventDisableTiming));
+        KSL_CUDA(cudaEventCreateWithFlags(&hc.ev_done, cudaEventDisableTiming));
+    }
+    // Large batches go through in chunks on two streams: the host->device copy of chunk j+1 and the device->host copy of
+    // chunk j-1 overlap the kernels of chunk j (samples are independent, so chunking cannot change a result).
+    const bool shared = (n_t == 1);
+    const int nchunk = (n >= (1 << 18)) ? 4 : 1;
+    const size_t un = (size_t)n, unc = (size_t)n_coarse;
+    const size_t m = (un + (size_t)nchunk - 1) / (size_t)nchunk;          // samples per chunk (the last may be shorter)
+    const int nslot = nchunk > 1 ? 2 : 1;
+    const size_t mt = shared ? 1 : m;
     auto pad = [](size_t b) { return ((b + 255) / 256) * 256; };
-    size_t need = pad(8 * 7 * unt) + pad(8 * 7 * un) + pad(8 * unt) + pad(8 * un) + pad(8 * unc) +
-                  pad(8 * KSL_NCONST * unt) + pad(8 * KSL_NCONST * un) + pad(4 * unt) + pad(4 * un) +
-                  4 * pad(8 * un) + pad(4 * un) + pad((size_t)ksl_screen_ws(n_t, n, n_coarse)) +
-                  pad((size_t)ksl_screen_summary_ws(n)) + pad(8 * KSL_SUM_NCOUNT) + pad(8 * KSL_SUM_NMOMENT) + 4096;
+    const size_t ws_bytes = (size_t)ksl_screen_ws(shared ? 1 : (int64_t)m, (int64_t)m, n_coarse);
+    const size_t slot_bytes = pad(8 * 7 * m) + pad(8 * m) + pad(8 * KSL_NCONST * m) + pad(4 * m) +
+                              pad(8 * 7 * mt) + pad(8 * mt) + pad(8 * KSL_NCONST * mt) + pad(4 * mt) + pad(ws_bytes);
+    const size_t need = pad(8 * unc) + 4 * pad(8 * un) + pad(4 * un) + (size_t)nslot * slot_bytes +
+                        pad((size_t)ksl_screen_summary_ws(n)) + pad(8 * KSL_SUM_NCOUNT) + pad(8 * KSL_SUM_NMOMENT) + 4096;
     if (hc.cap < need) {
         if (hc.arena) KSL_CUDA(cudaFree(hc.arena));
         hc.arena = nullptr;
@@ -1768,41 +1785,69 @@ extern "C" int ksl_screen_host(int device, const double *elems_t, const double *
         hc.cap = need;
     }
     Bump b{hc.arena};
-    double *d_elems_t = b.take<double>(7 * unt), *d_elems_c = b.take<double>(7 * un);
-    double *d_epoch_t = b.take<double>(unt), *d_epoch_c = b.take<double>(un), *d_times = b.take<double>(unc);
-    double *d_consts_t = b.take<double>(KSL_NCONST * unt), *d_consts_c = b.take<double>(KSL_NCONST * un);
-    int32_t *d_ierr_t = b.take<int32_t>(unt), *d_ierr_c = b.take<int32_t>(un);
+    double *d_times = b.take<double>(unc);
     int64_t *d_imin = b.take<int64_t>(un), *d_iconj = b.take<int64_t>(un);
     double *d_dmin = b.take<double>(un), *d_dconj = b.take<double>(un);
     int32_t *d_err = b.take<int32_t>(un);
-    void *d_ws = b.take<char>((size_t)ksl_screen_ws(n_t, n, n_coarse));
+    struct Slot {
+        double *el_c, *ep_c, *consts_c, *el_t, *ep_t, *consts_t;
+        int32_t *ierr_c, *ierr_t;
+        void *ws;
+    } slot[2];
+    for (int q = 0; q < nslot; ++q) {
+        slot[q].el_c = b.take<double>(7 * m); slot[q].ep_c = b.take<double>(m); slot[q].consts_c = b.take<double>(KSL_NCONST * m);
+        slot[q].ierr_c = b.take<int32_t>(m);
+        slot[q].el_t = b.take<double>(7 * mt); slot[q].ep_t = b.take<double>(mt); slot[q].consts_t = b.take<double>(KSL_NCONST * mt);
+        slot[q].ierr_t = b.take<int32_t>(mt);
+        slot[q].ws = b.take<char>(ws_bytes);
+    }
     void *d_sws = b.take<char>((size_t)ksl_screen_summary_ws(n));
     uint64_t *d_counts = b.take<uint64_t>(KSL_SUM_NCOUNT);
     double *d_mom = b.take<double>(KSL_SUM_NMOMENT);
-    cudaStream_t st = hc.stream;
-    KSL_CUDA(cudaMemcpyAsync(d_elems_t, elems_t, 8 * 7 * unt, cudaMemcpyHostToDevice, st));
-    KSL_CUDA(cudaMemcpyAsync(d_elems_c, elems_c, 8 * 7 * un, cudaMemcpyHostToDevice, st));
-    KSL_CUDA(cudaMemcpyAsync(d_epoch_t, epoch_t, 8 * unt, cudaMemcpyHostToDevice, st));
-    KSL_CUDA(cudaMemcpyAsync(d_epoch_c, epoch_c, 8 * un, cudaMemcpyHostToDevice, st));
-    KSL_CUDA(cudaMemcpyAsync(d_times, times_coarse, 8 * unc, cudaMemcpyHostToDevice, st));
-    int rc = ksl_sgp4_init(d_elems_t, n_t, d_consts_t, d_ierr_t, st);
-    if (rc) return rc;
-    rc = ksl_sgp4_init(d_elems_c, n, d_consts_c, d_ierr_c, st);
-    if (rc) return rc;
-    rc = ksl_screen(d_consts_t, d_epoch_t, d_ierr_t, n_t, d_consts_c, d_epoch_c, d_ierr_c, n, d_times, n_coarse, n_fine, thr_m,
-                    mode, d_imin, d_dmin, d_iconj, d_dconj, d_err, d_ws, st);
-    if (rc) return rc;
-    if (summary_counts || summary_moments) {
-        rc = ksl_screen_summary(d_iconj, d_dmin, d_err, n, collision_thr_m, d_counts, d_mom, d_sws, st);
+    cudaStream_t streams[2] = {hc.stream, hc.stream2};
+    KSL_CUDA(cudaMemcpyAsync(d_times, times_coarse, 8 * unc, cudaMemcpyHostToDevice, streams[0]));
+    KSL_CUDA(cudaEventRecord(hc.ev_ready, streams[0]));
+    for (int j = 0; j < nchunk; ++j) {
+        const size_t off = (size_t)j * m;
+        if (off >= un) break;
+        const size_t len = (off + m <= un) ? m : un - off;
+        Slot &sl = slot[j % nslot];
+        cudaStream_t st = streams[j % nslot];
+        if (j == 1) KSL_CUDA(cudaStreamWaitEvent(st, hc.ev_ready, 0));       // the time grid, copied on the other stream
+        // element SoA [7][n] -> the chunk's own SoA [7][len]
+        KSL_CUDA(cudaMemcpy2DAsync(sl.el_c, 8 * len, elems_c + off, 8 * un, 8 * len, 7, cudaMemcpyHostToDevice, st));
+        KSL_CUDA(cudaMemcpyAsync(sl.ep_c, epoch_c + off, 8 * len, cudaMemcpyHostToDevice, st));
+        const size_t lt = shared ? 1 : len;
+        if (shared) {
+            KSL_CUDA(cudaMemcpyAsync(sl.el_t, elems_t, 8 * 7, cudaMemcpyHostToDevice, st));
+            KSL_CUDA(cudaMemcpyAsync(sl.ep_t, epoch_t, 8, cudaMemcpyHostToDevice, st));
+        } else {
+            KSL_CUDA(cudaMemcpy2DAsync(sl.el_t, 8 * len, elems_t + off, 8 * un, 8 * len, 7, cudaMemcpyHostToDevice, st));
+            KSL_CUDA(cudaMemcpyAsync(sl.ep_t, epoch_t + off, 8 * len, cudaMemcpyHostToDevice, st));
+        }
+        int rc = ksl_sgp4_init(sl.el_t, (int64_t)lt, sl.consts_t, sl.ierr_t, st);
         if (rc) return rc;
-        if (summary_counts) KSL_CUDA(cudaMemcpyAsync(summary_counts, d_counts, 8 * KSL_SUM_NCOUNT, cudaMemcpyDeviceToHost, st));
-        if (summary_moments) KSL_CUDA(cudaMemcpyAsync(summary_moments, d_mom, 8 * KSL_SUM_NMOMENT, cudaMemcpyDeviceToHost, st));
+        rc = ksl_sgp4_init(sl.el_c, (int64_t)len, sl.consts_c, sl.ierr_c, st);
+        if (rc) return rc;
+        rc = ksl_screen(sl.consts_t, sl.ep_t, sl.ierr_t, (int64_t)lt, sl.consts_c, sl.ep_c, sl.ierr_c, (int64_t)len, d_times, n_coarse,
+                        n_fine, thr_m, mode, d_imin + off, d_dmin + off, d_iconj + off, d_dconj + off, d_err + off, sl.ws, st);
+        if (rc) return rc;
+        KSL_CUDA(cudaMemcpyAsync(i_min + off, d_imin + off, 8 * len, cudaMemcpyDeviceToHost, st));
+        KSL_CUDA(cudaMemcpyAsync(d_min + off, d_dmin + off, 8 * len, cudaMemcpyDeviceToHost, st));
+        KSL_CUDA(cudaMemcpyAsync(i_conj + off, d_iconj + off, 8 * len, cudaMemcpyDeviceToHost, st));
+        KSL_CUDA(cudaMemcpyAsync(d_conj + off, d_dconj + off, 8 * len, cudaMemcpyDeviceToHost, st));
+        if (err) KSL_CUDA(cudaMemcpyAsync(err + off, d_err + off, 4 * len, cudaMemcpyDeviceToHost, st));
     }
-    KSL_CUDA(cudaMemcpyAsync(i_min, d_imin, 8 * un, cudaMemcpyDeviceToHost, st));
-    KSL_CUDA(cudaMemcpyAsync(d_min, d_dmin, 8 * un, cudaMemcpyDeviceToHost, st));
-    KSL_CUDA(cudaMemcpyAsync(i_conj, d_iconj, 8 * un, cudaMemcpyDeviceToHost, st));
-    KSL_CUDA(cudaMemcpyAsync(d_conj, d_dconj, 8 * un, cudaMemcpyDeviceToHost, st));
-    if (err) KSL_CUDA(cudaMemcpyAsync(err, d_err, 4 * un, cudaMemcpyDeviceToHost, st));
-    KSL_CUDA(cudaStreamSynchronize(st));
+    if (nslot > 1) {
+        KSL_CUDA(cudaEventRecord(hc.ev_done, streams[1]));
+        KSL_CUDA(cudaStreamWaitEvent(streams[0], hc.ev_done, 0));
+    }
+    if (summary_counts || summary_moments) {
+        int rc = ksl_screen_summary(d_iconj, d_dmin, d_err, n, collision_thr_m, d_counts, d_mom, d_sws, streams[0]);
+        if (rc) return rc;
+        if (summary_counts) KSL_CUDA(cudaMemcpyAsync(summary_counts, d_counts, 8 * KSL_SUM_NCOUNT, cudaMemcpyDeviceToHost, streams[0]));
+        if (summary_moments) KSL_CUDA(cudaMemcpyAsync(summary_moments, d_mom, 8 * KSL_SUM_NMOMENT, cudaMemcpyDeviceToHost, streams[0]));
+    }
+    KSL_CUDA(cudaStreamSynchronize(streams[0]));
     return KSL_OK;
 }

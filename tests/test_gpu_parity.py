@@ -409,6 +409,33 @@ def test_screen_host_and_summary(eng):
     assert m[2] == pytest.approx((dev["d_min"] ** 2).sum(), rel=1e-12) and m[3] == dev["d_min"].min()
 
 
+def test_screen_host_chunked_pipeline(eng):
+    """Above 2^18 samples ksl_screen_host streams the batch through in four chunks on two streams (copies overlap
+    kernels): every per-sample output and the summary equal the single-launch device path, with per-sample targets
+    (ragged last chunk) and with one shared target."""
+    elt, ept, elc, epc, times, _ = _golden_batch(3000, 17)
+    n = (1 << 18) + 1237
+    rep = lambda a: np.ascontiguousarray(np.tile(a, (1, n // a.shape[1] + 1))[:, :n])
+    elt_b, elc_b = rep(elt), rep(elc)
+    rng = np.random.default_rng(2)
+    elc_b[5] = np.mod(elc_b[5] + np.round(rng.uniform(0, 360, n), 4) * np.pi / 180 * (rng.uniform(size=n) < 0.5), 2 * np.pi)
+    ept_b, epc_b = np.full(n, ept[0]), np.full(n, epc[0])
+    tc = np.ascontiguousarray(times[::100][:601])
+    nf = 60001
+    for shared in (False, True):
+        et, ep = (elt_b[:, :1].copy(), ept_b[:1]) if shared else (elt_b, ept_b)
+        dev = _screen(eng, et, ep, elc_b, epc_b, tc, nf, 5e3, 0)
+        host = eng.screen_host(et, ep, elc_b, epc_b, tc, nf, 5e3, 0, collision_thr_m=4900.0)
+        for k in ("i_min", "i_conj", "err", "d_min"):
+            assert np.array_equal(host[k], dev[k]), (shared, k)
+        assert np.array_equal(np.isnan(host["d_conj"]), np.isnan(dev["d_conj"]))
+        ok = ~np.isnan(dev["d_conj"])
+        assert np.array_equal(host["d_conj"][ok], dev["d_conj"][ok])
+        cnt = host["counts"].astype(np.int64)
+        assert cnt[0] == n and cnt[2] == (dev["i_conj"] >= 0).sum() and cnt[4] == (dev["d_min"] < 4900.0).sum()
+        assert host["moments"][3] == dev["d_min"].min()
+
+
 # ---------------------------------------------------------------------------------------
 def test_tca_moments_parity(eng):
     """model.py:523-550 on the default mc_samples = 100 and on 20 000 samples."""
