@@ -221,3 +221,89 @@ def test_cdm_record_roundtrip():
     assert c.get_object(0, "X") == 7000.0
     with pytest.raises(ValueError):
         c.set_object(2, "X", 0.0)
+
+
+def test_cdm_kvn_wire_format_roundtrip(tmp_path):
+    """The reference's own CDM test (tests/test_cdm.py: load -> save -> load gives an equal message) on a message in
+    the reference's KVN layout, plus what that layout is: 37-column keys, obligatory keys always written, unknown keys
+    and comments ignored, exponents as %.3E."""
+    text = """
+        COMMENT an example in the layout the reference writes
+        CCSDS_CDM_VERS                        = 1.0
+        CREATION_DATE                         = 2021-03-04T10:20:30.000
+        ORIGINATOR                            = KESSLER_SOFTWARE
+        MESSAGE_ID                            = KESSLER_SOFTWARE_0001
+        TCA                                   = 2021-03-07T01:02:03.500
+        MISS_DISTANCE                         = 715.5
+        RELATIVE_SPEED                        = 14123.25
+        COLLISION_PROBABILITY                 = 3.25E-05
+        COLLISION_PROBABILITY_METHOD          = MC
+        SOME_FUTURE_KEY                       = ignored
+        OBJECT                                = OBJECT1
+        OBJECT_DESIGNATOR                     = 12345.0
+        CATALOG_NAME                          = SATCAT
+        OBJECT_NAME                           = TARGET
+        INTERNATIONAL_DESIGNATOR              = 1998-067A
+        EPHEMERIS_NAME                        = NONE
+        COVARIANCE_METHOD                     = CALCULATED
+        MANEUVERABLE                          = N/A
+        REF_FRAME                             = ITRF
+        SEDR                                  = 7.305E-05
+        X                                     = -731.97
+        Y                                     = -1871.2
+        Z                                     = -6876.4
+        X_DOT                                 = -1.1177
+        Y_DOT                                 = -7.044
+        Z_DOT                                 = 2.0366
+        CR_R                                  = 38.33
+        CT_R                                  = 93.6
+        CT_T                                  = 3410.0
+        CDRG_R                                = 1.5
+        OBJECT                                = OBJECT2
+        OBJECT_DESIGNATOR                     = 54321.0
+        OBJECT_NAME                           = CHASER
+        X                                     = -731.5
+        Y                                     = -1871.0
+        Z                                     = -6876.0
+        X_DOT                                 = 1.0
+        Y_DOT                                 = 7.0
+        Z_DOT                                 = -2.0
+        CR_R                                  = 1.0e-9
+    """
+    p1, p2 = str(tmp_path / "a.cdm.kvn.txt"), str(tmp_path / "b.cdm.kvn.txt")
+    with open(p1, "w") as f:
+        f.write(text)
+    a = ConjunctionDataMessage.load(p1)
+    a.save(p2)
+    b = ConjunctionDataMessage(p2)                      # constructor form of load (cdm.py:61-62)
+    assert a == b and hash(a) == hash(b) and a.kvn() == b.kvn()
+    assert a["MISS_DISTANCE"] == 715.5 and a["COLLISION_PROBABILITY"] == 3.25e-5 and a["OBJECT1_OBJECT_NAME"] == "TARGET"
+    assert a["OBJECT2_X"] == -731.5 and a.get_object(0, "SEDR") == 7.305e-5 and a.get_object(0, "CDRG_R") == 1.5
+    assert np.isnan(a.get_object(1, "CT_T")) and a.to_dict()["OBJECT2_CT_T"] is None
+    lines = a.kvn().splitlines()
+    assert all(line[37:39] == " =" for line in lines)
+    assert "COLLISION_PROBABILITY".ljust(37) + " = 3.250E-05" in lines and "MISS_DISTANCE".ljust(37) + " = 715.5" in lines
+    assert "CT_T".ljust(37) + " =" in lines                      # obligatory but unset for object 2: written empty
+    assert not any(line.startswith("SOME_FUTURE_KEY") or line.startswith("COMMENT") for line in lines)
+    assert len(a.kvn(show_all=True).splitlines()) == 5 + 20 + 2 * (21 + 18 + 6 + 45)
+    missing = a.validate()
+    assert ("Object2 metadata", "CATALOG_NAME") in missing and ("header", "ORIGINATOR") not in missing
+    c = b.copy()
+    c["OBJECT2_Z"] = -6875.0
+    assert c != a
+    # a message produced by set_state / set_covariance survives the wire format with its derived fields
+    m = ConjunctionDataMessage()
+    m.set_header("ORIGINATOR", "KESSLER_SOFTWARE")
+    m.set_header("MESSAGE_ID", "X1")
+    m.set_relative_metadata("TCA", "2021-03-07T01:02:03.500000")
+    m.set_state(0, np.array([[7000., 0, 0], [0, 7.5, 0]]))
+    m.set_state(1, np.array([[7000., 1, 0.5], [0, -7.5, 0]]))
+    cov = np.diag([1.0, 2.0, 3.0, 1e-6, 2e-6, 3e-6])
+    m.set_covariance(0, cov)
+    m.set_covariance(1, 2 * cov)
+    m.save(p1)
+    back = ConjunctionDataMessage.load(p1)
+    assert back["MISS_DISTANCE"] == pytest.approx(m["MISS_DISTANCE"]) and np.allclose(back.get_covariance(1), 2 * cov)
+    assert np.allclose(back.get_state_relative(), m.get_state_relative())
+    frame = m.to_dataframe()
+    assert frame.shape[0] == 1 and frame["OBJECT1_X"][0] == 7000.0 and "OBJECT2_CNDOT_NDOT" in frame.columns
