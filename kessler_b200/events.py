@@ -18,6 +18,7 @@ against it event by event.  Random streams differ from the sequential path (one 
 stage instead of one per CDM), so the outputs are equal in distribution, not sample by sample.
 """
 import math
+import uuid
 
 import numpy as np
 import torch
@@ -220,9 +221,11 @@ def to_cdms(model, res, e, t_tle=None, c_tle=None):
             continue
         cdm = ConjunctionDataMessage()
         cdm.set_header("ORIGINATOR", "KESSLER_SOFTWARE")
-        if t_tle is not None and c_tle is not None:
-            model._describe_object(cdm, 0, t_tle, True, "TARGET")
-            model._describe_object(cdm, 1, c_tle, True, "CHASER")
+        # object metadata as generate_cdm writes it (model.py:335-372): from the TLEs when the caller has them, the
+        # KESSLER_SOFTWARE placeholders of a prior-sampled object otherwise -- every obligatory CCSDS key is set
+        model._describe_object(cdm, 0, t_tle, t_tle is not None, "TARGET")
+        model._describe_object(cdm, 1, c_tle, c_tle is not None, "CHASER")
+        cdm.set_header("MESSAGE_ID", "KESSLER_SOFTWARE_{}".format(uuid.uuid1()))
         cdm.set_relative_metadata("TCA", util.from_jd_to_cdm_datetime_str(tca_jd))
         cdm.set_header("CREATION_DATE", util.from_jd_to_cdm_datetime_str(util.from_mjd_to_jd(res["time_cdm"][i])))
         for o in (0, 1):

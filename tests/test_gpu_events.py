@@ -158,3 +158,27 @@ def test_feature_tensor_matches_cdm_objects(setup):
             want = [util.from_date_str_to_days(cdm["CREATION_DATE"], date0=date0), util.from_date_str_to_days(cdm["TCA"], date0=date0)]
             want += [cdm[k] for k in ev_mod.LSTM_FEATURES[2:]]
             assert np.allclose(row, np.array(want, dtype=np.float64), rtol=1e-12, atol=1e-9)
+
+
+def test_generated_cdms_are_complete_and_survive_the_wire_format(setup, tmp_path):
+    """Every CDM of the batched ground segment carries all obligatory CCSDS keys and reads back from its KVN file with
+    the same numbers (to the 16 significant digits `str(float)` writes; exponents are written with 4 digits, as the
+    reference does)."""
+    from kessler_b200.cdm import ConjunctionDataMessage, Event
+    ev_mod, model, batch, hits = setup["events"], setup["model"], setup["batch"], setup["hits"]
+    res = ev_mod.generate_cdm_batch(model, batch, hits, seed=3)
+    cdms = ev_mod.to_cdms(model, res, 0)
+    assert len(cdms) >= 1
+    paths = Event(cdms).save(str(tmp_path / "event0"))
+    assert len(paths) == len(cdms)
+    for cdm, path in zip(cdms, paths):
+        assert cdm.validate() == []
+        back = ConjunctionDataMessage.load(path)
+        assert back.validate() == []
+        for key in ("TCA", "CREATION_DATE", "OBJECT1_OBJECT_NAME", "OBJECT2_OBJECT_DESIGNATOR", "COLLISION_PROBABILITY_METHOD"):
+            assert str(back[key]) == str(cdm[key])
+        for key in ("MISS_DISTANCE", "RELATIVE_SPEED", "OBJECT1_X", "OBJECT2_Z_DOT", "OBJECT1_CT_T", "OBJECT2_CNDOT_NDOT"):
+            assert back[key] == pytest.approx(cdm[key], rel=1e-3)       # 1e-3: the %.3E form of tiny covariance terms
+        assert back["OBJECT1_X"] == cdm["OBJECT1_X"] and back["MISS_DISTANCE"] == cdm["MISS_DISTANCE"]
+    frame = Event(cdms).to_dataframe()
+    assert frame.shape[0] == len(cdms) and "OBJECT2_CR_R" in frame.columns
