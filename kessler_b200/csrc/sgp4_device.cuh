@@ -763,7 +763,7 @@ struct FastView {
 // (the exact path is kept out of line on the device so that its registers do not count against the callers' hot path)
 template <typename Base>
 #if defined(__CUDACC__)
-__device__ __noinline__
+__host__ __device__ __noinline__
 #else
 inline
 #endif
