@@ -324,12 +324,13 @@ class Event:
             return pd.DataFrame()
         return pd.concat([c.to_dataframe() for c in self._cdms], ignore_index=True)
 
-    def save(self, directory, prefix="cdm"):
-        """Writes one KVN file per CDM: <directory>/<prefix>_<k>.cdm.kvn.txt; returns the paths."""
+    def save(self, directory, prefix="event_0", extension=".kvn"):
+        """Writes one KVN file per CDM, <directory>/<prefix>_<k><extension> -- the naming the reference's
+        EventDataset(cdms_dir=directory) groups into events (event.py:168-189: `(.*)_([0-9]+.kvn)`); returns the paths."""
         import os
         os.makedirs(directory, exist_ok=True)
         paths = []
         for k, c in enumerate(self._cdms):
-            paths.append(os.path.join(directory, "{}_{}.cdm.kvn.txt".format(prefix, k)))
+            paths.append(os.path.join(directory, "{}_{}{}".format(prefix, k, extension)))
             c.save(paths[-1])
         return paths

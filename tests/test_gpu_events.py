@@ -169,8 +169,8 @@ def test_generated_cdms_are_complete_and_survive_the_wire_format(setup, tmp_path
     res = ev_mod.generate_cdm_batch(model, batch, hits, seed=3)
     cdms = ev_mod.to_cdms(model, res, 0)
     assert len(cdms) >= 1
-    paths = Event(cdms).save(str(tmp_path / "event0"))
-    assert len(paths) == len(cdms)
+    paths = Event(cdms).save(str(tmp_path), prefix="event_7")
+    assert len(paths) == len(cdms) and paths[0].endswith("event_7_0.kvn")
     for cdm, path in zip(cdms, paths):
         assert cdm.validate() == []
         back = ConjunctionDataMessage.load(path)
