@@ -280,6 +280,24 @@ def feature_tensor(res):
     return feats, ptr
 
 
+def to_dataframe(res, event_id_offset=0):
+    """The CDM sequences of a generate_cdm_batch() result as one pandas frame, one row per issued CDM: `event_id`,
+    the CDM date strings `CREATION_DATE` / `TCA`, `COLLISION_PROBABILITY`, and the 62 numeric CDM fields of
+    LSTM_FEATURES under their CDM keys (what `EventDataset.to_dataframe()` holds for these columns in the reference,
+    event.py:422-428) -- built from the struct-of-arrays result, no CDM objects."""
+    import pandas as pd
+    feats, ptr = feature_tensor(res)
+    e_i, c_i = np.nonzero(res["issued"])
+    creation = [util.from_jd_to_cdm_datetime_str(util.from_mjd_to_jd(t)) for t in res["time_cdm"]]
+    tca = [util.from_jd_to_cdm_datetime_str(util.from_mjd_to_jd(t)) for t in res["tca_mjd"]]
+    cols = {"event_id": e_i + int(event_id_offset), "CREATION_DATE": [creation[i] for i in c_i], "TCA": [tca[e] for e in e_i],
+            "COLLISION_PROBABILITY": res["pc"][e_i, c_i]}
+    for k, name in enumerate(LSTM_FEATURES):
+        if not name.startswith("__"):
+            cols[name] = feats[:, k]
+    return pd.DataFrame(cols)
+
+
 _BATCH_KEYS = ("elems_t", "elems_c", "epoch_t", "epoch_c", "time_min", "i_min", "d_min", "i_conj", "d_conj")
 
 

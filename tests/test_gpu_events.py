@@ -182,3 +182,10 @@ def test_generated_cdms_are_complete_and_survive_the_wire_format(setup, tmp_path
         assert back["OBJECT1_X"] == cdm["OBJECT1_X"] and back["MISS_DISTANCE"] == cdm["MISS_DISTANCE"]
     frame = Event(cdms).to_dataframe()
     assert frame.shape[0] == len(cdms) and "OBJECT2_CR_R" in frame.columns
+    # ... and the frame built straight from the struct-of-arrays result holds the same rows for this event
+    big = ev_mod.to_dataframe(res)
+    assert len(big) == int(res["issued"].sum()) and set(big["event_id"]) == set(np.nonzero(res["issued"].any(axis=1))[0])
+    mine = big[big["event_id"] == 0].reset_index(drop=True)
+    assert len(mine) == len(cdms) and list(mine["TCA"]) == list(frame["TCA"]) and list(mine["CREATION_DATE"]) == list(frame["CREATION_DATE"])
+    for key in ("MISS_DISTANCE", "RELATIVE_VELOCITY_T", "OBJECT1_Y", "OBJECT2_CTDOT_N", "COLLISION_PROBABILITY"):
+        assert np.allclose(mine[key].to_numpy(dtype=np.float64), frame[key].to_numpy(dtype=np.float64), rtol=1e-12, atol=1e-9)
