@@ -11,3 +11,20 @@ from . import _native  # noqa: F401
 from ._native import KesslerCudaError  # noqa: F401
 
 __version__ = "0.1.0"
+
+# The names `import kessler` offers for this path (/root/reference/kessler/__init__.py:13-18), resolved on first use so
+# that importing the package stays cheap (no torch import for the ABI-only users).
+_LAZY = {"seed": ("util", "seed"), "ConjunctionDataMessage": ("cdm", "ConjunctionDataMessage"), "CDM": ("cdm", "CDM"),
+         "Event": ("cdm", "Event"), "GNSS": ("observation_model", "GNSS"), "Radar": ("observation_model", "Radar")}
+_SUBMODULES = ("model", "util", "cdm", "observation_model", "events", "montecarlo", "engine", "tle", "sgp4", "distributed",
+               "workloads", "stats", "ppl")
+
+
+def __getattr__(name):
+    import importlib
+    if name in _LAZY:
+        module, attr = _LAZY[name]
+        return getattr(importlib.import_module("." + module, __name__), attr)
+    if name in _SUBMODULES:
+        return importlib.import_module("." + name, __name__)
+    raise AttributeError("module {!r} has no attribute {!r}".format(__name__, name))

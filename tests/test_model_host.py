@@ -307,3 +307,15 @@ def test_cdm_kvn_wire_format_roundtrip(tmp_path):
     assert np.allclose(back.get_state_relative(), m.get_state_relative())
     frame = m.to_dataframe()
     assert frame.shape[0] == 1 and frame["OBJECT1_X"][0] == 7000.0 and "OBJECT2_CNDOT_NDOT" in frame.columns
+
+
+def test_package_level_names_of_the_reference():
+    """`import kessler` exposes seed, ConjunctionDataMessage / CDM, Event, GNSS, Radar, model, util
+    (/root/reference/kessler/__init__.py): the same names resolve on this package."""
+    import kessler_b200 as kb
+    from kessler_b200 import cdm, observation_model
+    assert kb.ConjunctionDataMessage is cdm.ConjunctionDataMessage is kb.CDM and kb.Event is cdm.Event
+    assert kb.GNSS is observation_model.GNSS and kb.Radar is observation_model.Radar
+    assert callable(kb.seed) and hasattr(kb.model, "Conjunction") and hasattr(kb.util, "from_cartesian_to_rtn")
+    with pytest.raises(AttributeError):
+        kb.no_such_name
