@@ -67,6 +67,25 @@ def _format_value(v):
     return str(v)
 
 
+# header keys that carry a CCSDS time string (cdm.py:53,193-203: day-of-year timestamps are converted, anything that is
+# not yyyy-mm-ddTHH:MM:SS.f afterwards is refused)
+_DATE_KEYS = ("CREATION_DATE",)
+
+
+def _ccsds_date(key, value):
+    text = str(value)
+    if text.count("T") != 1 or text.find("T") not in (8, 10):
+        raise RuntimeError("*** Error -- Invalid CCSDS time string: {}\nDate format not one of yyyy-mm-dd or yyyy-DDD.".format(text))
+    if text.find("T") == 8:      # yyyy-DDDTHH:MM:SS[.f][Z]
+        day = datetime.datetime(int(text[0:4]), 1, 1) + datetime.timedelta(int(text[5:8]) - 1)
+        text = "{:04d}-{:02d}-{:02d}T{}".format(day.year, day.month, day.day, text[9:].rstrip("Z"))
+    try:
+        datetime.datetime.strptime(text, "%Y-%m-%dT%H:%M:%S.%f")
+    except Exception as e:
+        raise RuntimeError("{} ({}) is not in the expected format.\n{}".format(key, text, e))
+    return text
+
+
 class ConjunctionDataMessage:
     def __init__(self, file_name=None, set_defaults=True):
         self._header = dict.fromkeys(HEADER_KEYS)
@@ -93,6 +112,8 @@ class ConjunctionDataMessage:
     def set_header(self, key, value):
         if key not in HEADER_KEYS:
             raise ValueError("Invalid key ({}) for header".format(key))
+        if key in _DATE_KEYS:
+            value = _ccsds_date(key, value)
         self._header[key] = value
 
     def set_relative_metadata(self, key, value):
@@ -279,9 +300,9 @@ class ConjunctionDataMessage:
                     cdm._meta[target]["OBJECT"] = value
                 elif target is None:
                     if key in HEADER_KEYS:
-                        cdm._header[key] = value
+                        cdm.set_header(key, value)
                     elif key in RELATIVE_KEYS:
-                        cdm._relative[key] = value
+                        cdm.set_relative_metadata(key, value)
                 else:
                     try:
                         cdm.set_object(target, key, value)

@@ -520,6 +520,15 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
                 for (int d = 16; d > 0; d >>= 1) cutoff = fmin(cutoff, __shfl_xor_sync(0xffffffffu, cutoff, d));
                 want_f = ksl::segment_want_f32(cutoff, best.conj_j == kNoIndexW, p.thr2);
             }
+            // The pilot only seeds the running MINIMUM.  A crossing it found must not close this lane's search for the
+            // FIRST crossing: "crossing seen -> later segments need not be visited for the threshold" is only valid
+            // while segments are visited in increasing order, and the pilot's segments are late ones.  They are
+            // visited again in their turn, so forgetting the pilot's crossing loses nothing.
+            if (pilot) {
+                best.conj_j = kNoIndexW;
+                best.conj_sq = 0.0;
+                want_f = ksl::segment_want_f32(cutoff, true, p.thr2);
+            }
             __syncwarp();
             if (lane == 31) {
 #pragma unroll

@@ -105,7 +105,7 @@ KSL_HD long long first_fine_of(long long k, double scale, long long n_in, long l
 // t0/t1 (c0/c1): target (chaser) position in km at coarse epochs k and min(k+1, last).
 KSL_HD double seg_sq(long long j, long long k, double scale, const double *t0, const double *t1, const double *c0,
                      const double *c1) {
-    double l = (double)j * scale - (double)k;
+    double l = add_rn(mul_rn((double)j, scale), -(double)k);   // torch rounds the product first: no contraction
     l = l < 0.0 ? 0.0 : l;
     l = l > 1.0 ? 1.0 : l;
     const double w0 = 1.0 - l;
@@ -189,8 +189,8 @@ KSL_HD void segment_search(long long k, long long last, double scale, long long 
         } else {
             const double cur = best.sq;
             const double slack = 1.0 + 1e-9 * fmax(a0, cur < INFINITY ? cur : 0.0);
-            const double la = fmin(fmax((double)ja * scale - (double)k, 0.0), 1.0);
-            const double lb = fmin(fmax((double)jb * scale - (double)k, 0.0), 1.0);
+            const double la = fmin(fmax(add_rn(mul_rn((double)ja, scale), -(double)k), 0.0), 1.0);
+            const double lb = fmin(fmax(add_rn(mul_rn((double)jb, scale), -(double)k), 0.0), 1.0);
             const double lv = (a2 > 0.0) ? fmin(fmax(-a1 / a2, la), lb) : la;
             const double qv = a0 + lv * (2.0 * a1 + a2 * lv);  // analytic minimum over the segment
             const bool may_min = !(qv > cur + slack);

@@ -831,11 +831,11 @@ KSL_HD int sgp4_position(const double *c, int stride, double t, double r[3], con
 // ---- util.upsample index arithmetic (torch upsample_linear1d, align_corners) ----
 // scale = (n_in-1)/(n_out-1) in FP64; the integer part goes through FLOAT32.
 KSL_HD void upsample_index(int64_t j, double scale, int64_t n_in, int64_t *i0, int64_t *i1, double *w0, double *w1) {
-    const double src = (double)j * scale;
+    const double src = mul_rn((double)j, scale);   // rounded product, as torch forms it (no contraction with the subtraction below)
     int64_t a = (int64_t)floorf((float)src);
     if (a > n_in - 1) a = n_in - 1;
     const int64_t b = (a + 1 < n_in) ? a + 1 : n_in - 1;
-    double l = src - (double)a;
+    double l = add_rn(src, -(double)a);
     l = l < 0.0 ? 0.0 : l;
     l = l > 1.0 ? 1.0 : l;
     *i0 = a;

@@ -678,8 +678,8 @@ class ConjunctionSimplified(Conjunction):
                 index_prior = Categorical(torch.tensor(range(len(self._tles))))
             tle_index = self._draw(f'{who}_sampled_index', index_prior)
             given_tle = self._tles[int(tle_index)]
-            if who == 't':
-                self._t_tle_name = getattr(given_tle, 'name', '')
+        if who == 't':
+            self._t_tle_name = getattr(given_tle, 'name', '') or ''
         tle = given_tle.copy()
         tle.update({'mean_anomaly': mean_anomaly})
         self._record_tle_sites(who, tle)
@@ -691,9 +691,21 @@ class ConjunctionSimplified(Conjunction):
         if given is not None:
             return super().sample_elements(who, n)
         ma = self._prior_dict['mean_anomaly_prior'].sample((n,)).to(torch.float64).numpy()
-        if who == 'c' and self._exclude_object_name is not None:
-            raise NotImplementedError("batched sampling with exclude_object_name: use get_conjunction(batch_size=0)")
         idx = Categorical(torch.tensor(range(len(self._tles)))).sample((n,)).numpy()
+        if who == 't':
+            self._batch_t_idx = idx if self._t_tle is None else None
+        elif self._exclude_object_name is not None:
+            # model.py:813-814, per draw: when the draw's TARGET carries the excluded name, the chaser index comes from
+            # Categorical(tensor(include_idxs)) (the reference hands the indices over as unnormalised probabilities and
+            # uses the sampled value as the index: kept as is)
+            t_idx = getattr(self, '_batch_t_idx', None)
+            if t_idx is not None and len(t_idx) == n:
+                t_excl = np.array([getattr(t, 'name', '').startswith(self._exclude_object_name) for t in self._tles])[t_idx]
+            else:
+                t_excl = np.full(n, getattr(self._t_tle, 'name', '').startswith(self._exclude_object_name))
+            if t_excl.any():
+                alt = Categorical(torch.tensor(self._include_idxs)).sample((n,)).numpy()
+                idx = np.where(t_excl, alt, idx)
         base = np.stack([t.elements() for t in self._tles], axis=1)[:, idx]
         deg = math.pi / 180.0
         base[5] = _round_decimals(ma / deg, 4) * deg

@@ -253,8 +253,13 @@ class TLE:
 
     # -- dsgp4 surface ------------------------------------------------------------------
     def copy(self):
+        """Same object state, verbatim: the public fields (which keep the caller's raw values after a dict
+        construction / update) AND the text-quantised SGP4 inputs (_no_kozai, _ecco, ... -- what propagates).
+        Re-deriving the latter from the public fields would drop the quantisation."""
         new = TLE.__new__(TLE)
-        new._set(dict(self._data), self.line1, self.line2, getattr(self, "name", None))
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = dict(v) if isinstance(v, dict) else (list(v) if isinstance(v, list) else v)
+        new._initialized = False
         return new
 
     def update(self, fields):

@@ -295,6 +295,50 @@ def test_screen_analytic_equals_brute_large(eng):
     perm = rng.permutation(n)
     c = _screen(eng, np.ascontiguousarray(elt[:, perm]), ept_a, np.ascontiguousarray(elc[:, perm]), epc_a, tc, len(times), 5e3, 0)
     assert np.array_equal(c["i_min"], a["i_min"][perm]) and np.array_equal(c["d_min"], a["d_min"][perm])
+    assert np.array_equal(c["i_conj"], a["i_conj"][perm])    # the first crossing must not depend on the batch order either
+    assert np.array_equal(c["d_conj"][both[perm]], a["d_conj"][perm][both[perm]])
+
+
+def test_screen_first_crossing_with_slow_relative_motion(eng):
+    """Two co-orbital objects ~1 km of relative motion per coarse step: the distance dips below the threshold once per
+    orbit from the start of the window while the global minimum lies at its END.  The warp kernel's pilot chunk (the
+    epochs around the previous trace's minimum, searched first) then sees a late crossing before the early ones: the
+    first crossing must still be the earliest (round-1 defect: a crossing found by the pilot closed the lane's search
+    for earlier ones).  Checked against enumeration in the same kernel, the CTA kernel and the oracle."""
+    from kessler_b200 import _native as NV
+    et, ept, _, _, s = common.golden_pair()
+    times = K.time_grid(s["time0"], 2.0, 172800)
+    tc = np.ascontiguousarray(times[::100])
+    n = 6000                                    # > 2368 resident warps: every warp sees a second / third trace
+    rng = np.random.default_rng(5)
+    elt = np.repeat(et[:, None], n, 1)
+    elc = elt.copy()
+    elc[1] += 3e-4 + rng.normal(size=n) * 2e-5
+    elc[5] += 4e-4 + rng.normal(size=n) * 3e-5
+    elc[0] *= 1 + 2e-7 * (1 + rng.normal(size=n) * 0.3)
+    ep = np.full(n, ept)
+    thr = 8250.0
+    warp = _screen(eng, elt, ep, elc, ep, tc, len(times), thr, NV.SCREEN_FORCE_WARP)
+    brute = _screen(eng, elt, ep, elc, ep, tc, len(times), thr, NV.SCREEN_FORCE_WARP | 1)
+    cta = _screen(eng, elt[:, :400].copy(), ep[:400], elc[:, :400].copy(), ep[:400], tc, len(times), thr, NV.SCREEN_FORCE_CTA)
+    for k in ("i_min", "i_conj", "d_min"):
+        assert np.array_equal(warp[k], brute[k]), k
+        assert np.array_equal(warp[k][:400], cta[k]), k
+    hit = brute["i_conj"] >= 0
+    assert np.array_equal(warp["d_conj"][hit], brute["d_conj"][hit]) and np.isnan(warp["d_conj"][~hit]).all()
+    # the case is the one described: most traces cross early and bottom out late
+    assert (hit & (brute["i_conj"] < brute["i_min"] - 50000)).sum() > n // 3
+    sub = np.arange(0, n, 500)
+    ref = C.screen(elt[:, sub].copy(), ep[sub], elc[:, sub].copy(), ep[sub], tc, len(times), thr)
+    assert np.array_equal(ref["i_min"], warp["i_min"][sub]) and np.array_equal(ref["i_conj"], warp["i_conj"][sub])
+    # permutation / split invariance of the first crossing
+    perm = rng.permutation(n)
+    p = _screen(eng, np.ascontiguousarray(elt[:, perm]), ep, np.ascontiguousarray(elc[:, perm]), ep, tc, len(times), thr,
+                NV.SCREEN_FORCE_WARP)
+    assert np.array_equal(p["i_conj"], warp["i_conj"][perm]) and np.array_equal(p["i_min"], warp["i_min"][perm])
+    h = n // 2
+    a = _screen(eng, elt[:, :h].copy(), ep[:h], elc[:, :h].copy(), ep[:h], tc, len(times), thr, NV.SCREEN_FORCE_WARP)
+    assert np.array_equal(a["i_conj"], warp["i_conj"][:h]) and np.array_equal(a["d_conj"][hit[:h]], warp["d_conj"][:h][hit[:h]])
 
 
 def test_screen_cta_and_warp_decompositions_agree(eng):
@@ -383,6 +427,7 @@ def test_screen_full_size_properties(eng):
     h = n // 2
     a = _screen(eng, np.ascontiguousarray(elt[:, :h]), ept[:h], np.ascontiguousarray(elc[:, :h]), epc[:h], tc, nf, 5e3, 0)
     assert np.array_equal(a["i_min"], full["i_min"][:h]) and np.array_equal(a["d_min"], full["d_min"][:h])
+    assert np.array_equal(a["i_conj"], full["i_conj"][:h])
     # summary = NumPy recount
     res = {k: torch.from_numpy(v).cuda() for k, v in full.items()}
     counts, moments = eng.screen_summary(res, 70.0)

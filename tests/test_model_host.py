@@ -319,3 +319,60 @@ def test_package_level_names_of_the_reference():
     assert callable(kb.seed) and hasattr(kb.model, "Conjunction") and hasattr(kb.util, "from_cartesian_to_rtn")
     with pytest.raises(AttributeError):
         kb.no_such_name
+
+
+def test_tle_copy_keeps_the_text_quantised_sgp4_inputs():
+    """dsgp4's copy rebuilds through TLE(dict); a copied / deep-copied TLE must propagate like the original."""
+    import copy as _copy
+    from kessler_b200.tle import TLE
+    t = TLE(list(common.PAIR_A[0]))
+    t.update({"mean_anomaly": 0.4932476473698829, "inclination": 0.69851234567, "eccentricity": 0.00080961234})
+    assert t.mean_anomaly == 0.4932476473698829 and t._mo != t.mean_anomaly          # raw field kept, SGP4 input quantised
+    for c in (t.copy(), _copy.deepcopy(t), TLE(t)):
+        assert np.array_equal(c.elements(), t.elements())
+        assert c.line1 == t.line1 and c.line2 == t.line2 and c.date_mjd == t.date_mjd
+    c = t.copy()
+    assert c.mean_anomaly == t.mean_anomaly and c._data is not t._data
+    c.update({"mean_anomaly": 1.0})
+    assert t._mo != c._mo and t.mean_anomaly == 0.4932476473698829                  # independent objects
+
+
+def test_conjunction_simplified_exclude_object_name_batched_sampling():
+    """model.py:813-816 per draw: a target carrying the excluded name draws its chaser index from
+    Categorical(tensor(include_idxs)); the batched sampler no longer refuses the option."""
+    import torch
+    from kessler_b200.model import ConjunctionSimplified
+    from kessler_b200.tle import TLE
+    el, ep = common.population_elems()
+    tles = []
+    for k in range(6):
+        t = TLE(list(common.PAIR_A[k % 2]))
+        t.name = ("STARLINK-%d" % k) if k in (1, 4) else ("OBJ-%d" % k)
+        tles.append(t)
+    m = ConjunctionSimplified(tles, exclude_object_name="STARLINK")
+    assert m._include_idxs == [0, 2, 3, 5]
+    torch.manual_seed(0)
+    raw_t, el_t, _ = m.sample_elements('t', 4000)
+    raw_c, el_c, _ = m.sample_elements('c', 4000)
+    ti, ci = raw_t['sampled_index'], raw_c['sampled_index']
+    assert ti.min() >= 1 and ti.max() == 5                 # Categorical(range(6)): index 0 has probability 0 (reference quirk)
+    excl = np.isin(ti, (1, 4))
+    assert excl.any() and (~excl).any()
+    # include_idxs = [0, 2, 3, 5] as probabilities: values in {1, 2, 3}; the unconditional prior reaches 4 and 5
+    assert set(np.unique(ci[excl])) <= {1, 2, 3} and ci[~excl].max() == 5
+    assert el_c.shape == (7, 4000)
+
+
+def test_cdm_header_dates_follow_the_reference():
+    """cdm.py:193-203: day-of-year CREATION_DATE converted, malformed refused."""
+    from kessler_b200.cdm import ConjunctionDataMessage
+    c = ConjunctionDataMessage()
+    c.set_header("CREATION_DATE", "2022-068T19:10:13.500")
+    assert c._header["CREATION_DATE"] == "2022-03-09T19:10:13.500"
+    c.set_header("CREATION_DATE", "2022-03-09T19:10:13.5")
+    with pytest.raises(RuntimeError):
+        c.set_header("CREATION_DATE", "09/03/2022 19:10")
+    with pytest.raises(RuntimeError):
+        c.set_header("CREATION_DATE", "2022-03-09T19:10:13")
+    with pytest.raises(ValueError):
+        c.set_header("NOT_A_KEY", 1)
