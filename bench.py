@@ -207,12 +207,10 @@ def run_ours(args):
     screen_ms = []
 
     def step(timed):
-        ct, it = engine.sgp4_init(d_el_t)
-        cc, ic = engine.sgp4_init(d_el_c)
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        res = engine.screen(ct, d_ep_t, cc, d_ep_c, d_tc, N_FINE, THR_M, mode, init_err_t=it, init_err_c=ic)
+        res = engine.screen_elems(d_el_t, d_ep_t, d_el_c, d_ep_c, d_tc, N_FINE, THR_M, mode)
         if timed:
             e1.record()
             screen_ms.append((e0, e1))

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define KSL_VERSION 100
+#define KSL_VERSION 200
 
 /* return codes */
 #define KSL_OK 0
@@ -145,13 +145,29 @@ int ksl_find_conjunction(const double *tr0, const double *tr1, int64_t n, int64_
  * enumeration of all n_fine points (first index on ties, NaN counts as the minimum),
  * whichever search mode is used; samples are independent (any split or order of the
  * batch gives the same per-sample results).
- * workspace: ksl_screen_ws(n_t, n, n_coarse) bytes of device memory. */
+ * workspace: ksl_screen_ws(n_t, n, n_coarse) bytes of device memory; required when n_t == 1 < n, optional
+ * otherwise (with it, groups of traces are handed to warps through an atomic counter -- tail balance when
+ * some traces cost more than others; without it, by static striding). */
 int64_t ksl_screen_ws(int64_t n_t, int64_t n, int64_t n_coarse);
 int ksl_screen(const double *consts_t, const double *epoch_t, const int32_t *init_err_t, int64_t n_t,
                const double *consts_c, const double *epoch_c, const int32_t *init_err_c, int64_t n,
                const double *times_coarse, int64_t n_coarse, int64_t n_fine, double thr_m, int mode,
                int64_t *i_min, double *d_min, int64_t *i_conj, double *d_conj, int32_t *err,
                void *workspace, void *stream);
+
+/* The same, from the SGP4 INPUTS instead of initialised records: elems_t SoA [7][n_t], elems_c SoA [7][n]
+ * (enum ksl_elem_index).  This is the fused form of model.py:574-613 -- dsgp4.initialize_tle (model.py:581,592)
+ * included: from 65536 traces per call on, sgp4init runs inside the trace kernel (one lane per record, straight
+ * into the warp's shared-memory copy of the record), so a trace reads its 2 x (7 + 1) doubles from HBM and nothing
+ * else; smaller batches and a shared target go through ksl_sgp4_init into the workspace.  Results are bit-identical
+ * to ksl_sgp4_init + ksl_screen (one body of machine code initialises records on both paths).
+ * workspace: ksl_screen_elems_ws(n_t, n, n_coarse) bytes, required. */
+int64_t ksl_screen_elems_ws(int64_t n_t, int64_t n, int64_t n_coarse);
+int ksl_screen_elems(const double *elems_t, const double *epoch_t, int64_t n_t,
+                     const double *elems_c, const double *epoch_c, int64_t n,
+                     const double *times_coarse, int64_t n_coarse, int64_t n_fine, double thr_m, int mode,
+                     int64_t *i_min, double *d_min, int64_t *i_conj, double *d_conj, int32_t *err,
+                     void *workspace, void *stream);
 
 /* counts (uint64 [KSL_SUM_NCOUNT]) and moments (double [KSL_SUM_NMOMENT]) over the
  * outputs of ksl_screen; deterministic (fixed reduction order); these are the

@@ -77,14 +77,26 @@ using ksl::kNoIndex;
 // ------------------------------------------------------------------------------------
 // K1  sgp4init: one thread per TLE record, SoA in, SoA out (all accesses coalesced)
 // ------------------------------------------------------------------------------------
+// sgp4init of one element set into a private fast record (the 36 public constants, then the derived products).
+// Out of line on purpose: (1) one body of machine code serves k_sgp4_init and the fused kernel's prologue, so the
+// two paths produce bit-identical records; (2) its registers do not count against the epoch loop.
+__device__ __noinline__ int sgp4_init_record(const double *el, double *rec) {
+    double e7[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) e7[k] = el[k];
+    return ksl::sgp4_init(e7, [&](int k, double v) { rec[k] = v; });
+}
+
 __global__ void __launch_bounds__(128) k_sgp4_init(const double *__restrict__ elems, long long n,
                                                    double *__restrict__ consts, int *__restrict__ err) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double el[7];
+    double el[7], rec[KSL_NCONST];
 #pragma unroll
     for (int k = 0; k < 7; ++k) el[k] = elems[k * n + i];
-    const int e = ksl::sgp4_init(el, [&](int k, double v) { consts[(long long)k * n + i] = v; });
+    const int e = sgp4_init_record(el, rec);
+#pragma unroll
+    for (int k = 0; k < KSL_NCONST; ++k) consts[(long long)k * n + i] = rec[k];
     if (err) err[i] = e;
 }
 
@@ -242,12 +254,15 @@ constexpr int kScreenThreads = KSL_SCREEN_THREADS;
 constexpr int kMaxGridInSmem = 6144;  // time grid staged in shared memory up to this many epochs
 
 struct ScreenParams {
-    const double *consts_t, *epoch_t;
+    const double *consts_t, *epoch_t;   // consts_*: initialised records SoA [KSL_NCONST][n_*] (k_screen, k_screen_warp<.., false>)
     const int *init_err_t;
     long long n_t;
     const double *consts_c, *epoch_c;
     const int *init_err_c;
     long long n;
+    const double *elems_t, *elems_c;    // SGP4 inputs SoA [7][n_*]: k_screen_warp<.., true> runs sgp4init itself
+    unsigned long long *counter;        // next group of traces to hand out (zeroed before the launch); NULL = static striding
+    int group;                          // traces per group, 1..kMaxGroup
     const double *times_coarse;
     long long n_coarse, n_fine;
     double scale, thr2;
@@ -400,16 +415,73 @@ __device__ __forceinline__ BestW best_compact(const Best &b) {
     return w;
 }
 
-template <bool kSharedTarget, int kMode>
+// Traces are handed to warps in GROUPS: the warp first fills its shared-memory slice with the group's fast records --
+// one lane per record, from the raw elements (kFromElems: sgp4init runs here, nothing but 2 x 7 doubles per trace is
+// read from HBM) or from records k_sgp4_init wrote --, then runs the traces of the group one after the other.  Groups
+// come from an atomic counter when the caller provides one (tail balance: a trace on the exact SGP4 path costs 4-5
+// fast ones), else by static striding.
+constexpr int kMaxGroup = 8;                    // traces per group with per-sample targets (2 x 8 records per warp)
+constexpr int kGroupRecs = 2 * kMaxGroup;       // records per warp slice; a shared target leaves all 16 to chasers
+constexpr int kRecEpoch = ksl::KSL_F_PAD;       // spare slots of a fast record: the record's epoch (MJD) ...
+constexpr int kRecErr = KSL_C_PAD;              // ... and its sgp4init error flag (as a double)
+
+// sgp4init flag of a record in the warp's slice (a shared target has none there: its flag is ScreenParams::target_err)
+template <bool kAbsent>
+__device__ __forceinline__ int record_err(const double *rec) { return kAbsent ? 0 : (int)rec[kRecErr]; }
+
+// The group's records into the warp's slice: chaser of trace q in slot q, target in slot kMaxGroup + q.  Called by the whole
+// warp; out of line so that the prologue's registers (sgp4init's arguments, the copy loops) stay out of the epoch loop's budget.
+template <bool kSharedTarget, bool kFromElems>
+__device__ __noinline__ void fill_group_records(const double *src_t, const double *epoch_t, const int *ierr_t, long long n_t,
+                                                const double *src_c, const double *epoch_c, const int *ierr_c, long long n,
+                                                long long s0, int cnt, double *s_rec) {
+    const int lane = threadIdx.x & 31;
+    const int nrec = kSharedTarget ? cnt : 2 * cnt;
+    if (!kFromElems) {
+        for (int r = 0; r < nrec; ++r) {
+            const bool tgt = r >= cnt;
+            const long long idx = s0 + (tgt ? r - cnt : r);
+            const double *src = tgt ? src_t : src_c;
+            const long long stride = tgt ? n_t : n;
+            double *rec = s_rec + (tgt ? kMaxGroup + (r - cnt) : r) * ksl::KSL_NFAST;
+            for (int q = lane; q < KSL_NCONST; q += 32) rec[q] = src[(long long)q * stride + idx];
+        }
+        __syncwarp();
+    }
+    if (lane < nrec) {
+        const bool tgt = lane >= cnt;
+        const int q = tgt ? lane - cnt : lane;
+        const long long idx = s0 + q;
+        double *rec = s_rec + (tgt ? kMaxGroup + q : q) * ksl::KSL_NFAST;
+        int ierr;
+        if (kFromElems) {
+            const double *src = tgt ? src_t : src_c;
+            const long long stride = tgt ? n_t : n;
+            double el[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) el[k] = src[(long long)k * stride + idx];
+            ierr = sgp4_init_record(el, rec);
+        } else {
+            const int *ie = tgt ? ierr_t : ierr_c;
+            ierr = ie ? ie[idx] : 0;
+        }
+        ksl::prepare_fast_record(rec, 1);
+        rec[kRecErr] = (double)ierr;
+        rec[kRecEpoch] = (tgt ? epoch_t : epoch_c)[idx];
+    }
+    __syncwarp();
+}
+
+template <bool kSharedTarget, int kMode, bool kFromElems>
 __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_warp(const ScreenParams p) {
-    extern __shared__ double s_times[];
-    __shared__ double s_c[kWarpsPerCta][2][ksl::KSL_NFAST];
+    extern __shared__ double s_dyn[];
     __shared__ __align__(16) double s_grid[2 * ksl::kGridPoints];          // ksl::kGridSinCos, for sincos_grid
     __shared__ double s_carry_all[kWarpsPerCta][8];   // lane 31's (target, chaser, float d) for the next chunk's lane 0
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool grid_in_smem = KSL_SCREEN_GRID_SMEM && p.n_coarse <= kMaxGridInSmem;
-    // first fine index of every coarse segment (+ n_fine at the end), behind the time grid in dynamic smem
+    // dynamic shared memory: [records: warps x kGroupRecs x KSL_NFAST][time grid][first fine index per segment (+ n_fine)]
+    double *s_times = s_dyn + kWarpsPerCta * kGroupRecs * ksl::KSL_NFAST;
     int *s_ja = reinterpret_cast<int *>(s_times + (grid_in_smem ? p.n_coarse : 0));
     if (grid_in_smem)
         for (long long k = tid; k < p.n_coarse; k += kScreenThreads) s_times[k] = p.times_coarse[k];
@@ -421,26 +493,39 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
     for (int q = tid; q < 2 * ksl::kGridPoints; q += kScreenThreads) s_grid[q] = ksl::kGridSinCos[q];
     __syncthreads();
 
-    double *s_ct = s_c[warp][0], *s_cc = s_c[warp][1], *s_carry = s_carry_all[warp];
+    double *s_rec = s_dyn + warp * kGroupRecs * ksl::KSL_NFAST;
+    double *s_carry = s_carry_all[warp];
     float *s_carry_f = reinterpret_cast<float *>(s_carry + 6);
-    const long long warps_total = (long long)gridDim.x * kWarpsPerCta;
     const int last = (int)p.n_coarse - 1;
-    int hint = -1;   // first epoch of the pilot chunk (see below); none for a warp's first trace
-    for (long long s = (long long)blockIdx.x * kWarpsPerCta + warp; s < p.n; s += warps_total) {
-        const long long it = (p.n_t == 1) ? 0 : s;
-        __syncwarp();
-        for (int q = lane; q < KSL_NCONST; q += 32) {
-            s_cc[q] = p.consts_c[(long long)q * p.n + s];
-            if (!kSharedTarget) s_ct[q] = p.consts_t[(long long)q * p.n_t + it];
+    // first epoch of the pilot chunk (see below): >= 0 use it, kNoHint none, otherwise -1 - epoch = known but the last two
+    // traces of this warp were unrelated
+    constexpr int kNoHint = -0x7fffffff - 1;
+    int hint = kNoHint;
+    unsigned int g_static = blockIdx.x * kWarpsPerCta + warp;   // (the launcher keeps the number of groups below 2^32)
+    for (;;) {
+        unsigned int g;
+        if (p.counter) {
+            unsigned int t = 0;
+            if (lane == 0) t = (unsigned int)atomicAdd(p.counter, 1ULL);
+            g = __shfl_sync(0xffffffffu, t, 0);
+        } else {
+            g = g_static;
+            g_static += gridDim.x * kWarpsPerCta;
         }
-        const double epoch_t = p.epoch_t[it], epoch_c = p.epoch_c[s];
-        const int ierr_t = p.init_err_t ? p.init_err_t[it] : 0, ierr_c = p.init_err_c ? p.init_err_c[s] : 0;
+        const long long s0 = (long long)g * p.group;
+        if (s0 >= p.n) break;
+        const int cnt = (p.n - s0 < p.group) ? (int)(p.n - s0) : p.group;
         __syncwarp();
-        if (lane == 0) ksl::prepare_fast_record(s_cc, 1);
-        if (!kSharedTarget && lane == 1) ksl::prepare_fast_record(s_ct, 1);
-        __syncwarp();
-        if ((ierr_t | ierr_c) & KSL_ERR_DEEPSPACE) {
+        fill_group_records<kSharedTarget, kFromElems>(kFromElems ? p.elems_t : p.consts_t, p.epoch_t, p.init_err_t, p.n_t,
+                                                      kFromElems ? p.elems_c : p.consts_c, p.epoch_c, p.init_err_c, p.n,
+                                                      (long long)g * p.group, cnt, s_rec);
+        for (int tq = 0; tq < cnt; ++tq) {
+        const double *s_cc = s_rec + tq * ksl::KSL_NFAST, *s_ct = s_rec + (kMaxGroup + tq) * ksl::KSL_NFAST;
+        const double epoch_c = s_cc[kRecEpoch], epoch_t = kSharedTarget ? 0.0 : s_ct[kRecEpoch];
+        if ((record_err<kSharedTarget>(s_ct) | record_err<false>(s_cc)) & KSL_ERR_DEEPSPACE) {
             if (lane == 0) {
+                const long long s = (long long)g * p.group + tq;
+                const int ierr_c = record_err<false>(s_cc), ierr_t = record_err<kSharedTarget>(s_ct);
                 p.i_min[s] = -1;
                 p.d_min[s] = NAN;
                 p.i_conj[s] = -1;
@@ -462,6 +547,8 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
         // minimum (`cutoff`) close to the final one and the skip test below then prunes nearly every other segment.  It only
         // changes the order in which segments are visited (the pilot's epochs are evaluated again in their turn),
         // never the result: arg-min and first crossing are order-independent (ties go to the smaller index).
+        // It is used once two consecutive traces of this warp bottomed out within 64 epochs of each other (related
+        // traces); for unrelated ones (a catalog) it would be a wasted chunk.
         for (int it = (hint >= 0) ? -1 : 0, base; (base = (it < 0) ? hint : it * 32) <= last; ++it) {
             const bool pilot = it < 0;
             k = base + lane;
@@ -554,14 +641,23 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
             best_merge(full, o);
         }
         if (lane == 0) {
+            const long long s = (long long)g * p.group + tq;
             ksl::best_result(full, p.i_min + s, p.d_min + s, p.i_conj + s, p.d_conj + s);
-            int et = e_t | ierr_t;
+            int et = e_t | record_err<kSharedTarget>(s_ct);
             if (kSharedTarget && p.target_err) et |= *p.target_err;
-            p.err[s] = et | ((e_c | ierr_c) << KSL_ERR_CHASER_SHIFT);
+            p.err[s] = et | ((e_c | record_err<false>(s_cc)) << KSL_ERR_CHASER_SHIFT);
         }
-        // next trace's pilot chunk: centred on the coarse segment of this trace's minimum
+        // next trace's pilot chunk: centred on the coarse segment of this trace's minimum -- if this trace and the one
+        // before it bottomed out within 64 epochs of each other
         const long long j_min = __shfl_sync(0xffffffffu, full.j, 0);
-        hint = (kMode == KSL_SCREEN_BRUTE || j_min == ksl::kNoIndex) ? -1 : max(0, (int)ksl::up_i0(j_min, p.scale, p.n_coarse) - 15);
+        if (kMode == KSL_SCREEN_BRUTE || j_min == ksl::kNoIndex) {
+            hint = kNoHint;
+        } else {
+            const int now = max(0, (int)ksl::up_i0(j_min, p.scale, p.n_coarse) - 15);
+            const int before = (hint >= 0) ? hint : -1 - hint;      // (kNoHint decodes to a huge epoch: unrelated)
+            hint = (abs(now - before) <= 64) ? now : -1 - now;
+        }
+        }   // traces of the group
     }
 }
 
@@ -1394,41 +1490,82 @@ int ksl_find_conjunction(const double *tr0, const double *tr1, int64_t n, int64_
     return KSL_OK;
 }
 
-int64_t ksl_screen_ws(int64_t n_t, int64_t n, int64_t n_coarse) {
-    (void)n;
-    (void)n_t;
-    return (int64_t)(sizeof(double) * 3 * (size_t)(n_coarse > 0 ? n_coarse : 1) + 256);
-}
+}  // extern "C" (the screen launcher is C++)
 
-int ksl_screen(const double *consts_t, const double *epoch_t, const int32_t *init_err_t, int64_t n_t,
-               const double *consts_c, const double *epoch_c, const int32_t *init_err_c, int64_t n,
-               const double *times_coarse, int64_t n_coarse, int64_t n_fine, double thr_m, int mode, int64_t *i_min,
-               double *d_min, int64_t *i_conj, double *d_conj, int32_t *err, void *workspace, void *stream) {
+namespace {
+// workspace of the screen entry points: [target positions 3 x n_coarse][group counter][shared-target error flag]
+// (+ for ksl_screen_elems below kFuseMinTraces: initialised records and flags of chasers and targets)
+constexpr long long kFuseMinTraces = 65536;   // from here on sgp4init runs inside the screen kernel (one lane per record)
+size_t screen_ws_core(int64_t n_coarse) { return sizeof(double) * 3 * (size_t)(n_coarse > 0 ? n_coarse : 1) + 256; }
+size_t pad256(size_t b) { return ((b + 255) / 256) * 256; }
+
+int screen_impl(const double *consts_t, const double *elems_t, const double *epoch_t, const int32_t *init_err_t, int64_t n_t,
+                const double *consts_c, const double *elems_c, const double *epoch_c, const int32_t *init_err_c, int64_t n,
+                const double *times_coarse, int64_t n_coarse, int64_t n_fine, double thr_m, int mode, int64_t *i_min,
+                double *d_min, int64_t *i_conj, double *d_conj, int32_t *err, void *workspace, void *stream, const char *who) {
     if (n < 0 || n_coarse <= 0 || n_fine <= 0 || (n_t != 1 && n_t != n))
-        return fail(KSL_E_ARG, "ksl_screen: need n >= 0, n_coarse > 0, n_fine > 0, n_t in {1, n}");
+        return fail(KSL_E_ARG, "%s: need n >= 0, n_coarse > 0, n_fine > 0, n_t in {1, n}", who);
     const int force = mode & (KSL_SCREEN_FORCE_CTA | KSL_SCREEN_FORCE_WARP);
     mode &= ~(KSL_SCREEN_FORCE_CTA | KSL_SCREEN_FORCE_WARP);
-    if (mode != KSL_SCREEN_ANALYTIC && mode != KSL_SCREEN_BRUTE) return fail(KSL_E_ARG, "ksl_screen: unknown mode %d", mode);
+    if (mode != KSL_SCREEN_ANALYTIC && mode != KSL_SCREEN_BRUTE) return fail(KSL_E_ARG, "%s: unknown mode %d", who, mode);
     if (n == 0) return KSL_OK;
-    if (!consts_t || !epoch_t || !consts_c || !epoch_c || !times_coarse || !i_min || !d_min || !i_conj || !d_conj || !err)
-        return fail(KSL_E_ARG, "ksl_screen: NULL pointer");
+    const bool from_elems_in = elems_c != nullptr;
+    if ((!from_elems_in && (!consts_t || !consts_c)) || (from_elems_in && !elems_t) || !epoch_t || !epoch_c || !times_coarse ||
+        !i_min || !d_min || !i_conj || !d_conj || !err)
+        return fail(KSL_E_ARG, "%s: NULL pointer", who);
     int sms = 0;
     int rc = sm_count(&sms);
     if (rc) return rc;
+    const bool shared = (n_t == 1 && n > 1);
+    // enough samples to give (three quarters of) the resident warps their own trace -> warp-per-trace kernel, else
+    // CTA-per-trace (measured crossover on B200: ~1700 of 2368 warps; one warp needs 0.7 ms for a default trace, a CTA 0.18 ms)
+    // (the warp kernel keeps 32-bit epoch / fine-grid indices)
+    const bool fits32 = n_coarse < 0x40000000LL && n_fine < 0x7fffffffLL;   // (chunk bases advance by 32 in an int)
+    const bool per_warp = fits32 && ((force & KSL_SCREEN_FORCE_WARP) ||
+                                     (!(force & KSL_SCREEN_FORCE_CTA) && 4 * n >= 3LL * sms * KSL_SCREEN_MIN_CTAS * kWarpsPerCta));
+    // sgp4init inside the warp kernel pays once a warp has whole groups of records to initialise (one lane each)
+    const bool fuse_init = from_elems_in && per_warp && n >= kFuseMinTraces;
+    char *ws = reinterpret_cast<char *>(workspace);
+    if ((shared || (from_elems_in && !fuse_init)) && !ws) return fail(KSL_E_NOMEM, "%s: workspace required", who);
+    double *pos = reinterpret_cast<double *>(ws);
+    unsigned long long *counter = ws ? reinterpret_cast<unsigned long long *>(ws + sizeof(double) * 3 * (size_t)n_coarse) : nullptr;
+    int *terr = ws ? reinterpret_cast<int *>(counter + 1) : nullptr;
+    if (from_elems_in && (!fuse_init || shared)) {
+        // records through k_sgp4_init: all of them below the fusing size, the shared target's single one always
+        char *q = ws + screen_ws_core(n_coarse);
+        double *ct = reinterpret_cast<double *>(q);
+        q += pad256(sizeof(double) * KSL_NCONST * (size_t)n_t);
+        int32_t *it = reinterpret_cast<int32_t *>(q);
+        q += pad256(sizeof(int32_t) * (size_t)n_t);
+        if (shared || !fuse_init) {
+            rc = ksl_sgp4_init(elems_t, n_t, ct, it, stream);
+            if (rc) return rc;
+            consts_t = ct;
+            init_err_t = it;
+        }
+        if (!fuse_init) {
+            double *cc = reinterpret_cast<double *>(q);
+            q += pad256(sizeof(double) * KSL_NCONST * (size_t)n);
+            int32_t *ic = reinterpret_cast<int32_t *>(q);
+            rc = ksl_sgp4_init(elems_c, n, cc, ic, stream);
+            if (rc) return rc;
+            consts_c = cc;
+            init_err_c = ic;
+        }
+    }
     ScreenParams p;
     p.consts_t = consts_t; p.epoch_t = epoch_t; p.init_err_t = init_err_t; p.n_t = n_t;
     p.consts_c = consts_c; p.epoch_c = epoch_c; p.init_err_c = init_err_c; p.n = n;
+    p.elems_t = elems_t; p.elems_c = elems_c;
     p.times_coarse = times_coarse; p.n_coarse = n_coarse; p.n_fine = n_fine;
     p.scale = up_scale(n_coarse, n_fine);
     p.thr2 = thr_m * thr_m;
     p.target_pos = nullptr; p.target_err = nullptr;
     p.i_min = reinterpret_cast<long long *>(i_min); p.i_conj = reinterpret_cast<long long *>(i_conj);
     p.d_min = d_min; p.d_conj = d_conj; p.err = err;
-    const bool shared = (n_t == 1 && n > 1);
+    p.counter = nullptr;
+    p.group = 1;
     if (shared) {
-        if (!workspace) return fail(KSL_E_NOMEM, "ksl_screen: workspace required when the target is shared");
-        double *pos = reinterpret_cast<double *>(workspace);
-        int *terr = reinterpret_cast<int *>(pos + 3 * n_coarse);
         KSL_CUDA(cudaMemsetAsync(terr, 0, sizeof(int), S(stream)));
         k_target_positions<<<(unsigned)((n_coarse + 127) / 128), 128, 0, S(stream)>>>(consts_t, epoch_t, times_coarse, n_coarse,
                                                                                        pos, terr);
@@ -1436,21 +1573,31 @@ int ksl_screen(const double *consts_t, const double *epoch_t, const int32_t *ini
         p.target_pos = pos;
         p.target_err = terr;
     }
-    const size_t dyn = ((KSL_SCREEN_GRID_SMEM && n_coarse <= kMaxGridInSmem) ? sizeof(double) * (size_t)n_coarse : 0) +
-                       ((n_coarse <= kMaxGridInSmem && n_fine < 0x7fffffffLL) ? sizeof(int) * (size_t)(n_coarse + 2) : 0);
-    // enough samples to give (three quarters of) the resident warps their own trace -> warp-per-trace kernel, else
-    // CTA-per-trace (measured crossover on B200: ~1700 of 2368 warps; one warp needs 0.7 ms for a default trace, a CTA 0.18 ms)
-    // (the warp kernel keeps 32-bit epoch / fine-grid indices)
-    const bool fits32 = n_coarse < 0x40000000LL && n_fine < 0x7fffffffLL;   // (chunk bases advance by 32 in an int)
-    const bool per_warp = fits32 && ((force & KSL_SCREEN_FORCE_WARP) ||
-                                     (!(force & KSL_SCREEN_FORCE_CTA) && 4 * n >= 3LL * sms * KSL_SCREEN_MIN_CTAS * kWarpsPerCta));
+    const size_t dyn_grid = ((KSL_SCREEN_GRID_SMEM && n_coarse <= kMaxGridInSmem) ? sizeof(double) * (size_t)n_coarse : 0) +
+                            ((n_coarse <= kMaxGridInSmem && n_fine < 0x7fffffffLL) ? sizeof(int) * (size_t)(n_coarse + 2) : 0);
+    const size_t dyn = dyn_grid + (per_warp ? sizeof(double) * kWarpsPerCta * kGroupRecs * ksl::KSL_NFAST : 0);
     long long grid = (long long)sms * KSL_SCREEN_MIN_CTAS;
     if (!per_warp && grid > n) grid = n;
+    if (per_warp) {
+        // group size: as large as the per-warp record slice allows once every warp still gets >= 8 groups
+        const long long warps_total = grid * kWarpsPerCta;
+        long long g = n / (warps_total * 8);
+        const long long gmax = shared ? kGroupRecs : kMaxGroup;
+        p.group = (int)(g < 1 ? 1 : (g > gmax ? gmax : g));
+        if (fuse_init && p.group < 4) p.group = 4;
+        if (counter) {
+            KSL_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), S(stream)));
+            p.counter = counter;
+        }
+    }
 #define KSL_SCREEN_LAUNCH(SH, MD)                                                                       \
     do {                                                                                                \
-        if (per_warp) {                                                                                 \
-            KSL_CUDA(cudaFuncSetAttribute(k_screen_warp<SH, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-            k_screen_warp<SH, MD><<<(unsigned)grid, kScreenThreads, dyn, S(stream)>>>(p);               \
+        if (per_warp && fuse_init) {                                                                    \
+            KSL_CUDA(cudaFuncSetAttribute(k_screen_warp<SH, MD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+            k_screen_warp<SH, MD, true><<<(unsigned)grid, kScreenThreads, dyn, S(stream)>>>(p);         \
+        } else if (per_warp) {                                                                          \
+            KSL_CUDA(cudaFuncSetAttribute(k_screen_warp<SH, MD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+            k_screen_warp<SH, MD, false><<<(unsigned)grid, kScreenThreads, dyn, S(stream)>>>(p);        \
         } else {                                                                                        \
             KSL_CUDA(cudaFuncSetAttribute(k_screen<SH, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
             k_screen<SH, MD><<<(unsigned)grid, kScreenThreads, dyn, S(stream)>>>(p);                    \
@@ -1466,6 +1613,39 @@ int ksl_screen(const double *consts_t, const double *epoch_t, const int32_t *ini
 #undef KSL_SCREEN_LAUNCH
     KSL_LAUNCH_CHECK();
     return KSL_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int64_t ksl_screen_ws(int64_t n_t, int64_t n, int64_t n_coarse) {
+    (void)n;
+    (void)n_t;
+    return (int64_t)screen_ws_core(n_coarse);
+}
+
+int ksl_screen(const double *consts_t, const double *epoch_t, const int32_t *init_err_t, int64_t n_t,
+               const double *consts_c, const double *epoch_c, const int32_t *init_err_c, int64_t n,
+               const double *times_coarse, int64_t n_coarse, int64_t n_fine, double thr_m, int mode, int64_t *i_min,
+               double *d_min, int64_t *i_conj, double *d_conj, int32_t *err, void *workspace, void *stream) {
+    return screen_impl(consts_t, nullptr, epoch_t, init_err_t, n_t, consts_c, nullptr, epoch_c, init_err_c, n, times_coarse, n_coarse,
+                       n_fine, thr_m, mode, i_min, d_min, i_conj, d_conj, err, workspace, stream, "ksl_screen");
+}
+
+int64_t ksl_screen_elems_ws(int64_t n_t, int64_t n, int64_t n_coarse) {
+    size_t b = screen_ws_core(n_coarse);
+    const size_t nt = (size_t)(n_t > 0 ? n_t : 1), nn = (size_t)(n > 0 ? n : 1);
+    b += pad256(sizeof(double) * KSL_NCONST * nt) + pad256(sizeof(int32_t) * nt);
+    if (n < kFuseMinTraces) b += pad256(sizeof(double) * KSL_NCONST * nn) + pad256(sizeof(int32_t) * nn);
+    return (int64_t)b;
+}
+
+int ksl_screen_elems(const double *elems_t, const double *epoch_t, int64_t n_t, const double *elems_c, const double *epoch_c,
+                     int64_t n, const double *times_coarse, int64_t n_coarse, int64_t n_fine, double thr_m, int mode,
+                     int64_t *i_min, double *d_min, int64_t *i_conj, double *d_conj, int32_t *err, void *workspace, void *stream) {
+    if (n > 0 && (!elems_t || !elems_c)) return fail(KSL_E_ARG, "ksl_screen_elems: NULL pointer");
+    return screen_impl(nullptr, elems_t, epoch_t, nullptr, n_t, nullptr, elems_c, epoch_c, nullptr, n, times_coarse, n_coarse, n_fine,
+                       thr_m, mode, i_min, d_min, i_conj, d_conj, err, workspace, stream, "ksl_screen_elems");
 }
 
 int64_t ksl_screen_summary_ws(int64_t n) {
@@ -1714,13 +1894,14 @@ int ksl_fp64_peak_kernel(int blocks, int threads, int64_t iters, double *sink, v
 // ---- end-to-end entry point: host buffers in, host buffers out ----------------------
 namespace {
 struct HostCache {
+    std::mutex mu;            // one call at a time PER DEVICE (the arena and the two streams are per device);
+                              // calls on different devices run concurrently
     char *arena = nullptr;
     size_t cap = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
 };
 HostCache g_cache[64];
-std::mutex g_cache_mu;
 
 struct Bump {
     char *base;
@@ -1732,40 +1913,13 @@ struct Bump {
         return p;
     }
 };
-}  // namespace
 
-extern "C" int ksl_host_cache_free(void) {
-    std::lock_guard<std::mutex> lk(g_cache_mu);
-    int cur = 0;
-    cudaGetDevice(&cur);
-    for (int d = 0; d < 64; ++d) {
-        if (!g_cache[d].arena && !g_cache[d].stream) continue;
-        cudaSetDevice(d);
-        if (g_cache[d].arena) cudaFree(g_cache[d].arena);
-        if (g_cache[d].stream) cudaStreamDestroy(g_cache[d].stream);
-        if (g_cache[d].stream2) cudaStreamDestroy(g_cache[d].stream2);
-        if (g_cache[d].ev_ready) cudaEventDestroy(g_cache[d].ev_ready);
-        if (g_cache[d].ev_done) cudaEventDestroy(g_cache[d].ev_done);
-        g_cache[d] = HostCache();
-    }
-    cudaSetDevice(cur);
-    return KSL_OK;
-}
-
-extern "C" int ksl_screen_host(int device, const double *elems_t, const double *epoch_t, int64_t n_t, const double *elems_c,
-                               const double *epoch_c, int64_t n, const double *times_coarse, int64_t n_coarse,
-                               int64_t n_fine, double thr_m, int mode, double collision_thr_m, int64_t *i_min,
-                               double *d_min, int64_t *i_conj, double *d_conj, int32_t *err, uint64_t *summary_counts,
-                               double *summary_moments) {
-    if (device < 0 || device >= 64) return fail(KSL_E_ARG, "ksl_screen_host: bad device %d", device);
-    if (n < 0 || n_coarse <= 0 || n_fine <= 0 || (n_t != 1 && n_t != n)) return fail(KSL_E_ARG, "ksl_screen_host: bad sizes");
-    if (n == 0) return KSL_OK;
-    if (!elems_t || !epoch_t || !elems_c || !epoch_c || !times_coarse || !i_min || !d_min || !i_conj || !d_conj)
-        return fail(KSL_E_ARG, "ksl_screen_host: NULL pointer");
-    if (ksl_device_count() <= device) return fail(KSL_E_CUDA, "ksl_screen_host: CUDA device %d not available (no CPU fallback)", device);
-    std::lock_guard<std::mutex> lk(g_cache_mu);
-    KSL_CUDA(cudaSetDevice(device));
-    HostCache &hc = g_cache[device];
+// the body of ksl_screen_host once the device is selected and its cache locked; any error leaves work in flight,
+// the caller drains both streams before it returns
+int screen_host_locked(HostCache &hc, const double *elems_t, const double *epoch_t, int64_t n_t, const double *elems_c,
+                       const double *epoch_c, int64_t n, const double *times_coarse, int64_t n_coarse, int64_t n_fine,
+                       double thr_m, int mode, double collision_thr_m, int64_t *i_min, double *d_min, int64_t *i_conj,
+                       double *d_conj, int32_t *err, uint64_t *summary_counts, double *summary_moments) {
     if (!hc.stream) {
         KSL_CUDA(cudaStreamCreateWithFlags(&hc.stream, cudaStreamNonBlocking));
         KSL_CUDA(cudaStreamCreateWithFlags(&hc.stream2, cudaStreamNonBlocking));
@@ -1773,7 +1927,8 @@ extern "C" int ksl_screen_host(int device, const double *elems_t, const double *
         KSL_CUDA(cudaEventCreateWithFlags(&hc.ev_done, cudaEventDisableTiming));
     }
     // Large batches go through in chunks on two streams: the host->device copy of chunk j+1 and the device->host copy of
-    // chunk j-1 overlap the kernels of chunk j (samples are independent, so chunking cannot change a result).
+    // chunk j-1 overlap the kernels of chunk j (samples are independent, so chunking cannot change a result).  sgp4init
+    // runs inside the screen kernel, so what is staged per chunk is 2 x 8 doubles per trace and nothing else.
     const bool shared = (n_t == 1);
     const int nchunk = (n >= (1 << 18)) ? 4 : 1;
     const size_t un = (size_t)n, unc = (size_t)n_coarse;
@@ -1781,9 +1936,8 @@ extern "C" int ksl_screen_host(int device, const double *elems_t, const double *
     const int nslot = nchunk > 1 ? 2 : 1;
     const size_t mt = shared ? 1 : m;
     auto pad = [](size_t b) { return ((b + 255) / 256) * 256; };
-    const size_t ws_bytes = (size_t)ksl_screen_ws(shared ? 1 : (int64_t)m, (int64_t)m, n_coarse);
-    const size_t slot_bytes = pad(8 * 7 * m) + pad(8 * m) + pad(8 * KSL_NCONST * m) + pad(4 * m) +
-                              pad(8 * 7 * mt) + pad(8 * mt) + pad(8 * KSL_NCONST * mt) + pad(4 * mt) + pad(ws_bytes);
+    const size_t ws_bytes = (size_t)ksl_screen_elems_ws((int64_t)mt, (int64_t)m, n_coarse);
+    const size_t slot_bytes = pad(8 * 7 * m) + pad(8 * m) + pad(8 * 7 * mt) + pad(8 * mt) + pad(ws_bytes);
     const size_t need = pad(8 * unc) + 4 * pad(8 * un) + pad(4 * un) + (size_t)nslot * slot_bytes +
                         pad((size_t)ksl_screen_summary_ws(n)) + pad(8 * KSL_SUM_NCOUNT) + pad(8 * KSL_SUM_NMOMENT) + 4096;
     if (hc.cap < need) {
@@ -1799,15 +1953,12 @@ extern "C" int ksl_screen_host(int device, const double *elems_t, const double *
     double *d_dmin = b.take<double>(un), *d_dconj = b.take<double>(un);
     int32_t *d_err = b.take<int32_t>(un);
     struct Slot {
-        double *el_c, *ep_c, *consts_c, *el_t, *ep_t, *consts_t;
-        int32_t *ierr_c, *ierr_t;
+        double *el_c, *ep_c, *el_t, *ep_t;
         void *ws;
     } slot[2];
     for (int q = 0; q < nslot; ++q) {
-        slot[q].el_c = b.take<double>(7 * m); slot[q].ep_c = b.take<double>(m); slot[q].consts_c = b.take<double>(KSL_NCONST * m);
-        slot[q].ierr_c = b.take<int32_t>(m);
-        slot[q].el_t = b.take<double>(7 * mt); slot[q].ep_t = b.take<double>(mt); slot[q].consts_t = b.take<double>(KSL_NCONST * mt);
-        slot[q].ierr_t = b.take<int32_t>(mt);
+        slot[q].el_c = b.take<double>(7 * m); slot[q].ep_c = b.take<double>(m);
+        slot[q].el_t = b.take<double>(7 * mt); slot[q].ep_t = b.take<double>(mt);
         slot[q].ws = b.take<char>(ws_bytes);
     }
     void *d_sws = b.take<char>((size_t)ksl_screen_summary_ws(n));
@@ -1834,12 +1985,8 @@ extern "C" int ksl_screen_host(int device, const double *elems_t, const double *
             KSL_CUDA(cudaMemcpy2DAsync(sl.el_t, 8 * len, elems_t + off, 8 * un, 8 * len, 7, cudaMemcpyHostToDevice, st));
             KSL_CUDA(cudaMemcpyAsync(sl.ep_t, epoch_t + off, 8 * len, cudaMemcpyHostToDevice, st));
         }
-        int rc = ksl_sgp4_init(sl.el_t, (int64_t)lt, sl.consts_t, sl.ierr_t, st);
-        if (rc) return rc;
-        rc = ksl_sgp4_init(sl.el_c, (int64_t)len, sl.consts_c, sl.ierr_c, st);
-        if (rc) return rc;
-        rc = ksl_screen(sl.consts_t, sl.ep_t, sl.ierr_t, (int64_t)lt, sl.consts_c, sl.ep_c, sl.ierr_c, (int64_t)len, d_times, n_coarse,
-                        n_fine, thr_m, mode, d_imin + off, d_dmin + off, d_iconj + off, d_dconj + off, d_err + off, sl.ws, st);
+        const int rc = ksl_screen_elems(sl.el_t, sl.ep_t, (int64_t)lt, sl.el_c, sl.ep_c, (int64_t)len, d_times, n_coarse, n_fine, thr_m,
+                                        mode, d_imin + off, d_dmin + off, d_iconj + off, d_dconj + off, d_err + off, sl.ws, st);
         if (rc) return rc;
         KSL_CUDA(cudaMemcpyAsync(i_min + off, d_imin + off, 8 * len, cudaMemcpyDeviceToHost, st));
         KSL_CUDA(cudaMemcpyAsync(d_min + off, d_dmin + off, 8 * len, cudaMemcpyDeviceToHost, st));
@@ -1852,11 +1999,60 @@ extern "C" int ksl_screen_host(int device, const double *elems_t, const double *
         KSL_CUDA(cudaStreamWaitEvent(streams[0], hc.ev_done, 0));
     }
     if (summary_counts || summary_moments) {
-        int rc = ksl_screen_summary(d_iconj, d_dmin, d_err, n, collision_thr_m, d_counts, d_mom, d_sws, streams[0]);
+        const int rc = ksl_screen_summary(d_iconj, d_dmin, d_err, n, collision_thr_m, d_counts, d_mom, d_sws, streams[0]);
         if (rc) return rc;
         if (summary_counts) KSL_CUDA(cudaMemcpyAsync(summary_counts, d_counts, 8 * KSL_SUM_NCOUNT, cudaMemcpyDeviceToHost, streams[0]));
         if (summary_moments) KSL_CUDA(cudaMemcpyAsync(summary_moments, d_mom, 8 * KSL_SUM_NMOMENT, cudaMemcpyDeviceToHost, streams[0]));
     }
-    KSL_CUDA(cudaStreamSynchronize(streams[0]));
     return KSL_OK;
+}
+}  // namespace
+
+extern "C" int ksl_host_cache_free(void) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 64; ++d) {
+        std::lock_guard<std::mutex> lk(g_cache[d].mu);
+        HostCache &hc = g_cache[d];
+        if (!hc.arena && !hc.stream) continue;
+        cudaSetDevice(d);
+        if (hc.arena) cudaFree(hc.arena);
+        if (hc.stream) cudaStreamDestroy(hc.stream);
+        if (hc.stream2) cudaStreamDestroy(hc.stream2);
+        if (hc.ev_ready) cudaEventDestroy(hc.ev_ready);
+        if (hc.ev_done) cudaEventDestroy(hc.ev_done);
+        hc.arena = nullptr; hc.cap = 0;
+        hc.stream = hc.stream2 = nullptr;
+        hc.ev_ready = hc.ev_done = nullptr;
+    }
+    cudaSetDevice(cur);
+    return KSL_OK;
+}
+
+extern "C" int ksl_screen_host(int device, const double *elems_t, const double *epoch_t, int64_t n_t, const double *elems_c,
+                               const double *epoch_c, int64_t n, const double *times_coarse, int64_t n_coarse,
+                               int64_t n_fine, double thr_m, int mode, double collision_thr_m, int64_t *i_min,
+                               double *d_min, int64_t *i_conj, double *d_conj, int32_t *err, uint64_t *summary_counts,
+                               double *summary_moments) {
+    if (device < 0 || device >= 64) return fail(KSL_E_ARG, "ksl_screen_host: bad device %d", device);
+    if (n < 0 || n_coarse <= 0 || n_fine <= 0 || (n_t != 1 && n_t != n)) return fail(KSL_E_ARG, "ksl_screen_host: bad sizes");
+    if (n == 0) return KSL_OK;
+    if (!elems_t || !epoch_t || !elems_c || !epoch_c || !times_coarse || !i_min || !d_min || !i_conj || !d_conj)
+        return fail(KSL_E_ARG, "ksl_screen_host: NULL pointer");
+    if (ksl_device_count() <= device) return fail(KSL_E_CUDA, "ksl_screen_host: CUDA device %d not available (no CPU fallback)", device);
+    HostCache &hc = g_cache[device];
+    std::lock_guard<std::mutex> lk(hc.mu);   // per device: a process driving 8 GPUs from 8 threads is not serialised
+    int prev = 0;
+    KSL_CUDA(cudaGetDevice(&prev));          // the current device is per host thread
+    KSL_CUDA(cudaSetDevice(device));
+    int rc = screen_host_locked(hc, elems_t, epoch_t, n_t, elems_c, epoch_c, n, times_coarse, n_coarse, n_fine, thr_m, mode,
+                                collision_thr_m, i_min, d_min, i_conj, d_conj, err, summary_counts, summary_moments);
+    // success or not, nothing of this call may still be in flight when the arena becomes reusable and the caller's
+    // buffers are handed back
+    const cudaError_t e0 = hc.stream ? cudaStreamSynchronize(hc.stream) : cudaSuccess;
+    const cudaError_t e1 = hc.stream2 ? cudaStreamSynchronize(hc.stream2) : cudaSuccess;
+    if (rc == KSL_OK && (e0 != cudaSuccess || e1 != cudaSuccess))
+        rc = fail(KSL_E_CUDA, "ksl_screen_host: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    cudaSetDevice(prev);
+    return rc;
 }

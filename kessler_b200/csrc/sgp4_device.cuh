@@ -735,7 +735,7 @@ KSL_HD void prepare_fast_record(double *c, int stride) {
     at(KSL_F_KSU) = -0.125 * kJ2 * at(KSL_C_X7THM1);
     at(KSL_F_KNODE) = 0.75 * kJ2 * at(KSL_C_COSIO);
     at(KSL_F_KINC) = 0.75 * kJ2 * at(KSL_C_COSIO) * at(KSL_C_SINIO);
-    at(KSL_F_PAD) = 0.0;
+    // KSL_F_PAD is the caller's (the warp kernel keeps the record's epoch there)
 }
 
 // A record that lives only as its 36 public constants (global memory, registers) seen as a fast record: the derived

@@ -131,6 +131,29 @@ def screen(consts_t, epoch_t, consts_c, epoch_c, times_coarse, n_fine, thr_m, mo
     return out
 
 
+def screen_elems(elems_t, epoch_t, elems_c, epoch_c, times_coarse, n_fine, thr_m, mode=N.SCREEN_ANALYTIC):
+    """The fused trace from the SGP4 inputs (sgp4init included): elems_t [7, n_t], elems_c [7, n] device tensors.
+    Returns dict(i_min, d_min, i_conj, d_conj, err) of device tensors [n]."""
+    dev = _dev()
+    elems_t, elems_c = _cf64(elems_t, dev), _cf64(elems_c, dev)
+    if elems_t.dim() == 1:
+        elems_t = elems_t.reshape(7, 1)
+    epoch_t = _cf64(epoch_t, dev).reshape(-1)
+    epoch_c = _cf64(epoch_c, dev).reshape(-1)
+    times_coarse = _cf64(times_coarse, dev)
+    n_t, n = elems_t.shape[1], elems_c.shape[1]
+    assert elems_t.shape[0] == 7 and elems_c.shape[0] == 7 and epoch_t.numel() == n_t and epoch_c.numel() == n and n_t in (1, n)
+    out = dict(i_min=torch.empty(n, dtype=torch.int64, device=dev), d_min=torch.empty(n, dtype=F64, device=dev),
+               i_conj=torch.empty(n, dtype=torch.int64, device=dev), d_conj=torch.empty(n, dtype=F64, device=dev),
+               err=torch.empty(n, dtype=torch.int32, device=dev))
+    n_coarse = times_coarse.numel()
+    ws = torch.empty(int(N.lib().ksl_screen_elems_ws(n_t, n, n_coarse)), dtype=torch.uint8, device=dev)
+    N.check(N.lib().ksl_screen_elems(ptr(elems_t), ptr(epoch_t), n_t, ptr(elems_c), ptr(epoch_c), n, ptr(times_coarse), n_coarse,
+                                     int(n_fine), float(thr_m), int(mode), ptr(out["i_min"]), ptr(out["d_min"]), ptr(out["i_conj"]),
+                                     ptr(out["d_conj"]), ptr(out["err"]), ptr(ws), stream_ptr()), "ksl_screen_elems")
+    return out
+
+
 def screen_summary(res, collision_thr_m):
     """res = dict from screen(); returns (counts uint64-as-int64 [8], moments f64 [4]) device tensors."""
     dev = _dev()

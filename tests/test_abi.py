@@ -33,7 +33,7 @@ def test_exports_every_declared_symbol():
 
 def test_metadata_calls_and_sm100a_cubin():
     lib = N.lib()
-    assert lib.ksl_version() == 100
+    assert lib.ksl_version() == 200
     assert lib.ksl_nconst() == N.NCONST == 36
     assert lib.ksl_device_count() >= 0
     out = os.popen(f"cuobjdump -lelf {N.LIB_PATH} 2>/dev/null").read()

@@ -437,6 +437,64 @@ def test_screen_full_size_properties(eng):
     assert moments[1] == pytest.approx(full["d_min"].sum(), rel=1e-12)
 
 
+def test_screen_elems_fused_init_is_bit_identical(eng):
+    """ksl_screen_elems (sgp4init inside the trace kernel from 65536 traces on, through ksl_sgp4_init below) returns
+    exactly what ksl_sgp4_init + ksl_screen return: every output bit-equal, with per-sample and shared targets, a
+    ragged last group, deep-space / decayed / non-finite records in the batch, and static as well as counter-driven
+    group assignment (ksl_screen without workspace is not reachable from the engine, so the latter is the default)."""
+    from kessler_b200 import _native as NV
+    elt, ept, elc, epc, times, _ = _golden_batch(3000, 23)
+    tc = np.ascontiguousarray(times[::100][:301])
+    nf = 30001
+    cat = common.synthetic_catalog(4096, seed=31)
+    for n in (65536 + 3, 70001, 2000):
+        rep = lambda a: np.ascontiguousarray(np.tile(a, (1, n // a.shape[1] + 1))[:, :n])
+        elt_b, elc_b = rep(elt), rep(elc)
+        elc_b[:, 1000:1000 + min(n - 1000, 4096)] = cat[:, :min(n - 1000, 4096)]      # refused / decaying / exact-path records
+        elt_b[:, 500:600] = cat[:, 100:200]
+        ept_b, epc_b = np.full(n, ept[0]), np.full(n, epc[0])
+        for shared in (False, True):
+            et, ep = (elt_b[:, :1].copy(), ept_b[:1]) if shared else (elt_b, ept_b)
+            ct, it = eng.sgp4_init(et)
+            cc, ic = eng.sgp4_init(elc_b)
+            a = {k: _np(v) for k, v in eng.screen(ct, ep, cc, epc_b, tc, nf, 5e3, 0, init_err_t=it, init_err_c=ic).items()}
+            for force in (0, NV.SCREEN_FORCE_WARP):
+                b = {k: _np(v) for k, v in eng.screen_elems(et, ep, elc_b, epc_b, tc, nf, 5e3, force).items()}
+                for k in ("i_min", "i_conj", "err"):
+                    assert np.array_equal(a[k], b[k]), (n, shared, k)
+                for k in ("d_min", "d_conj"):
+                    assert np.array_equal(a[k], b[k], equal_nan=True), (n, shared, k)
+        assert ((a["err"] >> 8) & 16).sum() > 0 and (a["i_min"] == -1).sum() > 0
+
+
+def test_screen_host_two_devices_two_threads(eng):
+    """ksl_screen_host holds a per-DEVICE lock: two host threads driving two devices run concurrently and each gets
+    its own results; two threads on ONE device are serialised and both correct.  (One GPU: the second form only.)"""
+    import threading
+    elt, ept, elc, epc, times, _ = _golden_batch(4000, 29)
+    tc = np.ascontiguousarray(times[::100][:301])
+    nf = 30001
+    want = _screen(eng, elt, ept, elc, epc, tc, nf, 5e3, 0)
+    ndev = torch.cuda.device_count()
+    jobs = [(d % ndev) for d in range(4)]
+    out, errs = [None] * len(jobs), []
+
+    def work(i, dev):
+        try:
+            for _ in range(3):
+                out[i] = eng.screen_host(elt, ept, elc, epc, tc, nf, 5e3, 0, device=dev)
+        except Exception as e:     # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=work, args=(i, d)) for i, d in enumerate(jobs)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for r in out:
+        for k in ("i_min", "i_conj", "err", "d_min"):
+            assert np.array_equal(r[k], want[k])
+    assert torch.cuda.current_device() == 0
+
+
 def test_screen_host_and_summary(eng):
     elt, ept, elc, epc, times, _ = _golden_batch(500, 9)
     tc = np.ascontiguousarray(times[::100])
