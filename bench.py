@@ -31,7 +31,6 @@ UNIT = "traces/s"
 N_COARSE, N_FINE, UPSAMPLE = 6000, 600000, 100
 EVALS_PER_TRACE = 2 * N_COARSE
 FLOP_PER_EVAL = 940.0          # canonical algorithmic FP64 flop per SGP4 evaluation
-EXECUTED_FLOP_PER_EVAL = 354.0  # ncu, profiles/r01i_k_screen_warp_sass_opcode_mix.csv: 2 x 125.2 DFMA + 77.3 DMUL + 26.4 DADD
 FLOP_PER_INIT = 600.0
 BYTES_PER_TRACE = 2 * 7 * 8 + 32  # algorithmic bytes: 2x7 doubles in, 4 values out
 THR_M, COLLISION_M = 5e3, 70.0
@@ -171,6 +170,168 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------
+# What the committed ncu captures say about the dominant kernel (profiles/current.json names them).  bench.py DERIVES the
+# executed-flop figure from the opcode-mix CSV at run time instead of carrying a literal, so the roofline record cannot
+# drift from the evidence; tests/test_bench_contract.py checks that manifest, CSV and metrics JSON agree.
+def kernel_sources_sha():
+    import hashlib
+    h = hashlib.sha256()
+    for name in ("kessler_b200.cu", "sgp4_device.cuh", "screen_device.cuh", "sincos_grid_table.cuh"):
+        h.update(open(os.path.join(ROOT, "kessler_b200", "csrc", name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_profile(kernel="k_screen_warp"):
+    """-> dict(executed_flop_per_unit, fp64_instr_per_unit, pipe_active_pct, issue_active_pct, dram_bytes_per_trace,
+    files, matches_source) from profiles/current.json, or None."""
+    try:
+        man = json.load(open(os.path.join(ROOT, "profiles", "current.json")))[kernel]
+        per = {}
+        for ln in open(os.path.join(ROOT, "profiles", man["opcode_mix"])).read().strip().splitlines()[1:]:
+            op, _, per_unit = ln.split(",")
+            per[op] = float(per_unit)
+        met = json.load(open(os.path.join(ROOT, "profiles", man["metrics"])))
+        return {"executed_flop_per_unit": 2.0 * per.get("DFMA", 0.0) + per.get("DMUL", 0.0) + per.get("DADD", 0.0),
+                "fp64_instr_per_unit": sum(per.get(k, 0.0) for k in ("DFMA", "DMUL", "DADD", "DSETP")),
+                "instr_per_unit": sum(per.values()),
+                "pipe_active_pct": met.get("sm__pipe_fp64_cycles_active_pct"), "issue_active_pct": met.get("smsp__issue_active_pct"),
+                "dram_bytes_per_trace": met.get("bytes_per_trace"), "traces_per_launch": met.get("traces_per_launch"),
+                "files": [man["opcode_mix"], man["metrics"]],
+                "matches_source": man.get("kernel_sources_sha16") == kernel_sources_sha()}
+    except Exception:
+        return None
+
+
+def device_ms(fn, reps=3, warm=1):
+    """median CUDA-event time of fn() on the current stream"""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ms.append(a.elapsed_time(b))
+    return float(np.median(ms))
+
+
+def default_prior_catalog(n, seed=3):
+    """n TLE element sets drawn from default_prior() (model.py:54-153) with seed `seed`, rejecting
+    period >= 225 min and perigee < 120 km.  Host sampler (the reference's own distributions), TLE-text quantised."""
+    import torch
+    from kessler_b200.model import Conjunction
+    from kessler_b200.tle import MU_EARTH, R_EARTH
+    torch.manual_seed(seed)
+    m = Conjunction()
+    out, raws = np.zeros((7, 0)), []
+    while out.shape[1] < n:
+        raw, el, _ = m.sample_elements('c', 2 * n)
+        a = (MU_EARTH / np.maximum(raw['mean_motion'], 1e-12) ** 2) ** (1.0 / 3.0)
+        keep = (raw['mean_motion'] > 2 * np.pi / (225.0 * 60.0)) & (a * (1 - raw['eccentricity']) - R_EARTH > 120e3)
+        out = np.concatenate([out, el[:, keep]], axis=1)
+    return np.ascontiguousarray(out[:, :n])
+
+
+def secondary_workloads(engine, NV, W, D, rank, world, dev, peak_tf, hbm_peak):
+    """BASELINE configs[2] (strong scaling over the ranks), and -- single GPU only -- configs[3], K2 and K5.
+    Every figure is device time (CUDA events) unless it says e2e."""
+    import torch
+    from kessler_b200 import montecarlo as MC
+    from kessler_b200.tle import MU_EARTH, R_EARTH
+    sec = {}
+    t_tle, c_tle = W.pair_a()
+    # ---- configs[2]: 1e8-sample Monte Carlo Pc of one pair, TOTAL fixed, sharded over the ranks -----------------------
+    n_total = 100000000
+    st_t, st_c = MC.nominal_state_m(t_tle, 0.0).reshape(2, 3), MC.nominal_state_m(c_tle, 0.0).reshape(2, 3)
+    pp = MC.prepare_pair(t_tle, st_t, W.T_COV_RTN, c_tle, st_c, W.C_COV_RTN, t_tle.date_mjd + 1.0)
+    MC.run_prepared(pp, n_total, seed=2, to_host=False)
+    torch.cuda.synchronize()
+    D.barrier()
+    ms = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        D.barrier()
+        a.record()
+        packed, mom = MC.run_prepared(pp, n_total, seed=2, to_host=False)     # kernel(s) + the one collective
+        b.record()
+        b.synchronize()
+        ms.append(D.max_over_ranks(a.elapsed_time(b)))
+    t = float(np.median(ms))
+    sec["configs2_mc_pc"] = {"workload": "BASELINE configs[2]: 1e8-sample Monte Carlo Pc of the default pair, device-side draws, "
+                                         "sgp4init + sgp4 at TCA for both objects, count + 2 x 28 moments, one packed all-gather",
+                             "n_total": n_total, "scaling": "strong", "n_gpus": world, "ms": t, "samples_per_s": n_total / (t * 1e-3),
+                             "sgp4_init_plus_eval_per_s": 2 * n_total / (t * 1e-3), "count": int(packed[0]), "err_count": int(packed[1]),
+                             "n_ok": float(mom[0])}
+    if world > 1 or rank != 0:
+        return sec
+    # ---- configs[3]: 30 000 objects drawn from default_prior() (seed 3) against one target, 7 days ---------------------
+    cat = default_prior_catalog(30000, seed=3)
+    time0 = t_tle.date_mjd - 3.5
+    times = W.time_grid(time0)
+    tc = np.ascontiguousarray(times[::UPSAMPLE])
+    ep_c = np.full(cat.shape[1], t_tle.date_mjd)
+    el_t = t_tle.elements().reshape(7, 1)
+    a_c = (MU_EARTH / (cat[0] / 60.0) ** 2) ** (1.0 / 3.0)
+    apo_c, per_c = a_c * (1 + cat[1]) - R_EARTH, a_c * (1 - cat[1]) - R_EARTH
+    pre = ((t_tle.apogee_alt() + THR_M + 1000) < per_c) | ((apo_c + THR_M + 1000) < t_tle.perigee_alt())     # model.py:567
+    c3 = {"workload": "BASELINE configs[3]: 30000 objects from default_prior() (seed 3; period < 225 min, perigee > 120 km) vs the "
+                      "pair-A target, 7 days, 6000 coarse epochs -> 600000 fine points", "objects": int(cat.shape[1]),
+          "rejected_by_altitude_filter": int(pre.sum())}
+    for tag, sel in (("unfiltered", np.ones(cat.shape[1], bool)), ("prefiltered", ~pre)):
+        el = np.ascontiguousarray(cat[:, sel])
+        d_el, d_ep = torch.from_numpy(el).to(dev), torch.from_numpy(ep_c[sel]).to(dev)
+        d_t, d_te, d_tc = torch.from_numpy(el_t).to(dev), torch.tensor([t_tle.date_mjd], dtype=torch.float64, device=dev), torch.from_numpy(tc).to(dev)
+        t = device_ms(lambda: engine.screen_elems(d_t, d_te, d_el, d_ep, d_tc, len(times), THR_M), reps=5)
+        t0 = time.perf_counter()
+        out = engine.screen_host(el_t, [t_tle.date_mjd], el, ep_c[sel], tc, len(times), THR_M)
+        e2e = (time.perf_counter() - t0) * 1e3
+        nobj = int(sel.sum())
+        fast = int(((out["err"] >> 8) == 0).sum())
+        c3[tag] = {"objects": nobj, "ms": t, "objects_per_s": nobj / (t * 1e-3), "sgp4_evals_per_s": (nobj + 1) * len(tc) / (t * 1e-3),
+                   "e2e_ms_pageable": e2e, "conjunctions_below_5km": int((out["i_conj"] > 0).sum()),
+                   "min_d_min_m": float(np.nanmin(out["d_min"])), "objects_without_error_bits": fast}
+    sec["configs3_catalog"] = c3
+    # ---- K2: dsgp4.propagate / propagate_batch standalone (states written: 48 B per evaluation) ------------------------
+    n_rec, m_ep = 8192, 6000
+    wl = W.config2_batch(n_rec, seed=5, rank=0, state_t=st_t, state_c=st_c)
+    consts, _ = engine.sgp4_init(wl["elems_t"].to(dev))
+    ts = torch.from_numpy((tc - wl["epoch_t"]) * 1440.0).to(dev)
+    rv = torch.empty((n_rec, m_ep, 6), dtype=torch.float64, device=dev)
+    err = torch.zeros(n_rec, dtype=torch.int32, device=dev)
+    from kessler_b200._native import ptr, stream_ptr
+    run_k2 = lambda: NV.check(NV.lib().ksl_sgp4_prop(ptr(consts), n_rec, ptr(ts), m_ep, 0, ptr(rv), ptr(err), stream_ptr()), "ksl_sgp4_prop")
+    t = device_ms(run_k2, reps=5)
+    evals = n_rec * m_ep
+    sec["k2_sgp4_prop"] = {"workload": f"ksl_sgp4_prop: {n_rec} records x {m_ep} epochs, full state [n][m][6] written",
+                           "evals": evals, "ms": t, "evals_per_s": evals / (t * 1e-3),
+                           "roofline_hbm": {"bytes_per_eval": 48, "achieved_gbs": 48 * evals / (t * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                                            "frac": 48 * evals / (t * 1e-3) / 1e9 / hbm_peak},
+                           "roofline_fp64_algorithmic": {"flop_per_eval": FLOP_PER_EVAL, "achieved_tflops": FLOP_PER_EVAL * evals / (t * 1e-3) / 1e12,
+                                                         "peak_tflops": peak_tf}}
+    del rv
+    # ---- K5: model.py:432-437 at the reference size, 1e4 x 1e4 pairs (8 non-fused FP64 operations + compare per pair) ------
+    rng = np.random.default_rng(4)
+    tp = torch.from_numpy(rng.standard_normal((3, 10000)) * 60.0).to(dev)
+    cp = torch.from_numpy(rng.standard_normal((3, 10000)) * 60.0).to(dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    t = device_ms(lambda: engine.pc_count(tp, cp, COLLISION_M, count=cnt), reps=5, warm=2)
+    pairs = 1e8
+    sec["k5_pc_all_pairs"] = {"workload": "ksl_pc_count: 1e4 x 1e4 position samples, all pairs, bit-exact integer count",
+                              "pairs": pairs, "ms": t, "pairs_per_s": pairs / (t * 1e-3),
+                              "roofline_fp64": {"fp64_instr_per_pair": 9, "note": "3 DADD + 3 DMUL + 2 DADD + 1 DSETP, none fused (the count must "
+                                                "match the reference's roundings): the pipe issues 32 lanes / 2 cycles / SMSP",
+                                                "achieved_ginstr_per_s": 9 * pairs / (t * 1e-3) / 1e9,
+                                                "peak_ginstr_per_s": peak_tf * 1e12 / 2 / 1e9,
+                                                "frac": 9 * pairs / (t * 1e-3) / (peak_tf * 1e12 / 2)}}
+    return sec
+
+
+# ------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     from kessler_b200 import _native as NV
@@ -207,6 +368,7 @@ def run_ours(args):
     screen_ms = []
 
     def step(timed):
+        # one launch does sgp4init (in the kernel's prologue) + 2 x 6000 SGP4 evaluations + the search per trace
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -248,65 +410,78 @@ def run_ours(args):
     moments_h = moments.cpu().numpy().tolist()
 
     # ---- end-to-end arm: host buffers through the C ABI (H2D + kernels + D2H every step) -----
-    out = dict(i_min=torch.empty(n, dtype=torch.int64).pin_memory().numpy(), d_min=torch.empty(n, dtype=torch.float64).pin_memory().numpy(),
-               i_conj=torch.empty(n, dtype=torch.int64).pin_memory().numpy(), d_conj=torch.empty(n, dtype=torch.float64).pin_memory().numpy(),
-               err=torch.empty(n, dtype=torch.int32).pin_memory().numpy())
-    np_in = (h_el_t.numpy(), h_ep_t.numpy(), h_el_c.numpy(), h_ep_c.numpy())
+    def make_out(pinned):
+        mk = (lambda dt: torch.empty(n, dtype=dt).pin_memory().numpy()) if pinned else (lambda dt: torch.empty(n, dtype=dt).numpy())
+        return dict(i_min=mk(torch.int64), d_min=mk(torch.float64), i_conj=mk(torch.int64), d_conj=mk(torch.float64), err=mk(torch.int32))
 
-    def e2e_step():
-        r = engine.screen_host(np_in[0], np_in[1], np_in[2], np_in[3], tc, N_FINE, THR_M, mode, COLLISION_M, device=local_rank, out=out)
-        if world > 1:
-            c = torch.from_numpy(r["counts"].astype(np.int64)).to(dev)
-            m = torch.from_numpy(r["moments"]).to(dev)
-            D.allreduce_summary(c, m)
-            c.cpu()
-        return r
+    def e2e_run(np_in, out):
+        def e2e_step():
+            r = engine.screen_host(np_in[0], np_in[1], np_in[2], np_in[3], tc, N_FINE, THR_M, mode, COLLISION_M, device=local_rank, out=out)
+            if world > 1:
+                c = torch.from_numpy(r["counts"].astype(np.int64)).to(dev)
+                m = torch.from_numpy(r["moments"]).to(dev)
+                D.allreduce_summary(c, m)
+                c.cpu()
+            return r
+        e2e_step()
+        torch.cuda.synchronize()
+        D.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r_host = e2e_step()
+        torch.cuda.synchronize()
+        s = D.max_over_ranks(time.perf_counter() - t0)
+        D.barrier()
+        return s, r_host
 
-    e2e_step()
-    torch.cuda.synchronize()
-    D.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        r_host = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = D.max_over_ranks(time.perf_counter() - t0)
-    D.barrier()
+    e2e_s, r_host = e2e_run((h_el_t.numpy(), h_ep_t.numpy(), h_el_c.numpy(), h_ep_c.numpy()), make_out(True))
     e2e_value = world * n * args.steps / e2e_s
+    same = bool(np.array_equal(r_host["i_min"], res["i_min"].cpu().numpy()) and
+                np.array_equal(r_host["i_conj"], res["i_conj"].cpu().numpy()))
+    # ... and with plain (pageable) NumPy arrays, what a caller that never heard of pinned memory hands over
+    pg_in = tuple(np.array(a.numpy(), copy=True) for a in (h_el_t, h_ep_t, h_el_c, h_ep_c))
+    e2e_pg_s, _ = e2e_run(pg_in, make_out(False))
     h2d = (2 * 7 * 8 + 2 * 8) * n + 8 * N_COARSE
     d2h = (4 * 8 + 4) * n + 8 * (NV.SUM_NCOUNT + NV.SUM_NMOMENT)
-    same = bool(np.array_equal(r_host["i_min"], res["i_min"].cpu().numpy()))
 
-    if rank != 0:
-        D.barrier()
-        return
-    # ---- roofline of the dominant kernel (k_screen), FP64 vector pipe ------------------------
-    peak_tf = engine.fp64_peak_tflops()
-    flop_per_launch = n * EVALS_PER_TRACE * FLOP_PER_EVAL
-    achieved_tf = flop_per_launch / scr_s / 1e12
+    # ---- peaks ---------------------------------------------------------------------------------
+    peak_tf = engine.fp64_peak_tflops() if rank == 0 else 0.0
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    traffic, pipe_pct = None, None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum of k_screen_warp from the committed ncu --set full capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01i_k_screen_warp_traffic.json")))
-        traffic = tr["dram_bytes_total"] * (n / tr["traces_per_launch"])
-        pipe_pct = tr.get("sm__pipe_fp64_cycles_active_pct")
-    except Exception:
-        pass
-    roofline = {"bound": "fp64", "kernel": "k_screen_warp (fused SGP4 x2 + closed-form TCA search, one warp per trace)", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": traffic,
-                "traffic_source": "profiles/r01i_k_screen_warp_traffic.json (ncu --set full at 1e6 traces/launch; scaled by n if --samples differs)",
-                "peak_source": "measured in this run: dependent-free DFMA probe (ksl_fp64_peak_kernel); MEASURED_PEAKS.json has no FP64 entry",
-                "flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": n * EVALS_PER_TRACE, "launch_ms": scr_s * 1e3,
-                # frac is ALGORITHMIC flop (the reference algorithm's 940 flop / evaluation) over the
-                # measured peak, so it exceeds 1 once the kernel needs fewer operations than that count; what the
-                # hardware actually ran is in the keys below (committed ncu capture, profiles/r01i_*)
-                "executed_flop_per_eval": EXECUTED_FLOP_PER_EVAL,
-                "executed_frac": n * EVALS_PER_TRACE * EXECUTED_FLOP_PER_EVAL / scr_s / 1e12 / peak_tf,
-                "fp64_pipe_active_pct_ncu": pipe_pct,
+    secondary = None
+    if not args.no_secondary:
+        secondary = secondary_workloads(engine, NV, W, D, rank, world, dev, peak_tf, hbm_peak)
+    if rank != 0:
+        D.barrier()
+        return
+    # ---- roofline of the dominant kernel (k_screen_warp), FP64 vector pipe ----------------------
+    # frac      = EXECUTED FP64 flop (2 DFMA + DMUL + DADD per evaluation, from the committed ncu opcode mix of this very
+    #             kernel) x evaluations per launch / launch time (CUDA events, this run) / measured DFMA peak (this run)
+    # pipe_active = sm__pipe_fp64_cycles_active of the same capture: the honest distance to the ceiling, because DMUL /
+    #             DADD / DSETP occupy a pipe slot for one flop or none
+    # algorithmic_ratio = the reference algorithm's 940 flop / evaluation on the same clock: how much
+    #             cheaper than that count the kernel's instruction stream is (can exceed 1)
+    prof = load_profile("k_screen_warp")
+    evals = n * EVALS_PER_TRACE
+    exe = prof["executed_flop_per_unit"] if prof else None
+    achieved_tf = (evals * exe / scr_s / 1e12) if exe else None
+    roofline = {"bound": "fp64", "kernel": "k_screen_warp<false, analytic, fused init> (sgp4init + SGP4 x2 + closed-form TCA search, one warp per trace)",
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved_tf / peak_tf) if exe else None,
+                "pipe_active": (prof["pipe_active_pct"] / 100.0) if prof and prof["pipe_active_pct"] else None,
+                "issue_active": (prof["issue_active_pct"] / 100.0) if prof and prof["issue_active_pct"] else None,
+                "executed_flop_per_eval": exe, "fp64_instr_per_eval": prof["fp64_instr_per_unit"] if prof else None,
+                "instr_per_eval": prof["instr_per_unit"] if prof else None,
+                "algorithmic_flop_per_eval": FLOP_PER_EVAL, "algorithmic_ratio": evals * FLOP_PER_EVAL / scr_s / 1e12 / peak_tf,
+                "evals_per_launch": evals, "launch_ms": scr_s * 1e3,
+                "traffic": (prof["dram_bytes_per_trace"] * n) if prof and prof["dram_bytes_per_trace"] else None,
+                "traffic_algorithmic": n * BYTES_PER_TRACE,
+                "profile_files": prof["files"] if prof else None, "profile_matches_source": prof["matches_source"] if prof else None,
+                "peak_source": "measured in this run: dependent-free DFMA probe (ksl_fp64_peak_kernel; ncu of the probe in "
+                               "profiles/: pipe 99 %); MEASURED_PEAKS.json has no FP64 entry",
                 "hbm": {"achieved_gbs": n * BYTES_PER_TRACE / scr_s / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)",
                         "note": "algorithmic 144 B/trace; the path is FP64-bound, not HBM-bound"}}
@@ -346,12 +521,14 @@ def run_ours(args):
             "config": {"workload": "BASELINE configs[1]: 1e6 perturbed-TLE samples (per GPU) of the default LEO pair "
                                    "(44227/44229), 7-day window, 6000 coarse SGP4 epochs -> 600000 fine points, 5 km threshold",
                        "samples_per_gpu": n, "n_coarse": N_COARSE, "n_fine": N_FINE, "search": args.mode,
-                       "l2": "256 MiB flush between timed steps; per-step working set (constants 576 MB) > L2",
-                       "parallelism": f"dp{world} (samples sharded, no data-path collective; summary all-reduce)"},
+                       "l2": "256 MiB flush between timed steps (outside the event pairs)",
+                       "parallelism": f"dp{world} (samples sharded, no data-path collective; one packed all-gather of the summary)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s * 1e3 / args.steps, "matches_device_arm": same},
+                    "ms_per_step": e2e_s * 1e3 / args.steps, "matches_device_arm": same, "host_buffers": "pinned",
+                    "pageable": {"value": world * n * args.steps / e2e_pg_s, "unit": UNIT, "ms_per_step": e2e_pg_s * 1e3 / args.steps,
+                                 "host_buffers": "plain NumPy arrays in and out (no pinning)"}},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "summary": {"counts": counts_h, "moments": moments_h}}
+            "summary": {"counts": counts_h, "moments": moments_h}, "secondary": secondary}
     print(json.dumps(line), flush=True)
     D.barrier()
 
@@ -365,6 +542,7 @@ def main():
     ap.add_argument("--samples", type=float, default=1e6, help="samples per GPU per step")
     ap.add_argument("--mode", default="analytic", choices=["analytic", "brute"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (configs[2], configs[3], K2, K5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

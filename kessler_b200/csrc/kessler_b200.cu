@@ -760,59 +760,105 @@ __global__ void k_summary_final(const double *__restrict__ partial, int nparts, 
 }
 
 // ------------------------------------------------------------------------------------
-// K4  Monte Carlo states at TCA + shifted moments (model.py:536-550).  Thread per
-// sample; sgp4init and sgp4 fused, constants live in registers.
+// K4  Monte Carlo states at TCA + shifted moments (model.py:536-550).  Thread per sample: sgp4init (fast form)
+// and the fast SGP4 state, all in registers, no call and no stack.  A sample the fast path declines (eccentricity
+// above 0.12, decayed, non-finite ...) is only MARKED -- one bit in a per-warp-iteration mask --, and the exact
+// route (sgp4_init + sgp4_prop, out of line) is taken for the marked samples by a second, tiny kernel, so the hot
+// kernel carries neither that code's registers nor its stack frame.  Both kernels reduce their 28 shifted moments
+// in a fixed order into rows of `partial`; k_moments_final adds the rows in order: deterministic.
 // ------------------------------------------------------------------------------------
 constexpr int kTcaThreads = 128;
-__global__ void __launch_bounds__(kTcaThreads) k_tca_moments(const double *__restrict__ elems, long long n, double tsince,
-                                                             const double *__restrict__ ref, double *__restrict__ states,
-                                                             double *__restrict__ partial /*[grid][KSL_NMOMENT]*/,
-                                                             unsigned long long *__restrict__ err_count) {
+
+__device__ __forceinline__ void moments_add(double acc[KSL_NMOMENT], const double x[6], const double *ref) {
+    double d[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) d[q] = x[q] - ref[q];
+    acc[0] += 1.0;
+    int o = 7;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        acc[1 + a] += d[a];
+#pragma unroll
+        for (int b = a; b < 6; ++b) { acc[o] = fma(d[a], d[b], acc[o]); ++o; }
+    }
+}
+// the same on accumulators that live in shared memory, one column per thread (stride = threads per CTA: conflict-free)
+template <int kStride>
+__device__ __forceinline__ void moments_add_strided(double *acc, const double x[6], const double *ref) {
+    double d[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) d[q] = x[q] - ref[q];
+    acc[0] += 1.0;
+    int o = 7;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        acc[(1 + a) * kStride] += d[a];
+#pragma unroll
+        for (int b = a; b < 6; ++b) { acc[o * kStride] = fma(d[a], d[b], acc[o * kStride]); ++o; }
+    }
+}
+__device__ __forceinline__ bool finite6(const double x[6]) {
+    bool f = true;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) f = f && (fabs(x[q]) < INFINITY);
+    return f;
+}
+// sum of acc[q] over the lanes selected by the xor-distances `first`, first/2, ... 1 ... (all lanes: first = 16)
+template <int kFirst, int kLast>
+__device__ __forceinline__ double lanes_sum(double v) {
+#pragma unroll
+    for (int d = kFirst; d >= kLast; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+__global__ void __launch_bounds__(kTcaThreads, 3) k_tca_moments(const double *__restrict__ elems, long long n, double tsince,
+                                                                const double *__restrict__ ref, double *__restrict__ states,
+                                                                double *__restrict__ partial /*[rows][KSL_NMOMENT]*/,
+                                                                unsigned int *__restrict__ masks /*[ceil(n/32)], zeroed*/,
+                                                                unsigned long long *__restrict__ err_count) {
+    __shared__ __align__(16) double s_grid[2 * ksl::kGridPoints];
+    __shared__ double s_ref[6];
+    __shared__ double sm[kTcaThreads / 32][KSL_NMOMENT];
+    for (int q = threadIdx.x; q < 2 * ksl::kGridPoints; q += kTcaThreads) s_grid[q] = ksl::kGridSinCos[q];
+    if (threadIdx.x < 6) s_ref[threadIdx.x] = ref[threadIdx.x];
+    __syncthreads();
     double acc[KSL_NMOMENT];
 #pragma unroll
     for (int q = 0; q < KSL_NMOMENT; ++q) acc[q] = 0.0;
-    double rf[6];
-#pragma unroll
-    for (int q = 0; q < 6; ++q) rf[q] = ref[q];
-    unsigned long long nerr = 0;
-    for (long long i = (long long)blockIdx.x * kTcaThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kTcaThreads) {
+    unsigned int nerr = 0;
+    const int lane = threadIdx.x & 31;
+    const long long warps_total = (long long)gridDim.x * (kTcaThreads / 32);
+    for (long long it = (long long)blockIdx.x * (kTcaThreads / 32) + (threadIdx.x >> 5); it * 32 < n; it += warps_total) {
+        const long long i = it * 32 + lane;
+        const bool active = i < n;
         double el[7], x[6];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) el[k] = elems[k * n + i];
-        int e = ksl::sgp4_init_state(el, tsince, x, x + 3, ksl::kGridSinCos);
+        for (int k = 0; k < 7; ++k) el[k] = elems[k * n + (active ? i : 0)];
+        int ierr;
+        const bool ok = ksl::sgp4_init_state_fast(el, tsince, x, x + 3, s_grid, &ierr);
 #pragma unroll
         for (int q = 0; q < 6; ++q) x[q] *= 1e3;  // model.py:541: *1e3 -> metres
-        if (states) {
-#pragma unroll
-            for (int q = 0; q < 6; ++q) states[6 * i + q] = x[q];
+        const unsigned int declined = __ballot_sync(0xffffffffu, active && !ok);
+        if (declined && lane == 0) {
+            masks[it] = declined;
+            masks[-1] = 1u;          // "some sample needs the exact route" (the word in front of the masks)
         }
-        if (e) { nerr += 1; }
-        bool finite = true;
+        if (active && ok) {
+            if (states) {
 #pragma unroll
-        for (int q = 0; q < 6; ++q) finite = finite && (fabs(x[q]) < INFINITY);
-        if (finite) {
-            double dlt[6];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) dlt[q] = x[q] - rf[q];
-            acc[0] += 1.0;
-            int o = 7;
-#pragma unroll
-            for (int a = 0; a < 6; ++a) {
-                acc[1 + a] += dlt[a];
-#pragma unroll
-                for (int b = a; b < 6; ++b) acc[o++] += dlt[a] * dlt[b];
+                for (int q = 0; q < 6; ++q) states[6 * i + q] = x[q];
             }
+            nerr += ierr ? 1u : 0u;
+            moments_add(acc, x, s_ref);
         }
     }
-    __shared__ double sm[kTcaThreads / 32][KSL_NMOMENT];
 #pragma unroll
     for (int q = 0; q < KSL_NMOMENT; ++q) {
-        double v = acc[q];
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5][q] = v;
+        const double v = lanes_sum<16, 1>(acc[q]);
+        if (lane == 0) sm[threadIdx.x >> 5][q] = v;
     }
-    for (int d = 16; d > 0; d >>= 1) nerr += __shfl_down_sync(0xffffffffu, nerr, d);
-    if ((threadIdx.x & 31) == 0 && nerr) atomicAdd(err_count, nerr);
+    nerr = __reduce_add_sync(0xffffffffu, nerr);
+    if (lane == 0 && nerr) atomicAdd(err_count, (unsigned long long)nerr);
     __syncthreads();
     if (threadIdx.x < KSL_NMOMENT) {
         double v = 0.0;
@@ -821,12 +867,59 @@ __global__ void __launch_bounds__(kTcaThreads) k_tca_moments(const double *__res
     }
 }
 
+// the samples k_tca_moments marked: exact route.  One thread per mask word; a single CTA row of `partial` per block.
+constexpr int kExactThreads = 128;
+__global__ void __launch_bounds__(kExactThreads) k_tca_moments_exact(const double *__restrict__ elems, long long n, double tsince,
+                                                                     const double *__restrict__ ref, double *__restrict__ states,
+                                                                     double *__restrict__ partial, const unsigned int *__restrict__ masks,
+                                                                     unsigned long long *__restrict__ err_count) {
+    __shared__ double sm[kExactThreads / 32][KSL_NMOMENT];
+    double acc[KSL_NMOMENT];
+    for (int q = 0; q < KSL_NMOMENT; ++q) acc[q] = 0.0;
+    double rf[6];
+    for (int q = 0; q < 6; ++q) rf[q] = ref[q];
+    unsigned long long nerr = 0;
+    const long long n_it = (masks[-1] != 0u) ? (n + 31) / 32 : 0;     // nothing marked: only the (zero) partial row is written
+    for (long long it = (long long)blockIdx.x * kExactThreads + threadIdx.x; it < n_it; it += (long long)gridDim.x * kExactThreads) {
+        unsigned int m = masks[it];
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const long long i = it * 32 + b;
+            double el[7], x[6];
+            for (int k = 0; k < 7; ++k) el[k] = elems[k * n + i];
+            const int e = ksl::sgp4_init_state_exact(el, tsince, x, x + 3);
+            for (int q = 0; q < 6; ++q) x[q] *= 1e3;
+            if (states)
+                for (int q = 0; q < 6; ++q) states[6 * i + q] = x[q];
+            nerr += e ? 1 : 0;
+            if (finite6(x)) moments_add(acc, x, rf);
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    for (int q = 0; q < KSL_NMOMENT; ++q) {
+        const double v = lanes_sum<16, 1>(acc[q]);
+        if (lane == 0) sm[threadIdx.x >> 5][q] = v;
+    }
+    for (int d = 16; d > 0; d >>= 1) nerr += __shfl_xor_sync(0xffffffffu, nerr, d);
+    if (lane == 0 && nerr) atomicAdd(err_count, nerr);
+    __syncthreads();
+    if (threadIdx.x < KSL_NMOMENT) {
+        double v = 0.0;
+        for (int w = 0; w < kExactThreads / 32; ++w) v += sm[w][threadIdx.x];
+        partial[(long long)blockIdx.x * KSL_NMOMENT + threadIdx.x] = v;
+    }
+}
+
+// rows of partial moments -> their sum, in a fixed order: column q is handled by the 32 lanes of warp q (lane l adds
+// rows l, l + 32, ... in order, then a fixed shuffle tree): deterministic, and 32 loads in flight per column
 __global__ void k_moments_final(const double *__restrict__ partial, int nparts, int width, double *__restrict__ out) {
-    const int q = threadIdx.x;
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= width) return;
     double v = 0.0;
-    for (int b = 0; b < nparts; ++b) v += partial[(long long)b * width + q];
-    out[q] = v;
+    for (int b = lane; b < nparts; b += 32) v += partial[(long long)b * width + q];
+    v = lanes_sum<16, 1>(v);
+    if (lane == 0) out[q] = v;
 }
 
 // ------------------------------------------------------------------------------------
@@ -891,11 +984,19 @@ __global__ void __launch_bounds__(256) k_pc_elementwise(const double *__restrict
 // ------------------------------------------------------------------------------------
 // K6  scale-out Monte Carlo collision probability (BASELINE configs[2]):
 // for every global sample index g: draw (a, e, i, Omega, omega, M) ~ N(mean, L L^T) for target and
-// chaser with a counter-based generator keyed by (seed, g) -- so the draws do not depend on how the
+// chaser with a counter-based generator keyed by (seed, g, object) -- so the draws do not depend on how the
 // samples are sharded over GPUs --, convert as model.py:500,525-533 do, sgp4init + sgp4 at the TCA,
 // and reduce (i) the number of samples whose miss distance is below the threshold (exact integer)
-// and (ii) the shifted moments of both states.  Everything stays in registers; 96 B of moments per
-// CTA and one atomic per CTA leave the SM.
+// and (ii) the shifted moments of both states.
+// Mapping: a PAIR of adjacent lanes per sample -- the even lane is the target, the odd lane the chaser.  Every
+// lane runs the same instruction stream on its own object (parameters from a two-entry shared-memory table),
+// keeps ONE set of 28 moment accumulators, and the two positions meet through three shuffles for the
+// miss-distance test.  sgp4init in its fast form and the fast SGP4 state stay in registers; samples they decline
+// are marked in a mask and redone on the exact route by k_mc_pc_exact (see K4).  96 B of moments per CTA and one
+// atomic per CTA leave the SM.
+// The standard normals are single-precision Box-Muller deviates (24 significant bits, tails to 6.8 sigma) widened to
+// FP64: the FP32 / MUFU pipes idle in this kernel while the FP64 pipe is what bounds it; everything from the
+// element vector on is FP64.
 // ------------------------------------------------------------------------------------
 struct McObject {
     double mean[6];   // a [m], e, i, raan, argp, M
@@ -903,6 +1004,7 @@ struct McObject {
     double bstar, tsince;
     double ref[6];    // reference state [m, m/s] for the shifted moments
 };
+constexpr int kMcObjDoubles = sizeof(McObject) / sizeof(double);   // 35
 
 __device__ __forceinline__ void philox4x32_10(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3,
                                               unsigned int k0, unsigned int k1, unsigned int out[4]) {
@@ -925,113 +1027,144 @@ __device__ __forceinline__ double u53(unsigned int a, unsigned int b) {
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
-// six standard normals for (seed, sample g, stream s): three Box-Muller pairs from three Philox blocks
-__device__ __forceinline__ void normals6(unsigned long long seed, unsigned long long g, unsigned int stream, double z[6]) {
-#pragma unroll
-    for (int b = 0; b < 3; ++b) {
-        unsigned int w[4];
-        philox4x32_10((unsigned int)g, (unsigned int)(g >> 32), stream * 3u + b, 0x4b534c31u, (unsigned int)seed,
-                      (unsigned int)(seed >> 32), w);
-        const double rad = sqrt(-2.0 * log(u53(w[0], w[1])));
-        double sn, cs;
-        sincospi(2.0 * u53(w[2], w[3]), &sn, &cs);
-        z[2 * b] = rad * cs;
-        z[2 * b + 1] = rad * sn;
-    }
+// one Box-Muller pair in single precision from two 32-bit words: radius from u1 = (w0 + 1/2) 2^-32 in (0, 1] (a float
+// keeps the small values that make the tails exactly), angle 2 pi w1 2^-32 - pi in [-pi, pi].  log, sin and cos are the
+// MUFU-based intrinsics: absolute error 4e-7 (2^-21.4) in the logarithm near u1 = 1 and in sin / cos -- a relative
+// 1e-6 distortion of a random deviate, far below the Monte Carlo error of any statistic of 1e8 samples -- and the
+// special-function unit they run on is otherwise idle here.  max(., 0) guards the radius against that error at u1 -> 1.
+__device__ __forceinline__ void box_muller_f32(unsigned int w0, unsigned int w1, double &z0, double &z1) {
+    const float u1 = fmaf(__uint2float_rn(w0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float rad = sqrtf(fmaxf(-2.0f * __logf(u1), 0.0f));
+    const float ang = fmaf(__uint2float_rn(w1), 1.4629180792671596e-09f, -3.14159265358979f);   // 2 pi 2^-32 w1 - pi
+    z0 = (double)(rad * __cosf(ang));
+    z1 = (double)(rad * __sinf(ang));
 }
 
-__device__ __forceinline__ int mc_state(const McObject &o, const double z[6], double mu, double el_out[7], double x[6]) {
+// six standard normals for (seed, sample g, stream): two Philox blocks, three Box-Muller pairs
+__device__ __forceinline__ void normals6(unsigned long long seed, unsigned long long g, unsigned int stream, double z[6]) {
+    unsigned int w[4], v[4];
+    philox4x32_10((unsigned int)g, (unsigned int)(g >> 32), stream * 2u, 0x4b534c32u, (unsigned int)seed, (unsigned int)(seed >> 32), w);
+    philox4x32_10((unsigned int)g, (unsigned int)(g >> 32), stream * 2u + 1u, 0x4b534c32u, (unsigned int)seed, (unsigned int)(seed >> 32), v);
+    box_muller_f32(w[0], w[1], z[0], z[1]);
+    box_muller_f32(w[2], w[3], z[2], z[3]);
+    box_muller_f32(v[0], v[1], z[4], z[5]);
+}
+
+// element vector of one draw: q = mean + L z, then a -> mean motion [rad/min] and e < 0 -> 0 (model.py:500,525-533).
+// `o` points at the object's 35 parameters (shared memory or a register copy); explicit roundings, so that the fast
+// kernel and the exact-route kernel form bit-identical elements from the same draw.
+__device__ __forceinline__ void mc_elements(const double *o, const double z[6], double mu, double el[7]) {
     double q[6];
-    int idx = 0;
+    int idx = 6;
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-        double acc = o.mean[r];
+        double acc = o[r];
 #pragma unroll
-        for (int cidx = 0; cidx <= r; ++cidx) acc += o.chol[idx++] * z[cidx];
+        for (int c = 0; c <= r; ++c) acc = ksl::fma_rn(o[idx++], z[c], acc);
         q[r] = acc;
     }
-    double el[7];
-    el[0] = sqrt(mu / (q[0] * q[0] * q[0])) * 60.0;   // model.py:500: a -> mean motion [rad/s]; *60 -> rad/min
-    el[1] = q[1] < 0.0 ? 0.0 : q[1];                  // model.py:525-528
+    const double a3 = ksl::mul_rn(ksl::mul_rn(q[0], q[0]), q[0]);
+    el[0] = ksl::mul_rn(sqrt(ksl::mul_rn(mu, ksl::rcp_2(a3))), 60.0);
+    el[1] = q[1] < 0.0 ? 0.0 : q[1];
     el[2] = q[2]; el[3] = q[3]; el[4] = q[4]; el[5] = q[5];
-    el[6] = o.bstar;
-#pragma unroll
-    for (int r = 0; r < 7; ++r) el_out[r] = el[r];
-    const int e = ksl::sgp4_init_state(el, o.tsince, x, x + 3, ksl::kGridSinCos);
-#pragma unroll
-    for (int r = 0; r < 6; ++r) x[r] *= 1e3;
-    return e;
+    el[6] = o[27];
 }
 
-__device__ __forceinline__ void accumulate_moments(double acc[KSL_NMOMENT], const double x[6], const double ref[6]) {
-    bool finite = true;
-#pragma unroll
-    for (int q = 0; q < 6; ++q) finite = finite && (fabs(x[q]) < INFINITY);
-    if (!finite) return;
-    double d[6];
-#pragma unroll
-    for (int q = 0; q < 6; ++q) d[q] = x[q] - ref[q];
-    acc[0] += 1.0;
-    int o = 7;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-        acc[1 + a] += d[a];
-#pragma unroll
-        for (int b = a; b < 6; ++b) acc[o++] += d[a] * d[b];
-    }
-}
-
+#ifndef KSL_MC_SMEM_ACC
+#define KSL_MC_SMEM_ACC 0      // 1: moment accumulators in shared memory (frees 56 registers per thread)
+#endif
+#ifndef KSL_MC_MIN_CTAS
+#define KSL_MC_MIN_CTAS 3
+#endif
 constexpr int kMcThreads = 128;
-__global__ void __launch_bounds__(kMcThreads) k_mc_pc(const McObject tgt, const McObject chs, unsigned long long seed,
-                                                      long long offset, long long n, double thr2, double mu,
-                                                      unsigned long long *__restrict__ count,
-                                                      double *__restrict__ partial /*[grid][2][KSL_NMOMENT]*/,
-                                                      unsigned long long *__restrict__ nerr,
-                                                      double *__restrict__ dump /*[n_dump][26] or NULL*/, long long n_dump) {
-    double acc_t[KSL_NMOMENT], acc_c[KSL_NMOMENT];
-#pragma unroll
-    for (int q = 0; q < KSL_NMOMENT; ++q) { acc_t[q] = 0.0; acc_c[q] = 0.0; }
-    unsigned long long hits = 0, errs = 0;
-    for (long long i = (long long)blockIdx.x * kMcThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kMcThreads) {
-        const unsigned long long g = (unsigned long long)(offset + i);
-        double z[6], el_t[7], el_c[7], xt[6], xc[6];
-        normals6(seed, g, 0u, z);
-        const int e0 = mc_state(tgt, z, mu, el_t, xt);
-        normals6(seed, g, 1u, z);
-        const int e1 = mc_state(chs, z, mu, el_c, xc);
-        const double dx = ksl::add_rn(xt[0], -xc[0]), dy = ksl::add_rn(xt[1], -xc[1]), dz = ksl::add_rn(xt[2], -xc[2]);
-        hits += (ksl::sqdist3(dx, dy, dz) < thr2) ? 1u : 0u;
-        errs += (e0 | e1) ? 1u : 0u;
-        accumulate_moments(acc_t, xt, tgt.ref);
-        accumulate_moments(acc_c, xc, chs.ref);
-        if (dump && i < n_dump) {
-            double *o = dump + i * 26;
-#pragma unroll
-            for (int q = 0; q < 7; ++q) { o[q] = el_t[q]; o[7 + q] = el_c[q]; }
-#pragma unroll
-            for (int q = 0; q < 6; ++q) { o[14 + q] = xt[q]; o[20 + q] = xc[q]; }
-        }
-    }
+__global__ void __launch_bounds__(kMcThreads, KSL_MC_MIN_CTAS) k_mc_pc(const McObject tgt, const McObject chs, unsigned long long seed,
+                                                         long long offset, long long n, double thr2, double mu,
+                                                         unsigned long long *__restrict__ count,
+                                                         double *__restrict__ partial /*[rows][2][KSL_NMOMENT]*/,
+                                                         unsigned int *__restrict__ masks /*[ceil(n/16)], zeroed*/,
+                                                         unsigned long long *__restrict__ nerr,
+                                                         double *__restrict__ dump /*[n_dump][26] or NULL*/, long long n_dump) {
+    __shared__ __align__(16) double s_grid[2 * ksl::kGridPoints];
+    __shared__ double s_obj[2][kMcObjDoubles + 1];
     __shared__ double sm[kMcThreads / 32][2 * KSL_NMOMENT];
     __shared__ unsigned long long s_hits, s_errs;
+    for (int q = threadIdx.x; q < 2 * ksl::kGridPoints; q += kMcThreads) s_grid[q] = ksl::kGridSinCos[q];
+    if (threadIdx.x < kMcObjDoubles) {
+        s_obj[0][threadIdx.x] = reinterpret_cast<const double *>(&tgt)[threadIdx.x];
+        s_obj[1][threadIdx.x] = reinterpret_cast<const double *>(&chs)[threadIdx.x];
+    }
     if (threadIdx.x == 0) { s_hits = 0; s_errs = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, obj = lane & 1;
+    const double *o = s_obj[obj];
+#if KSL_MC_SMEM_ACC
+    __shared__ double s_acc[KSL_NMOMENT * kMcThreads];
+    double *acc = s_acc + threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < KSL_NMOMENT; ++q) acc[q * kMcThreads] = 0.0;
+#else
+    double acc[KSL_NMOMENT];
+#pragma unroll
+    for (int q = 0; q < KSL_NMOMENT; ++q) acc[q] = 0.0;
+#endif
+    unsigned int hits = 0, errs = 0;
+    const long long warps_total = (long long)gridDim.x * (kMcThreads / 32);
+    for (long long it = (long long)blockIdx.x * (kMcThreads / 32) + (threadIdx.x >> 5); it * 16 < n; it += warps_total) {
+        const long long i = it * 16 + (lane >> 1);
+        const bool active = i < n;
+        const unsigned long long g = (unsigned long long)(offset + (active ? i : 0));
+        double z[6], el[7], x[6];
+        normals6(seed, g, (unsigned int)obj, z);
+        mc_elements(o, z, mu, el);
+        int ierr;
+        const bool ok = ksl::sgp4_init_state_fast(el, o[28], x, x + 3, s_grid, &ierr);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) x[q] *= 1e3;
+        const bool ok_pair = ok && (__shfl_xor_sync(0xffffffffu, ok ? 1 : 0, 1) != 0);
+        const unsigned int declined = __ballot_sync(0xffffffffu, active && !ok_pair);
+        if (declined && lane == 0) {
+            masks[it] = declined;
+            masks[-1] = 1u;          // "some sample needs the exact route" (the word in front of the masks)
+        }
+        // miss distance: target minus chaser, in the oracle's arithmetic; both lanes of the pair hold it, the even one counts
+        const double dx = ksl::add_rn(x[0], -__shfl_xor_sync(0xffffffffu, x[0], 1));
+        const double dy = ksl::add_rn(x[1], -__shfl_xor_sync(0xffffffffu, x[1], 1));
+        const double dz = ksl::add_rn(x[2], -__shfl_xor_sync(0xffffffffu, x[2], 1));
+        const int e_pair = ierr | __shfl_xor_sync(0xffffffffu, ierr, 1);
+        if (active && ok_pair) {
+            if (obj == 0) {
+                hits += (ksl::sqdist3(dx, dy, dz) < thr2) ? 1u : 0u;
+                errs += e_pair ? 1u : 0u;
+            }
+#if KSL_MC_SMEM_ACC
+            moments_add_strided<kMcThreads>(acc, x, o + 29);
+#else
+            moments_add(acc, x, o + 29);
+#endif
+            if (dump && i < n_dump) {
+                double *d = dump + i * 26;
+#pragma unroll
+                for (int q = 0; q < 7; ++q) d[obj * 7 + q] = el[q];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) d[14 + obj * 6 + q] = x[q];
+            }
+        }
+    }
+    // even lanes hold target moments, odd lanes chaser moments: reduce over the 16 lanes of each parity
 #pragma unroll
     for (int q = 0; q < KSL_NMOMENT; ++q) {
-        double a = acc_t[q], b = acc_c[q];
-        for (int d = 16; d > 0; d >>= 1) {
-            a += __shfl_down_sync(0xffffffffu, a, d);
-            b += __shfl_down_sync(0xffffffffu, b, d);
-        }
-        if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5][q] = a; sm[threadIdx.x >> 5][KSL_NMOMENT + q] = b; }
+#if KSL_MC_SMEM_ACC
+        const double v = lanes_sum<16, 2>(acc[q * kMcThreads]);
+#else
+        const double v = lanes_sum<16, 2>(acc[q]);
+#endif
+        if (lane < 2) sm[threadIdx.x >> 5][lane * KSL_NMOMENT + q] = v;
     }
-    for (int d = 16; d > 0; d >>= 1) {
-        hits += __shfl_down_sync(0xffffffffu, hits, d);
-        errs += __shfl_down_sync(0xffffffffu, errs, d);
-    }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) {
-        if (hits) atomicAdd(&s_hits, hits);
-        if (errs) atomicAdd(&s_errs, errs);
+    hits = __reduce_add_sync(0xffffffffu, hits);
+    errs = __reduce_add_sync(0xffffffffu, errs);
+    if (lane == 0) {
+        if (hits) atomicAdd(&s_hits, (unsigned long long)hits);
+        if (errs) atomicAdd(&s_errs, (unsigned long long)errs);
     }
     __syncthreads();
     if (threadIdx.x < 2 * KSL_NMOMENT) {
@@ -1042,6 +1175,65 @@ __global__ void __launch_bounds__(kMcThreads) k_mc_pc(const McObject tgt, const 
     if (threadIdx.x == 0) {
         if (s_hits) atomicAdd(count, s_hits);
         if (s_errs) atomicAdd(nerr, s_errs);
+    }
+}
+
+// the samples k_mc_pc marked: both objects on the exact route (same draws, same elements).  One thread per mask word.
+__global__ void __launch_bounds__(kExactThreads) k_mc_pc_exact(const McObject tgt, const McObject chs, unsigned long long seed,
+                                                               long long offset, long long n, double thr2, double mu,
+                                                               unsigned long long *__restrict__ count, double *__restrict__ partial,
+                                                               const unsigned int *__restrict__ masks, unsigned long long *__restrict__ nerr,
+                                                               double *__restrict__ dump, long long n_dump) {
+    __shared__ double sm[kExactThreads / 32][2 * KSL_NMOMENT];
+    double acc_t[KSL_NMOMENT], acc_c[KSL_NMOMENT];
+    for (int q = 0; q < KSL_NMOMENT; ++q) { acc_t[q] = 0.0; acc_c[q] = 0.0; }
+    unsigned long long hits = 0, errs = 0;
+    const long long n_it = (masks[-1] != 0u) ? (n + 15) / 16 : 0;     // nothing marked: only the (zero) partial row is written
+    for (long long it = (long long)blockIdx.x * kExactThreads + threadIdx.x; it < n_it; it += (long long)gridDim.x * kExactThreads) {
+        unsigned int m = masks[it] & 0x55555555u;     // one bit per pair (both lanes of a declined pair voted)
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const long long i = it * 16 + (b >> 1);
+            const unsigned long long g = (unsigned long long)(offset + i);
+            double z[6], el_t[7], el_c[7], xt[6], xc[6];
+            normals6(seed, g, 0u, z);
+            mc_elements(reinterpret_cast<const double *>(&tgt), z, mu, el_t);
+            const int e0 = ksl::sgp4_init_state_exact(el_t, tgt.tsince, xt, xt + 3);
+            normals6(seed, g, 1u, z);
+            mc_elements(reinterpret_cast<const double *>(&chs), z, mu, el_c);
+            const int e1 = ksl::sgp4_init_state_exact(el_c, chs.tsince, xc, xc + 3);
+            for (int q = 0; q < 6; ++q) { xt[q] *= 1e3; xc[q] *= 1e3; }
+            const double dx = ksl::add_rn(xt[0], -xc[0]), dy = ksl::add_rn(xt[1], -xc[1]), dz = ksl::add_rn(xt[2], -xc[2]);
+            hits += (ksl::sqdist3(dx, dy, dz) < thr2) ? 1u : 0u;
+            errs += (e0 | e1) ? 1u : 0u;
+            if (finite6(xt)) moments_add(acc_t, xt, tgt.ref);
+            if (finite6(xc)) moments_add(acc_c, xc, chs.ref);
+            if (dump && i < n_dump) {
+                double *d = dump + i * 26;
+                for (int q = 0; q < 7; ++q) { d[q] = el_t[q]; d[7 + q] = el_c[q]; }
+                for (int q = 0; q < 6; ++q) { d[14 + q] = xt[q]; d[20 + q] = xc[q]; }
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    for (int q = 0; q < KSL_NMOMENT; ++q) {
+        const double a = lanes_sum<16, 1>(acc_t[q]), b = lanes_sum<16, 1>(acc_c[q]);
+        if (lane == 0) { sm[threadIdx.x >> 5][q] = a; sm[threadIdx.x >> 5][KSL_NMOMENT + q] = b; }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        hits += __shfl_xor_sync(0xffffffffu, hits, d);
+        errs += __shfl_xor_sync(0xffffffffu, errs, d);
+    }
+    if (lane == 0) {
+        if (hits) atomicAdd(count, hits);
+        if (errs) atomicAdd(nerr, errs);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * KSL_NMOMENT) {
+        double v = 0.0;
+        for (int w = 0; w < kExactThreads / 32; ++w) v += sm[w][threadIdx.x];
+        partial[(long long)blockIdx.x * 2 * KSL_NMOMENT + threadIdx.x] = v;
     }
 }
 
@@ -1671,16 +1863,12 @@ int ksl_screen_summary(const int64_t *i_conj, const double *d_min, const int32_t
     return KSL_OK;
 }
 
-static long long tca_blocks(int64_t n, int sms) {
-    long long blocks = (n + kTcaThreads - 1) / kTcaThreads;
-    const long long cap = (long long)sms * 4;
-    if (blocks > cap) blocks = cap;
-    return blocks < 1 ? 1 : blocks;
-}
+// Monte Carlo kernels: rows of partial moments (hot kernel: <= kMcMaxRows CTAs, exact-route kernel: kMcExactRows) + masks
+constexpr int kMcMaxRows = 1024, kMcExactRows = 64;
 
 int64_t ksl_tca_moments_ws(int64_t n) {
-    (void)n;
-    return (int64_t)sizeof(double) * KSL_NMOMENT * 4096 + 64;
+    const size_t words = (size_t)((n > 0 ? n : 0) + 31) / 32 + 8;
+    return (int64_t)(sizeof(double) * KSL_NMOMENT * (kMcMaxRows + kMcExactRows) + sizeof(unsigned int) * words + 256);
 }
 
 int ksl_tca_moments(const double *elems, int64_t n, double tsince, const double *ref_state_m, double *states_m,
@@ -1690,14 +1878,26 @@ int ksl_tca_moments(const double *elems, int64_t n, double tsince, const double 
     int sms = 0;
     int rc = sm_count(&sms);
     if (rc) return rc;
-    long long blocks = tca_blocks(n, sms);
-    if (blocks > 4096) blocks = 4096;
+    long long blocks = (n + kTcaThreads - 1) / kTcaThreads;
+    if (blocks > (long long)sms * 3) blocks = (long long)sms * 3;
+    if (blocks > kMcMaxRows) blocks = kMcMaxRows;
+    if (blocks < 1) blocks = 1;
+    const long long words = (n + 31) / 32;
+    long long xblocks = (words + kExactThreads - 1) / kExactThreads;
+    if (xblocks > kMcExactRows) xblocks = kMcExactRows;
+    if (xblocks < 1) xblocks = 1;
     double *partial = reinterpret_cast<double *>(workspace);
+    unsigned int *masks = reinterpret_cast<unsigned int *>(partial + (size_t)KSL_NMOMENT * (kMcMaxRows + kMcExactRows)) + 4;
     KSL_CUDA(cudaMemsetAsync(err_count, 0, sizeof(int64_t), S(stream)));
-    k_tca_moments<<<(unsigned)blocks, kTcaThreads, 0, S(stream)>>>(elems, n, tsince, ref_state_m, states_m, partial,
+    KSL_CUDA(cudaMemsetAsync(masks - 4, 0, sizeof(unsigned int) * (size_t)(words + 4), S(stream)));
+    k_tca_moments<<<(unsigned)blocks, kTcaThreads, 0, S(stream)>>>(elems, n, tsince, ref_state_m, states_m, partial, masks,
                                                                    reinterpret_cast<unsigned long long *>(err_count));
     KSL_LAUNCH_CHECK();
-    k_moments_final<<<1, 32, 0, S(stream)>>>(partial, (int)blocks, KSL_NMOMENT, moments);
+    k_tca_moments_exact<<<(unsigned)xblocks, kExactThreads, 0, S(stream)>>>(elems, n, tsince, ref_state_m, states_m,
+                                                                            partial + (size_t)KSL_NMOMENT * blocks, masks,
+                                                                            reinterpret_cast<unsigned long long *>(err_count));
+    KSL_LAUNCH_CHECK();
+    k_moments_final<<<1, 32 * KSL_NMOMENT, 0, S(stream)>>>(partial, (int)(blocks + xblocks), KSL_NMOMENT, moments);
     KSL_LAUNCH_CHECK();
     return KSL_OK;
 }
@@ -1755,8 +1955,8 @@ int ksl_propagate_upsample(const double *consts, double epoch_mjd, const double 
 }
 
 int64_t ksl_mc_pc_ws(int64_t n) {
-    (void)n;
-    return (int64_t)sizeof(double) * 2 * KSL_NMOMENT * 2048 + 64;
+    const size_t words = (size_t)((n > 0 ? n : 0) + 15) / 16 + 8;
+    return (int64_t)(sizeof(double) * 2 * KSL_NMOMENT * (kMcMaxRows + kMcExactRows) + sizeof(unsigned int) * words + 256);
 }
 
 int ksl_mc_pc(const double *mean_t, const double *chol_t, double bstar_t, double tsince_t, const double *ref_t,
@@ -1774,15 +1974,25 @@ int ksl_mc_pc(const double *mean_t, const double *chol_t, double bstar_t, double
     for (int i = 0; i < 6; ++i) { t.mean[i] = mean_t[i]; c.mean[i] = mean_c[i]; t.ref[i] = ref_t[i]; c.ref[i] = ref_c[i]; }
     for (int i = 0; i < 21; ++i) { t.chol[i] = chol_t[i]; c.chol[i] = chol_c[i]; }
     t.bstar = bstar_t; t.tsince = tsince_t; c.bstar = bstar_c; c.tsince = tsince_c;
-    long long blocks = (n + kMcThreads - 1) / kMcThreads;
-    const long long cap = (long long)sms * 4 < 2048 ? (long long)sms * 4 : 2048;
-    if (blocks > cap) blocks = cap;
+    long long blocks = (2 * n + kMcThreads - 1) / kMcThreads;     // two lanes per sample
+    if (blocks > (long long)sms * KSL_MC_MIN_CTAS) blocks = (long long)sms * KSL_MC_MIN_CTAS;
+    if (blocks > kMcMaxRows) blocks = kMcMaxRows;
     if (blocks < 1) blocks = 1;
+    const long long words = (n + 15) / 16;
+    long long xblocks = (words + kExactThreads - 1) / kExactThreads;
+    if (xblocks > kMcExactRows) xblocks = kMcExactRows;
+    if (xblocks < 1) xblocks = 1;
     double *partial = reinterpret_cast<double *>(workspace);
+    unsigned int *masks = reinterpret_cast<unsigned int *>(partial + (size_t)2 * KSL_NMOMENT * (kMcMaxRows + kMcExactRows)) + 4;
+    KSL_CUDA(cudaMemsetAsync(masks - 4, 0, sizeof(unsigned int) * (size_t)(words + 4), S(stream)));
     k_mc_pc<<<(unsigned)blocks, kMcThreads, 0, S(stream)>>>(t, c, (unsigned long long)seed, sample_offset, n, thr_m * thr_m, mu_m3s2,
-                                                             count, partial, err_count, dump, n_dump);
+                                                             count, partial, masks, err_count, dump, n_dump);
     KSL_LAUNCH_CHECK();
-    k_moments_final<<<1, 64, 0, S(stream)>>>(partial, (int)blocks, 2 * KSL_NMOMENT, moments_t);
+    k_mc_pc_exact<<<(unsigned)xblocks, kExactThreads, 0, S(stream)>>>(t, c, (unsigned long long)seed, sample_offset, n, thr_m * thr_m,
+                                                                      mu_m3s2, count, partial + (size_t)2 * KSL_NMOMENT * blocks, masks,
+                                                                      err_count, dump, n_dump);
+    KSL_LAUNCH_CHECK();
+    k_moments_final<<<2, 32 * KSL_NMOMENT, 0, S(stream)>>>(partial, (int)(blocks + xblocks), 2 * KSL_NMOMENT, moments_t);
     KSL_LAUNCH_CHECK();
     if (moments_c != moments_t + KSL_NMOMENT)
         KSL_CUDA(cudaMemcpyAsync(moments_c, moments_t + KSL_NMOMENT, sizeof(double) * KSL_NMOMENT, cudaMemcpyDeviceToDevice, S(stream)));

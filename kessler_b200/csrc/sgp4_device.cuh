@@ -541,6 +541,126 @@ KSL_HD double wrap_pm_pi(double x) {
     return fma_rn(-fn, kWrapTab[3], fma_rn(-fn, kWrapTab[2], x));
 }
 
+// ---- sgp4init, fast form (the Monte Carlo kernels: one record per sample, used once) -----------------------------
+// Same algebra as sgp4_init with the library calls replaced by what the fast propagation path already uses:
+// sin / cos from the 512-point grid (sincos_grid, one ulp), (xke / n)^(2/3) as cbrt(.)^2 (two ulp), reciprocals as
+// rcp.approx + two Newton steps (one ulp) and divisions as multiplications by them.  The constants agree with
+// sgp4_init's to a few ulp of each FACTOR (tests/test_hostcheck.py: the secular rates, which carry the phase, to
+// 1e-15; positions after a day to 1e-9 km); k_sgp4_init and the screening kernels keep sgp4_init.
+// Requires finite elements with |angles| < 2^18; anything else produces non-finite constants, which the fast
+// propagation path refuses (the caller then takes the exact route: sgp4_init + sgp4_prop).
+KSL_HD double rcp_2(double b) {
+    double r = rcp_seed(b);
+    r = fma_rn(r, fma_rn(-b, r, 1.0), r);
+    return fma_rn(r, fma_rn(-b, r, 1.0), r);
+}
+// a / b to one ulp: quotient from the reciprocal, one residual correction
+KSL_HD double div_2(double a, double b) {
+    const double r = rcp_2(b);
+    const double q = a * r;
+    return fma_rn(fma_rn(-b, q, a), r, q);
+}
+template <typename Store>
+KSL_HD int sgp4_init_fast(const double el[7], Store &&put, const double *grid) {
+    const double no_kozai = el[0], ecco = el[1], inclo = el[2], nodeo = el[3], argpo = el[4], mo = el[5], bstar = el[6];
+    const double eccsq = ecco * ecco, omeosq = 1.0 - eccsq, rteosq = sqrt(omeosq);
+    double sinio, cosio;
+    sincos_grid(inclo, grid, sinio, cosio);
+    const double cosio2 = cosio * cosio;
+    const double cb0 = cbrt(div_2(kXke, no_kozai));
+    const double ak = cb0 * cb0;
+    const double d1 = 0.75 * kJ2 * (3.0 * cosio2 - 1.0) * rcp_2(rteosq * omeosq);
+    double del = d1 * rcp_2(ak * ak);
+    const double adel = ak * (1.0 - del * del - del * (1.0 / 3.0 + (134.0 / 81.0) * del * del));
+    del = d1 * rcp_2(adel * adel);
+    const double no = div_2(no_kozai, 1.0 + del);
+    const double cb1 = cbrt(div_2(kXke, no));
+    const double ao = cb1 * cb1;
+    const double po = ao * omeosq;
+    const double con42 = 1.0 - 5.0 * cosio2;
+    const double con41 = -con42 - cosio2 - cosio2;
+    const double posq = po * po;
+    const double rp = ao * (1.0 - ecco);
+    const bool isimp = rp < (220.0 / kRe + 1.0);
+    double sfour = 78.0 / kRe + 1.0;
+    const double qz0 = (120.0 - 78.0) / kRe;
+    double qzms24 = qz0 * qz0 * qz0 * qz0;
+    const double perige = (rp - 1.0) * kRe;
+    if (perige < 156.0) {
+        sfour = perige - 78.0;
+        if (perige < 98.0) sfour = 20.0;
+        const double q = (120.0 - sfour) * (1.0 / kRe);
+        qzms24 = q * q * q * q;
+        sfour = sfour * (1.0 / kRe) + 1.0;
+    }
+    const double pinvsq = rcp_2(posq);
+    const double tsi = rcp_2(ao - sfour);
+    const double eta = ao * ecco * tsi, etasq = eta * eta, eeta = ecco * eta;
+    const double psisq = fabs(1.0 - etasq);
+    const double tsi2 = tsi * tsi;
+    const double coef = qzms24 * (tsi2 * tsi2);
+    const double ipsisq = rcp_2(psisq);
+    const double coef1 = coef * (ipsisq * ipsisq * ipsisq) * sqrt(ipsisq);
+    const double cc2 = coef1 * no * (ao * (1.0 + 1.5 * etasq + eeta * (4.0 + etasq)) +
+                                     0.375 * kJ2 * tsi * ipsisq * con41 * (8.0 + 3.0 * etasq * (8.0 + etasq)));
+    const double cc1 = bstar * cc2;
+    const bool ecc_big = ecco > 1.0e-4;
+    const double cc3 = ecc_big ? -2.0 * coef * tsi * kJ3oJ2 * no * sinio * rcp_2(ecco) : 0.0;
+    const double x1mth2 = 1.0 - cosio2;
+    double sw, cw;
+    sincos_grid(argpo, grid, sw, cw);
+    const double c2w = fma_rn(-2.0 * sw, sw, 1.0);          // cos(2 argpo)
+    const double cc4 = 2.0 * no * coef1 * ao * omeosq *
+                       (eta * (2.0 + 0.5 * etasq) + ecco * (0.5 + 2.0 * etasq) -
+                        kJ2 * tsi * rcp_2(ao * psisq) *
+                            (-3.0 * con41 * (1.0 - 2.0 * eeta + etasq * (1.5 - 0.5 * eeta)) +
+                             0.75 * x1mth2 * (2.0 * etasq - eeta * (1.0 + etasq)) * c2w));
+    const double cc5 = 2.0 * coef1 * ao * omeosq * (1.0 + 2.75 * (etasq + eeta) + eeta * etasq);
+    const double cosio4 = cosio2 * cosio2;
+    const double temp1 = 1.5 * kJ2 * pinvsq * no;
+    const double temp2 = 0.5 * temp1 * kJ2 * pinvsq;
+    const double temp3 = -0.46875 * kJ4 * pinvsq * pinvsq * no;
+    const double mdot = no + 0.5 * temp1 * rteosq * con41 + 0.0625 * temp2 * rteosq * (13.0 - 78.0 * cosio2 + 137.0 * cosio4);
+    const double argpdot = -0.5 * temp1 * con42 + 0.0625 * temp2 * (7.0 - 114.0 * cosio2 + 395.0 * cosio4) +
+                           temp3 * (3.0 - 36.0 * cosio2 + 49.0 * cosio4);
+    const double xhdot1 = -temp1 * cosio;
+    const double nodedot = xhdot1 + (0.5 * temp2 * (4.0 - 19.0 * cosio2) + 2.0 * temp3 * (3.0 - 7.0 * cosio2)) * cosio;
+    const double omgcof = bstar * cc3 * cw;
+    const double xmcof = ecc_big ? -kX2o3 * coef * bstar * rcp_2(eeta) : 0.0;
+    const double nodecf = 3.5 * omeosq * xhdot1 * cc1;
+    const double t2cof = 1.5 * cc1;
+    const double xl_den = (fabs(cosio + 1.0) > 1.5e-12) ? (1.0 + cosio) : 1.5e-12;
+    const double xlcof = -0.25 * kJ3oJ2 * sinio * (3.0 + 5.0 * cosio) * rcp_2(xl_den);
+    const double aycof = -0.5 * kJ3oJ2 * sinio;
+    double smo, cmo;
+    sincos_grid(mo, grid, smo, cmo);
+    const double delmotemp = 1.0 + eta * cmo;
+    const double delmo = delmotemp * delmotemp * delmotemp;
+    const double x7thm1 = 7.0 * cosio2 - 1.0;
+    double d2 = 0, d3 = 0, d4 = 0, t3cof = 0, t4cof = 0, t5cof = 0;
+    if (!isimp) {
+        const double cc1sq = cc1 * cc1;
+        d2 = 4.0 * ao * tsi * cc1sq;
+        const double temp = d2 * tsi * cc1 * (1.0 / 3.0);
+        d3 = (17.0 * ao + sfour) * temp;
+        d4 = 0.5 * temp * ao * tsi * (221.0 * ao + 31.0 * sfour) * cc1;
+        t3cof = d2 + 2.0 * cc1sq;
+        t4cof = 0.25 * (3.0 * d3 + cc1 * (12.0 * d2 + 10.0 * cc1sq));
+        t5cof = 0.2 * (3.0 * d4 + 12.0 * cc1 * d3 + 6.0 * d2 * d2 + 15.0 * cc1sq * (2.0 * d2 + cc1sq));
+    }
+    put(KSL_C_NO, no); put(KSL_C_ECCO, ecco); put(KSL_C_INCLO, inclo); put(KSL_C_NODEO, nodeo);
+    put(KSL_C_ARGPO, argpo); put(KSL_C_MO, mo); put(KSL_C_BSTAR, bstar); put(KSL_C_MDOT, mdot);
+    put(KSL_C_ARGPDOT, argpdot); put(KSL_C_NODEDOT, nodedot); put(KSL_C_NODECF, nodecf); put(KSL_C_CC1, cc1);
+    put(KSL_C_CC4, cc4); put(KSL_C_CC5, cc5); put(KSL_C_T2COF, t2cof); put(KSL_C_OMGCOF, omgcof);
+    put(KSL_C_XMCOF, xmcof); put(KSL_C_ETA, eta); put(KSL_C_DELMO, delmo); put(KSL_C_SINMAO, smo);
+    put(KSL_C_D2, d2); put(KSL_C_D3, d3); put(KSL_C_D4, d4); put(KSL_C_T3COF, t3cof); put(KSL_C_T4COF, t4cof);
+    put(KSL_C_T5COF, t5cof); put(KSL_C_AYCOF, aycof); put(KSL_C_XLCOF, xlcof); put(KSL_C_CON41, con41);
+    put(KSL_C_X1MTH2, x1mth2); put(KSL_C_X7THM1, x7thm1); put(KSL_C_ISIMP, isimp ? 1.0 : 0.0);
+    put(KSL_C_COSIO, cosio); put(KSL_C_SINIO, sinio); put(KSL_C_AOBASE, ao); put(KSL_C_PAD, 0.0);
+    if (!(no > 0.0) || !(no < 1.0e300)) return KSL_ERR_DEEPSPACE;   // NaN / inf / non-positive
+    return (225.0 * no <= kTwoPi) ? KSL_ERR_DEEPSPACE : 0;
+}
+
 // The fast path reads a FAST RECORD: the 36 public constants followed by products sgp4_prop rebuilds at
 // every call (prepare_fast_record fills them once per record, in the kernel's shared-memory copy).
 enum {
@@ -807,6 +927,16 @@ KSL_HD int sgp4_init_state(const double el[7], double t, double r[3], double v[3
     r[0] = rx[0]; r[1] = rx[1]; r[2] = rx[2];
     v[0] = vx[0]; v[1] = vx[1]; v[2] = vx[2];
     return e2;
+}
+
+// sgp4init (fast form) + full state, everything in registers and nothing out of line: `ok` false = the sample needs the
+// exact route (sgp4_init + sgp4_prop), nothing usable was written.  *err: sgp4init's flag (deep space).
+KSL_HD bool sgp4_init_state_fast(const double el[7], double t, double r[3], double v[3], const double *grid, int *err) {
+    double c[KSL_NCONST];
+    *err = sgp4_init_fast(el, [&](int k, double val) { c[k] = val; }, grid);
+    auto ld = [&](int k) { return c[k]; };
+    const FastView<decltype(ld)> view{ld, c[KSL_C_ISIMP] != 0.0};
+    return sgp4_prop_fast_rv<true>(view, t, r, v, grid);
 }
 
 // position at t through the fast path, falling back to the exact path when needed (c: masked record).  The exact path

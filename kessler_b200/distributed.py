@@ -34,38 +34,60 @@ def shard_range(n_total, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def _world():
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def exchange_packed(ints, sums, mins=None):
+    """The one collective of this package: every rank contributes integer counts (summed exactly), FP64 partial
+    sums (added in RANK ORDER, so the result does not depend on the reduction tree) and FP64 minima, packed into
+    ONE int64 buffer (the doubles travel as their bit patterns) and exchanged with a single all-gather -- <= 1 KB per
+    rank, latency-bound.  Returns new tensors (ints_total, sums_total, mins_total | None); identical on every rank."""
+    if _world() == 1:
+        return ints, sums, mins
+    ki, ks = ints.numel(), sums.numel()
+    pieces = [ints.reshape(-1).to(torch.int64), sums.reshape(-1).contiguous().view(torch.int64)]
+    if mins is not None:
+        pieces.append(mins.reshape(-1).contiguous().view(torch.int64))
+    buf = torch.cat(pieces)
+    parts = [torch.empty_like(buf) for _ in range(_world())]
+    dist.all_gather(parts, buf)
+    ints_out = parts[0][:ki].clone()
+    sums_out = parts[0][ki:ki + ks].clone().view(torch.float64)
+    mins_out = parts[0][ki + ks:].clone().view(torch.float64) if mins is not None else None
+    for p in parts[1:]:
+        ints_out += p[:ki]
+        sums_out += p[ki:ki + ks].view(torch.float64)
+        if mins is not None:
+            mins_out = torch.minimum(mins_out, p[ki + ks:].view(torch.float64))
+    return ints_out.reshape(ints.shape), sums_out.reshape(sums.shape), (mins_out.reshape(mins.shape) if mins is not None else None)
+
+
 def allreduce_summary(counts, moments):
     """In-place all-reduce of a screen summary: counts int64[8] SUM (bit-exact, associative);
-    moments f64[4] = (n_valid, sum d, sum d^2) SUM and min d MIN."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    moments f64[4] = (n_valid, sum d, sum d^2) SUM and min d MIN.  One collective."""
+    if _world() == 1:
         return counts, moments
-    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    head, tail = moments[:3].contiguous(), moments[3:].contiguous()
-    dist.all_reduce(head, op=dist.ReduceOp.SUM)
-    dist.all_reduce(tail, op=dist.ReduceOp.MIN)
-    moments[:3] = head
-    moments[3:] = tail
+    c, s, m = exchange_packed(counts, moments[:3], moments[3:])
+    counts.copy_(c)
+    moments[:3] = s
+    moments[3:] = m
     return counts, moments
 
 
 def allreduce_counts(counts):
     """SUM all-reduce of an integer count tensor (collision counts): exact."""
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if _world() > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     return counts
 
 
 def allgather_moments(moments):
-    """Shifted moments about a shared reference state add across ranks.  For a result that does
-    not depend on reduction order, gather the per-rank partials and sum them in rank order."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    """Shifted moments about a shared reference state add across ranks, summed in rank order."""
+    if _world() == 1:
         return moments
-    parts = [torch.empty_like(moments) for _ in range(dist.get_world_size())]
-    dist.all_gather(parts, moments.contiguous())
-    out = parts[0].clone()
-    for p in parts[1:]:
-        out += p
-    return out
+    _, s, _ = exchange_packed(torch.zeros(0, dtype=torch.int64, device=moments.device), moments)
+    return s
 
 
 def barrier():

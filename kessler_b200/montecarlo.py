@@ -31,27 +31,32 @@ def nominal_state_m(tle, tsince):
     return rv[0, 0].cpu().numpy() * 1e3
 
 
-def collision_probability(t_tle, t_state_m, t_cov_rtn, c_tle, c_state_m, c_cov_rtn, time_ca_mjd, n_total,
-                          collision_threshold=70.0, seed=2, n_dump=0, chunk=1 << 26):
-    """Returns dict(pc, count, n, mean_t, cov_rtn_t, mean_c, cov_rtn_c, err_count[, dump]).  Call from every rank
-    of an initialised process group (or from a single process): each rank runs its shard, the result is
-    identical on all ranks and -- because the generator is keyed by the global sample index -- the count does
-    not depend on the number of ranks."""
-    rank, world = (torch.distributed.get_rank(), torch.distributed.get_world_size()) if (
-        torch.distributed.is_available() and torch.distributed.is_initialized()) else (0, 1)
-    lo, hi = D.shard_range(n_total, rank, world)
+def prepare_pair(t_tle, t_state_m, t_cov_rtn, c_tle, c_state_m, c_cov_rtn, time_ca_mjd):
+    """Everything of a collision-probability run that does not depend on the samples: element distributions
+    (model.py:461-497), times since epoch, reference states.  Host algebra + two tiny launches; done once."""
     mean_t, L_t = element_distribution(t_tle, t_state_m, t_cov_rtn)
     mean_c, L_c = element_distribution(c_tle, c_state_m, c_cov_rtn)
     ts_t = (time_ca_mjd - t_tle.date_mjd) * 1440.0
     ts_c = (time_ca_mjd - c_tle.date_mjd) * 1440.0
-    ref_t, ref_c = nominal_state_m(t_tle, ts_t), nominal_state_m(c_tle, ts_c)
+    return dict(mean_t=mean_t, L_t=L_t, bstar_t=t_tle._bstar, ts_t=ts_t, ref_t=nominal_state_m(t_tle, ts_t),
+                mean_c=mean_c, L_c=L_c, bstar_c=c_tle._bstar, ts_c=ts_c, ref_c=nominal_state_m(c_tle, ts_c))
+
+
+def run_prepared(pp, n_total, collision_threshold=70.0, seed=2, n_dump=0, chunk=1 << 28, to_host=True):
+    """This rank's shard of [0, n_total) through ksl_mc_pc, then the ONE collective (counts exact, moments added in
+    rank order).  With to_host=False returns the device tensors (packed int64 [count, err], moments f64 [56]) without
+    any host synchronisation -- what bench.py times; otherwise the finished dict."""
+    rank, world = (torch.distributed.get_rank(), torch.distributed.get_world_size()) if (
+        torch.distributed.is_available() and torch.distributed.is_initialized()) else (0, 1)
+    lo, hi = D.shard_range(n_total, rank, world)
     count = err = None
     mom_t = mom_c = None
     dump = None
     for start in range(lo, hi, chunk):
         n = min(chunk, hi - start)
-        r = engine.mc_pc(mean_t, L_t, t_tle._bstar, ts_t, ref_t, mean_c, L_c, c_tle._bstar, ts_c, ref_c, seed, start, n,
-                         collision_threshold, n_dump=(n_dump if start == lo else 0), count=count, err_count=err)
+        r = engine.mc_pc(pp["mean_t"], pp["L_t"], pp["bstar_t"], pp["ts_t"], pp["ref_t"], pp["mean_c"], pp["L_c"], pp["bstar_c"],
+                         pp["ts_c"], pp["ref_c"], seed, start, n, collision_threshold, n_dump=(n_dump if start == lo else 0),
+                         count=count, err_count=err)
         count, err = r["count"], r["err_count"]
         mom_t = r["moments_t"].clone() if mom_t is None else mom_t + r["moments_t"]
         mom_c = r["moments_c"].clone() if mom_c is None else mom_c + r["moments_c"]
@@ -61,17 +66,28 @@ def collision_probability(t_tle, t_state_m, t_cov_rtn, c_tle, c_state_m, c_cov_r
     if count is None:   # empty shard
         count, err = torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(1, dtype=torch.int64, device=dev)
         mom_t, mom_c = torch.zeros(28, dtype=torch.float64, device=dev), torch.zeros(28, dtype=torch.float64, device=dev)
-    packed = torch.cat([count, err])
-    D.allreduce_counts(packed)
-    mom_t, mom_c = D.allgather_moments(mom_t), D.allgather_moments(mom_c)
-    mean_state_t, cov_t = moments_to_mean_cov_rtn(mom_t.cpu().numpy(), ref_t)
-    mean_state_c, cov_c = moments_to_mean_cov_rtn(mom_c.cpu().numpy(), ref_c)
-    cnt = int(packed[0])
-    out = dict(pc=cnt / float(n_total), count=cnt, n=int(n_total), err_count=int(packed[1]), mean_t=mean_state_t.reshape(2, 3),
+    packed, mom, _ = D.exchange_packed(torch.cat([count, err]), torch.cat([mom_t, mom_c]))
+    if not to_host:
+        return packed, mom
+    host = torch.cat([packed.to(torch.float64), mom]).cpu().numpy()       # ONE device -> host read
+    mean_state_t, cov_t = moments_to_mean_cov_rtn(host[2:30], pp["ref_t"])
+    mean_state_c, cov_c = moments_to_mean_cov_rtn(host[30:58], pp["ref_c"])
+    cnt, nerr = int(host[0]), int(host[1])          # (counts < 2^53: exact in a double)
+    out = dict(pc=cnt / float(n_total), count=cnt, n=int(n_total), err_count=nerr, mean_t=mean_state_t.reshape(2, 3),
                cov_rtn_t=cov_t, mean_c=mean_state_c.reshape(2, 3), cov_rtn_c=cov_c, shard=(lo, hi))
     if dump is not None:
         out["dump"] = dump
     return out
+
+
+def collision_probability(t_tle, t_state_m, t_cov_rtn, c_tle, c_state_m, c_cov_rtn, time_ca_mjd, n_total,
+                          collision_threshold=70.0, seed=2, n_dump=0, chunk=1 << 28):
+    """Returns dict(pc, count, n, mean_t, cov_rtn_t, mean_c, cov_rtn_c, err_count[, dump]).  Call from every rank
+    of an initialised process group (or from a single process): each rank runs its shard, the result is
+    identical on all ranks and -- because the generator is keyed by the global sample index -- the count does
+    not depend on the number of ranks."""
+    pp = prepare_pair(t_tle, t_state_m, t_cov_rtn, c_tle, c_state_m, c_cov_rtn, time_ca_mjd)
+    return run_prepared(pp, n_total, collision_threshold, seed, n_dump, chunk)
 
 
 def all_pairs_probability(t_xyz, c_xyz, collision_threshold=70.0):

@@ -20,6 +20,28 @@ int hc_sgp4_init(const double *elems, int64_t n, double *consts, int32_t *err) {
     return 0;
 }
 
+int hc_sgp4_init_fast(const double *elems, int64_t n, double *consts, int32_t *err) {
+    for (int64_t i = 0; i < n; ++i) {
+        double el[7];
+        for (int k = 0; k < 7; ++k) el[k] = elems[k * n + i];
+        int e = ksl::sgp4_init_fast(el, [&](int k, double v) { consts[(int64_t)k * n + i] = v; }, ksl::kGridSinCos);
+        if (err) err[i] = e;
+    }
+    return 0;
+}
+
+// what the Monte Carlo kernels run per sample: fast sgp4init + fast state; ok[i] = 0 where the sample is deferred to the exact route
+int hc_init_state_fast(const double *elems, int64_t n, double tsince, double *rv, int32_t *err, int32_t *ok) {
+    for (int64_t i = 0; i < n; ++i) {
+        double el[7];
+        for (int k = 0; k < 7; ++k) el[k] = elems[k * n + i];
+        int e = 0;
+        ok[i] = ksl::sgp4_init_state_fast(el, tsince, rv + 6 * i, rv + 6 * i + 3, ksl::kGridSinCos, &e) ? 1 : 0;
+        err[i] = e;
+    }
+    return 0;
+}
+
 int hc_sgp4_prop(const double *consts, int64_t n, const double *tsince, int64_t m, int per_sample_t, int want_vel,
                  double *rv, int32_t *err) {
     for (int64_t i = 0; i < n; ++i) {

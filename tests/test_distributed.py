@@ -32,6 +32,13 @@ c = D.allreduce_counts(torch.tensor([rank + 5], dtype=torch.int64)); assert c.it
 m = torch.arange(28, dtype=torch.float64) * (rank + 1)
 g = D.allgather_moments(m); assert torch.equal(g, torch.arange(28, dtype=torch.float64) * 3)
 assert D.max_over_ranks(1.5 + rank) == 2.5
+# the packed exchange itself: exact integer sums, rank-order FP64 sums (bit patterns survive the int64 transport), minima
+ints = torch.tensor([2 ** 40 + rank, -3 * rank], dtype=torch.int64)
+sums = torch.tensor([0.1 * (rank + 1), 1e300 * (1 - rank), -0.0], dtype=torch.float64)
+mins = torch.tensor([5.0 - rank, float("inf") if rank else 7.0], dtype=torch.float64)
+i2, s2, m2 = D.exchange_packed(ints, sums, mins)
+assert i2.tolist() == [2 ** 41 + 1, -3] and s2[0].item() == 0.1 + 0.2 and s2[1].item() == 1e300 and m2.tolist() == [4.0, 7.0]
+assert ints.tolist() == [2 ** 40 + rank, -3 * rank]            # inputs untouched
 D.barrier()
 print("rank", rank, "ok")
 '''

@@ -562,6 +562,66 @@ def test_tca_moments_parity(eng):
         assert np.allclose(cov, cov_ref, rtol=1e-5, atol=1e-9 * scale.max())
 
 
+def test_mc_kernels_exact_route_for_declined_samples(eng):
+    """K4 / K6 mark the samples their in-register fast path declines and a second kernel redoes those on the exact
+    route: a catalog with every awkward branch through K4, and a K6 cloud that straddles the fast path's
+    eccentricity bound (e = 0.12), against the oracle on identical samples."""
+    from kessler_b200.stats import moments_to_mean_cov_rtn
+    el = common.synthetic_catalog(5000, seed=41)
+    c_ref, e0 = C.sgp4_init(el)
+    el = np.ascontiguousarray(el[:, e0 == 0])                       # (deep-space records: flag parity is K1's business)
+    n = el.shape[1]
+    for ts in (1440.0, -4000.0):
+        st_ref, e_ref = C.tca_states(el, ts)
+        mom, errc, st = eng.tca_moments(el, ts, st_ref[0], want_states=True)
+        mom, st = _np(mom), _np(st)
+        fin = np.isfinite(st_ref).all(axis=1)
+        assert np.array_equal(np.isfinite(st).all(axis=1), fin)
+        good = fin & (e_ref == 0)
+        assert good.sum() > 3000 and (~good).sum() > 5
+        assert np.abs(st[good, :3] - st_ref[good, :3]).max() < 1e-3          # m: the tolerance of record (1e-6 km)
+        assert np.median(np.abs(st[good, :3] - st_ref[good, :3])) < 1e-7
+        assert int(errc[0]) == int((e_ref != 0).sum())
+        assert mom[0] == fin.sum()
+        d = st[fin] - st_ref[0]
+        assert np.allclose(mom[1:7], d.sum(axis=0), rtol=1e-9, atol=1e-6 * np.abs(d).sum(axis=0).max())
+    # K6: cloud around e = 0.1195 +- 1e-3 -> a mix of fast and exact-route samples in every warp
+    from kessler_b200 import montecarlo as MC, workloads as W
+    from kessler_b200.tle import TLE
+    g = common.golden_trace()
+    t_tle = TLE([g["tles"]["t_tle"]["line1"], g["tles"]["t_tle"]["line2"]])
+    st = MC.nominal_state_m(t_tle, 0.0).reshape(2, 3)
+    mean, L = MC.element_distribution(t_tle, st, W.T_COV_RTN)
+    mean = mean.copy()
+    mean[0], mean[1] = 7.4e6, 0.1195
+    L = L.copy()
+    L[1, :] = 0.0
+    L[1, 1] = 1e-3
+    ts = 300.0
+    ref = np.zeros(6)
+    nsamp = 40000
+    r = eng.mc_pc(mean, L, t_tle._bstar, ts, ref, mean, L * 1.5, t_tle._bstar, ts, ref, 11, 5, nsamp, 3000.0, n_dump=nsamp)
+    d = r["dump"].cpu().numpy()
+    el_t, el_c, x_t, x_c = d[:, :7].T.copy(), d[:, 7:14].T.copy(), d[:, 14:20], d[:, 20:26]
+    assert 0.2 < (el_t[1] > 0.12).mean() < 0.5 and 0.2 < (el_c[1] > 0.12).mean() < 0.6
+    ref_t, et = C.tca_states(el_t, ts)
+    ref_c, ec = C.tca_states(el_c, ts)
+    assert np.abs(x_t[:, :3] - ref_t[:, :3]).max() < 1e-3 and np.abs(x_c[:, :3] - ref_c[:, :3]).max() < 1e-3
+    want = C.pc_count(np.ascontiguousarray(x_t[:, :3].T), np.ascontiguousarray(x_c[:, :3].T), 3000.0, 1)
+    assert int(r["count"][0]) == want and 0 < want < nsamp
+    assert int(r["err_count"][0]) == int(((et | ec) != 0).sum())
+    mt, mc_ = r["moments_t"].cpu().numpy(), r["moments_c"].cpu().numpy()
+    assert mt[0] == nsamp and mc_[0] == nsamp
+    assert np.allclose(mt[1:7], x_t.sum(axis=0), rtol=1e-10) and np.allclose(mc_[1:7], x_c.sum(axis=0), rtol=1e-10)
+    assert np.allclose(mt[7], (x_t[:, 0] ** 2).sum(), rtol=1e-10) and np.allclose(mc_[27], (x_c[:, 5] ** 2).sum(), rtol=1e-10)
+    # the same draws whatever the split of the sample range (the exact route regenerates them from the global index)
+    a = eng.mc_pc(mean, L, t_tle._bstar, ts, ref, mean, L * 1.5, t_tle._bstar, ts, ref, 11, 5, 999, 3000.0, n_dump=999)
+    b = eng.mc_pc(mean, L, t_tle._bstar, ts, ref, mean, L * 1.5, t_tle._bstar, ts, ref, 11, 5 + 999, nsamp - 999, 3000.0, n_dump=64,
+                  count=a["count"], err_count=a["err_count"])
+    assert int(b["count"][0]) == want
+    assert np.array_equal(a["dump"].cpu().numpy(), d[:999]) and np.array_equal(b["dump"].cpu().numpy(), d[999:999 + 64])
+
+
 def test_pc_count_bit_exact(eng):
     """model.py:432-437 at the reference size (10^4 x 10^4) and ragged sizes: integer-exact."""
     rng = np.random.default_rng(4)

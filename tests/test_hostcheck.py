@@ -81,6 +81,50 @@ def test_device_sgp4init_matches_oracle(hc):
         assert rel[k].max() < 1e-15, S_NAMES[k]
 
 
+def test_device_fast_sgp4init_matches_oracle(hc):
+    """sgp4_init_fast (Monte Carlo kernels): the oracle's constants to a few ulp per factor, the phase-carrying ones to
+    1e-15, identical branch flags; and fast init + fast state (sgp4_init_state_fast) against the oracle's init + state
+    one and five days from the epoch."""
+    el, _ = common.population_elems()
+    gt, _, gc, _, _ = common.golden_pair()
+    el = np.concatenate([gt[:, None], gc[:, None], el, common.synthetic_catalog(2000, seed=17)], axis=1)
+    rng = np.random.default_rng(3)
+    mc = common.perturbed_samples(gt, 3000, 4)          # what the kernels actually see: a cloud around one TLE
+    el = np.ascontiguousarray(np.concatenate([el, mc], axis=1))
+    n = el.shape[1]
+    c1, e1 = C.sgp4_init(el)
+    c2, e2 = np.zeros((36, n)), np.zeros(n, np.int32)
+    hc.hc_sgp4_init_fast(_p(el, D), ctypes.c_int64(n), _p(c2, D), _p(e2, I32))
+    assert (e1 == e2).all()
+    ok = e1 == 0
+    assert np.array_equal(c1[31, ok], c2[31, ok])       # isimp
+    floor = 1e-6 * np.median(np.abs(c1[:, ok]), axis=1, keepdims=True)
+    for name in ("sinio", "xlcof", "aycof", "omgcof"):
+        floor[list(S_NAMES).index(name)] = max(floor[list(S_NAMES).index(name)], 1e-3)
+    rel = np.abs(c1[:, ok] - c2[:, ok]) / np.maximum(np.maximum(np.abs(c1[:, ok]), floor), 1e-300)
+    # (ao - s4 amplifies the two ulp of cbrt(.)^2 up to 1e3-fold in tsi^4 for perigees just above the s4 altitude)
+    assert rel.max() < 2e-11, {nm: float(r) for nm, r in zip(S_NAMES, rel.max(axis=1)) if r > 1e-13}
+    for k in (0, 7, 34):                                # no, mdot, ao
+        assert rel[k].max() < 1e-15, S_NAMES[k]
+    for k in (8, 9):                                    # argpdot, nodedot: absolute, as phase after 5e4 min
+        assert np.abs(c1[k, ok] - c2[k, ok]).max() * 5.0e4 < 1e-11, S_NAMES[k]
+    for ts in (1440.0, -7200.0):
+        ref, ea = C.tca_states(el, ts)                  # metres
+        rv, err, used = np.zeros((n, 6)), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        hc.hc_init_state_fast(_p(el, D), ctypes.c_int64(n), ctypes.c_double(ts), _p(rv, D), _p(err, I32), _p(used, I32))
+        good = ok & (ea == 0) & (used == 1)
+        assert good.sum() > 0.85 * ok.sum() and used[-3000:].all()
+        # metres.  Tolerance of record: 1e-6 km = 1e-3 m.  The catalog's extremes (perigee 150 km: drag terms amplify the
+        # ulps of ao 1e3-fold; e ~ 0.12) reach 1e-4 m after five days; the cloud around a real TLE stays below 5e-6 m
+        assert np.abs(rv[good, :3] * 1e3 - ref[good, :3]).max() < 2e-4
+        cloud = good & (np.arange(n) >= n - 3000)
+        assert np.abs(rv[cloud, :3] * 1e3 - ref[cloud, :3]).max() < 5e-6
+        assert np.median(np.abs(rv[good, :3] * 1e3 - ref[good, :3])) < 5e-8
+        assert np.abs(rv[good, 3:] * 1e3 - ref[good, 3:]).max() < 2e-7        # m/s (same extremes)
+        assert np.abs(rv[cloud, 3:] * 1e3 - ref[cloud, 3:]).max() < 5e-9
+        assert (err == e1).all()
+
+
 def test_device_sgp4_matches_oracle(hc):
     el, _ = common.population_elems()
     el = np.concatenate([el, common.synthetic_catalog(300)], axis=1)
