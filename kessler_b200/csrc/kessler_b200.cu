@@ -322,22 +322,33 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen(
             continue;
         }
         const double epoch_t = s_epoch[0], epoch_c = s_epoch[1];
+        const long long last = p.n_coarse - 1;
+        // the same choice of SGP4 form as k_screen_warp makes (near-circular records, decided per trace), so that the two
+        // work decompositions return bit-identical results
+        bool small_c, small_t = false;
+        {
+            const double t_first = p.times_coarse[0], t_last = p.times_coarse[last];
+            small_c = ksl::fast_record_is_small_e([&](int q) { return s_cc[q]; }, 1440.0 * fmax(fabs(t_first - epoch_c), fabs(t_last - epoch_c)));
+            if (!kSharedTarget) {
+                small_t = ksl::fast_record_is_small_e([&](int q) { return s_ct[q]; }, 1440.0 * fmax(fabs(t_first - epoch_t), fabs(t_last - epoch_t)));
+                small_c = small_t = (small_c && small_t);
+            }
+        }
 
         Best best;
         best_init(best);
         int e_t = 0, e_c = 0;
-        const long long last = p.n_coarse - 1;
         for (long long base = 0; base < last || base == 0; base += kScreenThreads - 1) {
             const long long k = base + tid;
             if (k <= last) {
                 const double tm = grid_in_smem ? s_times[k] : p.times_coarse[k];
                 double r[3];
-                e_c |= ksl::sgp4_position(s_cc, 1, (tm - epoch_c) * 1440.0, r, s_grid);
+                e_c |= ksl::sgp4_position(s_cc, 1, (tm - epoch_c) * 1440.0, r, s_grid, small_c);
                 s_pc[tid][0] = r[0]; s_pc[tid][1] = r[1]; s_pc[tid][2] = r[2];
                 if (kSharedTarget) {
                     r[0] = p.target_pos[3 * k]; r[1] = p.target_pos[3 * k + 1]; r[2] = p.target_pos[3 * k + 2];
                 } else {
-                    e_t |= ksl::sgp4_position(s_ct, 1, (tm - epoch_t) * 1440.0, r, s_grid);
+                    e_t |= ksl::sgp4_position(s_ct, 1, (tm - epoch_t) * 1440.0, r, s_grid, small_t);
                 }
                 s_pt[tid][0] = r[0]; s_pt[tid][1] = r[1]; s_pt[tid][2] = r[2];
             }
@@ -534,6 +545,17 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
             }
             continue;
         }
+        // near-circular records take the shorter Kepler solve (sgp4_device.cuh): decided once per trace from a bound on
+        // the eccentricity over the window, uniform over the warp
+        bool small_c, small_t = false;
+        {
+            const double t_first = grid_in_smem ? s_times[0] : __ldg(p.times_coarse), t_last = grid_in_smem ? s_times[last] : __ldg(p.times_coarse + last);
+            small_c = ksl::fast_record_is_small_e([&](int q) { return s_cc[q]; }, 1440.0 * fmax(fabs(t_first - epoch_c), fabs(t_last - epoch_c)));
+            if (!kSharedTarget) {
+                small_t = ksl::fast_record_is_small_e([&](int q) { return s_ct[q]; }, 1440.0 * fmax(fabs(t_first - epoch_t), fabs(t_last - epoch_t)));
+                small_c = small_t = (small_c && small_t);     // a mixed pair takes the general form for both (two code paths, not four)
+            }
+        }
         BestW best = {INFINITY, 0.0, kNoIndexW, kNoIndexW, kNoIndexW};
         int e_t = 0, e_c = 0;
         // lane i of a chunk evaluates epoch k = base + i and owns the segment [k-1, k] that ENDS there; lane 0
@@ -557,12 +579,18 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
                 // both fast evaluations back to back: one straight-line block with two independent
                 // dependency chains for the scheduler; the (rare) exact fallbacks come after
                 const double ts_c = (tm - epoch_c) * 1440.0, ts_t = (tm - epoch_t) * 1440.0;
-                const bool ok_c = ksl::sgp4_prop_fast([&](int q) { return s_cc[q]; }, ts_c, rc, s_grid);
-                bool ok_t = true;
+                bool ok_c, ok_t = true;
+                auto ld_c = [&](int q) { return s_cc[q]; };
+                auto ld_t = [&](int q) { return s_ct[q]; };
                 if (kSharedTarget) {
                     rt[0] = __ldg(p.target_pos + 3 * k); rt[1] = __ldg(p.target_pos + 3 * k + 1); rt[2] = __ldg(p.target_pos + 3 * k + 2);
+                    ok_c = small_c ? ksl::sgp4_prop_fast<true>(ld_c, ts_c, rc, s_grid) : ksl::sgp4_prop_fast<false>(ld_c, ts_c, rc, s_grid);
+                } else if (small_c && small_t) {     // one uniform branch per chunk; each arm is one straight-line block
+                    ok_c = ksl::sgp4_prop_fast<true>(ld_c, ts_c, rc, s_grid);
+                    ok_t = ksl::sgp4_prop_fast<true>(ld_t, ts_t, rt, s_grid);
                 } else {
-                    ok_t = ksl::sgp4_prop_fast([&](int q) { return s_ct[q]; }, ts_t, rt, s_grid);
+                    ok_c = ksl::sgp4_prop_fast<false>(ld_c, ts_c, rc, s_grid);
+                    ok_t = ksl::sgp4_prop_fast<false>(ld_t, ts_t, rt, s_grid);
                 }
                 // (through a scratch array: the out-of-line call takes an address, and rc / rt must stay in registers)
                 if (!ok_c) {

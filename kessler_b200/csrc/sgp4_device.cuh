@@ -679,7 +679,12 @@ enum {
 // algebraically the reference's with fewer intermediate roundings, ~1e-13 rad); false = assumptions violated,
 // nothing usable written: call sgp4_prop.
 // c: fast record (prepare_fast_record); grid: kGridSinCos or a copy of it; v (km/s) is written when kVel.
-template <bool kVel, typename Load>
+// small_e (a compile-time choice: the callers branch once per chunk on a flag that is uniform over the warp, so that each
+// form stays one straight-line block the scheduler can interleave with the other object's) selects the near-circular form: with
+// el2 = axnl^2 + aynl^2 < kSmallMaxEl2 (tested, like everything else, before the result is accepted) Kepler's equation
+// needs two sweeps instead of three and the series in el2 two terms instead of five; same accuracy class.
+constexpr double kSmallMaxEl2 = 1.0e-4;   // el < 0.01
+template <bool kVel, bool small_e = false, typename Load>
 KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], const double *grid) {
     // Angles that grow with t (mean anomaly, mean longitude: ~1e3 rad over the window) keep the reference's
     // own sequence of roundings -- each costs ~1e-13 rad = 1e-9 km; everything of magnitude <= 2 pi is free
@@ -747,6 +752,22 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
     const double dn = fma_rn(g, rden, qn);
     double d = fma_rn(dn * qn * -0.5, dn, dn);
     g -= d;
+    if (small_e) {
+        // |E - E0| <= el + pi / 512 < 0.0162: Halley leaves (el / 6) 0.0162^3 < 8e-9, the Newton step below -- reciprocal
+        // refined cubically, (el |d|)^3 < 5e-12 -- leaves (el / 2) (8e-9)^2 + 8e-9 x 5e-12 < 1e-19.
+        // rotation by |d| < 0.0162: sin through d^7 (d^9 / 9! < 3e-22), cos through d^6 (d^8 / 8! < 2e-19)
+        const double d2 = d * d;
+        const double ps = fma_rn(fma_rn(d2, kTrigTab[2], kTrigTab[1]), d2, kTrigTab[0]);
+        const double sd = fma_rn(ps * d2, d, d);
+        const double cd = fma_rn(fma_rn(fma_rn(d2, kTrigTab[6], kTrigTab[5]), d2, kTrigTab[4]), d2, 1.0);
+        const double s0 = se, c0 = ce;
+        se = fma_rn(s0, cd, c0 * sd);
+        ce = fma_rn(c0, cd, -(s0 * sd));
+        den = fma_rn(-se, aynl, fma_rn(-ce, axnl, 1.0));
+        const double er = fma_rn(-den, rden, 1.0);
+        rden = fma_rn(rden, fma_rn(er, er, er), rden);
+        d = fma_rn(axnl, se, fma_rn(-aynl, ce, g)) * rden;                     // |d| < 8e-9: first-order rotation, d^2 / 2 < 4e-17
+    } else {
     rotate_small(d, se, ce);
     den = fma_rn(-se, aynl, fma_rn(-ce, axnl, 1.0));
     const double er = fma_rn(-den, rden, 1.0);                                 // |er| < 0.02: the step changed den by e d
@@ -756,6 +777,7 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
     rotate_micro(d, se, ce);
     d = fma_rn(axnl, se, fma_rn(-aynl, ce, g)) * rden;
     ok = ok && abs_below_pow2(d, -30);
+    }
     const double s_prev = se;
     se = fma_rn(d, ce, se);                                                    // first-order rotation: d^2 / 2 < 5e-19
     ce = fma_rn(-d, s_prev, ce);
@@ -763,20 +785,30 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
     const double ecose = fma_rn(axnl, ce, aynl * se);
     const double esine = fma_rn(axnl, se, -(aynl * ce));
     const double el2 = fma_rn(axnl, axnl, aynl * aynl);
-    ok = ok && (el2 < kFastMaxEl2);
+    ok = ok && (el2 < (small_e ? kSmallMaxEl2 : kFastMaxEl2));
     const double omel2 = 1.0 - el2;
     const double pl = am * omel2;
     const double omecose = 1.0 - ecose;
     const double rl = am * omecose;
+    double betal, amorl;
+    if (small_e) {
+        // sqrt(1 - x) through x^2 (x^3 / 16 < 7e-14) and 1 / (1 + sqrt(1 - x)) = 1/2 + x/8 + x^2/16 (5 x^3 / 128 < 4e-14):
+        // both only enter multiplied by e^2 or J2
+        betal = fma_rn(fma_rn(el2, kSqrtTab[1], kSqrtTab[0]), el2, 1.0);
+        temp = esine * fma_rn(fma_rn(el2, 0.0625, 0.125), el2, 0.5);
+        // rden = 1 / den one (tiny) step earlier: el |d| < 1e-10 off -> one Newton step
+        amorl = fma_rn(rden, fma_rn(-omecose, rden, 1.0), rden);
+    } else {
     double bs = fma_rn(el2, kSqrtTab[4], kSqrtTab[3]);   // through x^5: 2e-13 at el2 = 0.0144, and betal only enters
     bs = fma_rn(bs, el2, kSqrtTab[2]);                  // multiplied by e^2 or J2
     bs = fma_rn(bs, el2, kSqrtTab[1]);
     bs = fma_rn(bs, el2, kSqrtTab[0]);
-    const double betal = fma_rn(bs, el2, 1.0);
+    betal = fma_rn(bs, el2, 1.0);
     temp = esine * rcp_1(1.0 + betal);                                          // enters as e * temp ~ e^2
     // am / rl = 1 / (1 - ecose): rden is that reciprocal one sweep earlier, good to 7e-6 -> cubic refinement, 3e-16
     const double ea = fma_rn(-omecose, rden, 1.0);
-    const double amorl = fma_rn(rden, fma_rn(ea, ea, ea), rden);
+    amorl = fma_rn(rden, fma_rn(ea, ea, ea), rden);
+    }
     const double sinu = amorl * (se - aynl - axnl * temp);
     const double cosu = amorl * (ce - axnl + aynl * temp);
     const double sin2u = (cosu + cosu) * sinu;
@@ -832,10 +864,18 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
     // pl < 0 is impossible with el2 < 0.0144; decay (mrt < 1) and non-finite values go to the exact path
     return ok && (mrt >= 1.0) && abs_below_pow2(mr, 996);
 }
-template <typename Load>
+template <bool kSmallE = false, typename Load>
 KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3], const double *grid) {
     double v[3];
-    return sgp4_prop_fast_rv<false>(c, t, r, v, grid);
+    return sgp4_prop_fast_rv<false, kSmallE>(c, t, r, v, grid);
+}
+// Is the near-circular form worth selecting for this record over |tsince| <= tmax?  A bound on el over the window:
+// the eccentricity and what drag can add to it, plus the long-period term of aynl (|aycof| / (a (1 - e^2)) < 1.3e-3).
+// Only a performance hint -- a wrong guess costs exact-path evaluations (el2 is tested per evaluation), never accuracy.
+template <typename Load>
+KSL_HD bool fast_record_is_small_e(Load &&c, double tmax) {
+    const double bound = c(KSL_C_ECCO) + fabs(c(KSL_F_BC4)) * tmax + 2.0 * fabs(c(KSL_F_BC5)) + 1.5e-3;
+    return bound < 0.0095;
 }
 
 // In-place preparation of a private (shared-memory / local) copy of a record, KSL_NFAST entries of `stride`
@@ -948,8 +988,9 @@ __device__ __noinline__ int sgp4_position_exact(const double *c, int stride, dou
 }
 #endif
 // c: pointer to constant 0 of the record, `stride` doubles between consecutive constants
-KSL_HD int sgp4_position(const double *c, int stride, double t, double r[3], const double *grid) {
-    if (sgp4_prop_fast([&](int k) { return c[(long long)k * stride]; }, t, r, grid)) return 0;
+KSL_HD int sgp4_position(const double *c, int stride, double t, double r[3], const double *grid, bool small_e = false) {
+    auto ld = [&](int k) { return c[(long long)k * stride]; };
+    if (small_e ? sgp4_prop_fast<true>(ld, t, r, grid) : sgp4_prop_fast<false>(ld, t, r, grid)) return 0;
 #if defined(__CUDA_ARCH__)
     return sgp4_position_exact(c, stride, t, r);
 #else

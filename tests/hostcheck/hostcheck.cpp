@@ -95,6 +95,27 @@ int hc_sgp4_position(const double *consts, int64_t n, const double *tsince, int6
     return 0;
 }
 
+// the same with the near-circular form where the record qualifies (as k_screen_warp decides it: once per record, from a
+// bound over |tsince| <= tmax); small_used[i] = 1 where it was selected
+int hc_sgp4_position_small(const double *consts, int64_t n, const double *tsince, int64_t m, double tmax, double *pos,
+                           int32_t *fast_used, int32_t *small_used) {
+    for (int64_t i = 0; i < n; ++i) {
+        double cm[ksl::KSL_NFAST];
+        for (int k = 0; k < KSL_NCONST; ++k) cm[k] = consts[(int64_t)k * n + i];
+        ksl::prepare_fast_record(cm, 1);
+        auto ld = [&](int k) { return cm[k]; };
+        const bool small = ksl::fast_record_is_small_e(ld, tmax);
+        small_used[i] = small ? 1 : 0;
+        for (int64_t j = 0; j < m; ++j) {
+            double *o = pos + (i * m + j) * 3;
+            const bool ok = small ? ksl::sgp4_prop_fast<true>(ld, tsince[j], o, ksl::kGridSinCos) : ksl::sgp4_prop_fast<false>(ld, tsince[j], o, ksl::kGridSinCos);
+            fast_used[i * m + j] = ok ? 1 : 0;
+            if (!ok) { double v[3]; ksl::sgp4_prop<false>(ld, tsince[j], o, v); }
+        }
+    }
+    return 0;
+}
+
 int hc_upsample_index(int64_t j, int64_t n_in, int64_t n_out, int64_t *i0, int64_t *i1, double *w0, double *w1) {
     double scale = n_out > 1 ? (double)(n_in - 1) / (double)(n_out - 1) : 0.0;
     ksl::upsample_index(j, scale, n_in, i0, i1, w0, w1);

@@ -172,6 +172,37 @@ def test_device_fast_path_matches_oracle(hc):
     assert dev[hi_e][fast[hi_e]].max() < 1e-8 and np.median(dev[hi_e][fast[hi_e]]) < 2e-11
 
 
+def test_device_near_circular_form_matches_oracle(hc):
+    """The two-sweep Kepler solve k_screen_warp selects for near-circular records (e + drag growth < 0.0095): selected for
+    the real LEO TLEs and their Monte Carlo clouds, accepted at (nearly) every epoch, and as accurate as the general form."""
+    el, _ = common.population_elems()
+    gt, _, gc, _, _ = common.golden_pair()
+    cat = common.synthetic_catalog(1500, seed=23)
+    rng = np.random.default_rng(9)
+    edge = np.repeat(gt[:, None], 400, 1)                   # around the class boundary: e from 0.004 to 0.012
+    edge[1] = rng.uniform(0.004, 0.012, 400)
+    edge[5] = rng.uniform(0, 2 * np.pi, 400)
+    el = np.ascontiguousarray(np.concatenate([gt[:, None], gc[:, None], el, common.perturbed_samples(gt, 500, 1), cat, edge], axis=1))
+    c1, e1 = C.sgp4_init(el)
+    ts = np.linspace(-1.2e4, 1.2e4, 301)
+    rv1, ea = C.sgp4_prop(c1, ts)
+    n, m = c1.shape[1], len(ts)
+    pos, used, small = np.zeros((n, m, 3)), np.zeros((n, m), np.int32), np.zeros(n, np.int32)
+    hc.hc_sgp4_position_small(_p(np.ascontiguousarray(c1), D), ctypes.c_int64(n), _p(ts, D), ctypes.c_int64(m), ctypes.c_double(1.2e4),
+                              _p(pos, D), _p(used, I32), _p(small, I32))
+    good = (e1 == 0) & (ea == 0)
+    assert small[:22].sum() >= 19 and small[22:522].all()               # the real TLEs and the cloud around one
+    sm = good & (small == 1)
+    assert sm.sum() > 800
+    dev = np.abs(pos - rv1[..., :3]).max(-1)
+    assert used[sm].mean() > 0.995                                      # the hint is right: (almost) no fallback evaluations
+    acc = (used == 1) & sm[:, None]
+    assert dev[acc].max() < 1e-8 and np.median(dev[acc]) < 2e-11        # km, as the general form
+    assert dev[good].max() < 1e-8
+    # the boundary cloud: whatever the hint said, every epoch is either accepted within tolerance or redone exactly
+    assert 50 < small[-400:].sum() < 350
+
+
 def test_device_fast_state_matches_oracle(hc):
     """sgp4_state (K2 / K4 / K6 / K9: fast path with velocity over the 36 public constants, exact fallback)."""
     el, _ = common.population_elems()
