@@ -111,6 +111,11 @@ int ksl_sgp4_init(const double *elems, int64_t n, double *consts, int32_t *err, 
 int ksl_sgp4_prop(const double *consts, int64_t n, const double *tsince, int64_t m, int per_sample_t,
                   double *rv_km, int32_t *err, void *stream);
 
+/* the same, additionally ADDING to *n_exact (device, may be NULL) the number of evaluations that did not take the
+ * fast path (m >= 32 only; the parity sweeps use it to report how much of the element space the fast path covers) */
+int ksl_sgp4_prop_counted(const double *consts, int64_t n, const double *tsince, int64_t m, int per_sample_t,
+                          double *rv_km, int32_t *err, unsigned long long *n_exact, void *stream);
+
 /* ---- util.upsample(s, target_resolution)  (util.py:541-555) -------------------
  * x [n_in][ch] -> y [n_out][ch], torch's linear/align_corners=True arithmetic
  * including its float32 floor of the source index. */

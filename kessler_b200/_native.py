@@ -68,6 +68,7 @@ _SIGNATURES = {
     "ksl_launch_count": [],
     "ksl_sgp4_init": [_vp, _i64, _vp, _vp, _vp],
     "ksl_sgp4_prop": [_vp, _i64, _vp, _i64, _int, _vp, _vp, _vp],
+    "ksl_sgp4_prop_counted": [_vp, _i64, _vp, _i64, _int, _vp, _vp, _vp, _vp],
     "ksl_upsample": [_vp, _i64, _i64, _i64, _vp, _vp],
     "ksl_propagate_upsample": [_vp, _f64, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
     "ksl_find_conjunction_ws": [_i64],

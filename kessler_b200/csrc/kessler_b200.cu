@@ -101,16 +101,95 @@ __global__ void __launch_bounds__(128) k_sgp4_init(const double *__restrict__ el
 }
 
 // ------------------------------------------------------------------------------------
-// K2  sgp4 over an (n records) x (m epochs) grid, one thread per (record, epoch).
-// Epochs run along the warp, so for m >= 32 a warp shares one record: its 36
-// constants are uniform (broadcast) loads.  The 6-double states of a warp are
-// transposed through shared memory so the stores are fully coalesced.
+// K2  sgp4 over an (n records) x (m epochs) grid, one thread per (record, epoch); two shapes.
+// k_sgp4_prop_tile (m >= 32, the propagate / propagate_upsample shape): a CTA owns 128 consecutive epochs of ONE
+// record; the record is staged once in shared memory as a fast record (the 36 constants + the products the
+// reference rebuilds per call), so every constant is a broadcast LDS operand, as in the screening kernel; the
+// sincos table sits next to it.  k_sgp4_prop (any m; the propagate_batch shape: many records, few epochs each):
+// epochs run along the warp, the constants are gathered through the read-only path.
+// Both transpose the 6-double states of a warp through shared memory so that the stores are fully coalesced
+// (48 B per evaluation is what bounds a state-writing kernel from the HBM side), choose the near-circular form of
+// the fast path per evaluation, and can count the evaluations that took the exact route (n_exact, optional).
 // ------------------------------------------------------------------------------------
 constexpr int kPropThreads = 128;
+
+// full state through the fast path (either form), exact route when it declines; c: a fast record
+__device__ __forceinline__ int prop_state_from_fast_record(const double *c, double t, double r[3], double v[3], const double *grid,
+                                                           unsigned int *n_exact) {
+    auto ld = [&](int q) { return c[q]; };
+    const bool small = ksl::fast_record_is_small_e(ld, fabs(t));
+    const bool ok = small ? ksl::sgp4_prop_fast_rv<true, true>(ld, t, r, v, grid) : ksl::sgp4_prop_fast_rv<true, false>(ld, t, r, v, grid);
+    if (ok) return 0;
+    *n_exact += 1;
+    double rx[3], vx[3];
+    const int e = ksl::sgp4_state_exact(ld, t, rx, vx);
+    r[0] = rx[0]; r[1] = rx[1]; r[2] = rx[2];
+    v[0] = vx[0]; v[1] = vx[1]; v[2] = vx[2];
+    return e;
+}
+
+__device__ __forceinline__ void store_states_coalesced(double (*stage)[32 * 6], int warp, int lane, long long first_eval_of_warp,
+                                                       long long evals_total, double *__restrict__ rv) {
+    __syncwarp();
+    const long long warp_base = first_eval_of_warp * 6;
+    const long long warp_valid = evals_total * 6 - warp_base;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const int o = q * 32 + lane;
+        if (o < warp_valid) rv[warp_base + o] = stage[warp][o];
+    }
+}
+
+__global__ void __launch_bounds__(kPropThreads) k_sgp4_prop_tile(const double *__restrict__ consts, long long n,
+                                                                 const double *__restrict__ tsince, long long m, int per_sample_t,
+                                                                 long long tiles_per_record, double *__restrict__ rv,
+                                                                 int *__restrict__ err, unsigned long long *__restrict__ n_exact) {
+    __shared__ double stage[kPropThreads / 32][32 * 6];
+    __shared__ double s_rec[ksl::KSL_NFAST];
+    __shared__ __align__(16) double s_grid[2 * ksl::kGridPoints];
+    const long long i = blockIdx.x / tiles_per_record;
+    const long long j0 = (blockIdx.x - i * tiles_per_record) * kPropThreads;
+    for (int q = threadIdx.x; q < 2 * ksl::kGridPoints; q += kPropThreads) s_grid[q] = ksl::kGridSinCos[q];
+    if (threadIdx.x < KSL_NCONST) s_rec[threadIdx.x] = consts[(long long)threadIdx.x * n + i];
+    __syncthreads();
+    if (threadIdx.x == 0) ksl::prepare_fast_record(s_rec, 1);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long j = j0 + threadIdx.x;
+    int e = 0;
+    unsigned int nx = 0;
+    if (j < m) {
+        const double t = per_sample_t ? tsince[i * m + j] : tsince[j];
+        double r[3], v[3];
+        e = prop_state_from_fast_record(s_rec, t, r, v, s_grid, &nx);
+        double *st = &stage[warp][lane * 6];
+        st[0] = r[0]; st[1] = r[1]; st[2] = r[2];
+        st[3] = v[0]; st[4] = v[1]; st[5] = v[2];
+    }
+    // the warp's 32 evaluations are consecutive epochs of record i: [i][j0 + 32 warp ...]; rows end at m
+    {
+        __syncwarp();
+        const long long jw = j0 + warp * 32;
+        const long long valid = (m - jw) * 6;       // doubles of this record left from the warp's first epoch on
+        double *dst = rv + (i * m + jw) * 6;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const int o = q * 32 + lane;
+            if (o < valid) dst[o] = stage[warp][o];
+        }
+    }
+    e = __reduce_or_sync(0xffffffffu, e);
+    nx = __reduce_add_sync(0xffffffffu, nx);
+    if (lane == 0) {
+        if (err && e) atomicOr(err + i, e);
+        if (n_exact && nx) atomicAdd(n_exact, (unsigned long long)nx);
+    }
+}
+
 __global__ void __launch_bounds__(kPropThreads) k_sgp4_prop(const double *__restrict__ consts, long long n,
                                                             const double *__restrict__ tsince, long long m,
                                                             int per_sample_t, double *__restrict__ rv,
-                                                            int *__restrict__ err) {
+                                                            int *__restrict__ err, unsigned long long *__restrict__ n_exact) {
     __shared__ double stage[kPropThreads / 32][32 * 6];
     const long long total = n * m;
     const long long idx = (long long)blockIdx.x * kPropThreads + threadIdx.x;
@@ -128,15 +207,9 @@ __global__ void __launch_bounds__(kPropThreads) k_sgp4_prop(const double *__rest
         st[0] = r[0]; st[1] = r[1]; st[2] = r[2];
         st[3] = v[0]; st[4] = v[1]; st[5] = v[2];
     }
-    __syncwarp();
-    const long long warp_base = ((long long)blockIdx.x * kPropThreads + warp * 32) * 6;
-    const long long warp_valid = (total * 6 - warp_base);
-#pragma unroll
-    for (int q = 0; q < 6; ++q) {
-        const int o = q * 32 + lane;
-        if (o < warp_valid) rv[warp_base + o] = stage[warp][o];
-    }
+    store_states_coalesced(stage, warp, lane, (long long)blockIdx.x * kPropThreads + warp * 32, total, rv);
     if (err && active && e) atomicOr(err + i, e);
+    (void)n_exact;
 }
 
 // ------------------------------------------------------------------------------------
@@ -1659,17 +1732,28 @@ int ksl_sgp4_init(const double *elems, int64_t n, double *consts, int32_t *err, 
     return KSL_OK;
 }
 
-int ksl_sgp4_prop(const double *consts, int64_t n, const double *tsince, int64_t m, int per_sample_t, double *rv_km,
-                  int32_t *err, void *stream) {
+int ksl_sgp4_prop_counted(const double *consts, int64_t n, const double *tsince, int64_t m, int per_sample_t, double *rv_km,
+                          int32_t *err, unsigned long long *n_exact, void *stream) {
     if (n < 0 || m < 0 || ((n > 0 && m > 0) && (!consts || !tsince || !rv_km)))
         return fail(KSL_E_ARG, "ksl_sgp4_prop: bad argument");
     if (n == 0 || m == 0) return KSL_OK;
-    const long long total = (long long)n * m;
-    const long long blocks = (total + kPropThreads - 1) / kPropThreads;
-    if (blocks > 0x7fffffffLL) return fail(KSL_E_ARG, "ksl_sgp4_prop: n*m too large for one launch");
-    k_sgp4_prop<<<(unsigned)blocks, kPropThreads, 0, S(stream)>>>(consts, n, tsince, m, per_sample_t, rv_km, err);
+    if (m >= 32) {       // a CTA per (record, 128 epochs): the record staged in shared memory
+        const long long tiles = (m + kPropThreads - 1) / kPropThreads;
+        if (tiles * n > 0x7fffffffLL) return fail(KSL_E_ARG, "ksl_sgp4_prop: n*m too large for one launch");
+        k_sgp4_prop_tile<<<(unsigned)(tiles * n), kPropThreads, 0, S(stream)>>>(consts, n, tsince, m, per_sample_t, tiles, rv_km, err, n_exact);
+    } else {
+        const long long total = (long long)n * m;
+        const long long blocks = (total + kPropThreads - 1) / kPropThreads;
+        if (blocks > 0x7fffffffLL) return fail(KSL_E_ARG, "ksl_sgp4_prop: n*m too large for one launch");
+        k_sgp4_prop<<<(unsigned)blocks, kPropThreads, 0, S(stream)>>>(consts, n, tsince, m, per_sample_t, rv_km, err, n_exact);
+    }
     KSL_LAUNCH_CHECK();
     return KSL_OK;
+}
+
+int ksl_sgp4_prop(const double *consts, int64_t n, const double *tsince, int64_t m, int per_sample_t, double *rv_km,
+                  int32_t *err, void *stream) {
+    return ksl_sgp4_prop_counted(consts, n, tsince, m, per_sample_t, rv_km, err, nullptr, stream);
 }
 
 static double up_scale(int64_t n_in, int64_t n_out) { return n_out > 1 ? (double)(n_in - 1) / (double)(n_out - 1) : 0.0; }

@@ -149,14 +149,17 @@ KSL_HD bool abs_below_pow2(double x, int e) { return (hi_word(x) & 0x7fffffff) <
 // quadrant bookkeeping at all.  Valid for |x| < 2^18: the step is split into 28 + 53 bits, so fn * step_hi is exact.
 //   [0] 512 / (2 pi)  [1] 1.5 * 2^52  [2] step_hi  [3] step_lo  [4..5] -1/6, 1/120  [6..7] -1/2, 1/24
 #include "sincos_grid_table.cuh"   // kGridPoints, kGridTab, kGridSinCos
+// kSinTerms / kCosTerms (2 or 1): terms of the kernels for sin r - r and cos r - 1.  The short forms are for callers whose
+// use of the result tolerates their truncation: sin through r^3 leaves r^5 / 120 < 7e-14, cos through r^2 leaves r^4 / 24 < 6e-11.
+template <int kSinTerms = 2, int kCosTerms = 2>
 KSL_HD void sincos_grid(double x, const double *grid, double &s, double &c) {
     const double t = fma_rn(x, kGridTab[0], kGridTab[1]);
     const int k = lo_word(t) & (kGridPoints - 1);
     const double fn = t - kGridTab[1];
     const double r = fma_rn(-fn, kGridTab[3], fma_rn(-fn, kGridTab[2], x));
     const double z = r * r;
-    const double sr = fma_rn(z * fma_rn(z, kGridTab[5], kGridTab[4]), r, r);   // sin r
-    const double cm1 = z * fma_rn(z, kGridTab[7], kGridTab[6]);               // cos r - 1
+    const double sr = fma_rn(z * (kSinTerms == 2 ? fma_rn(z, kGridTab[5], kGridTab[4]) : kGridTab[4]), r, r);   // sin r
+    const double cm1 = z * (kCosTerms == 2 ? fma_rn(z, kGridTab[7], kGridTab[6]) : kGridTab[6]);               // cos r - 1
 #if defined(__CUDA_ARCH__)
     const double2 sc = *reinterpret_cast<const double2 *>(grid + 2 * k);
     const double S = sc.x, C = sc.y;
@@ -729,7 +732,8 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
     const double lm = wrap_pm_pi(xlm) - nodem;
 
     double sarg, carg;
-    sincos_grid(argpm, grid, sarg, carg);
+    if (small_e) sincos_grid<1, 2>(argpm, grid, sarg, carg);    // enters multiplied by em < 0.01: 7e-14 there is 7e-16
+    else sincos_grid(argpm, grid, sarg, carg);
     const double axnl = em * carg;
     double temp = rcp_1(am * fma_rn(-em, em, 1.0));            // * aycof / xlcof ~ 1e-3: 1e-12 is plenty
     const double aynl = fma_rn(em, sarg, temp * c(KSL_C_AYCOF));
@@ -755,9 +759,10 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
     if (small_e) {
         // |E - E0| <= el + pi / 512 < 0.0162: Halley leaves (el / 6) 0.0162^3 < 8e-9, the Newton step below -- reciprocal
         // refined cubically, (el |d|)^3 < 5e-12 -- leaves (el / 2) (8e-9)^2 + 8e-9 x 5e-12 < 1e-19.
-        // rotation by |d| < 0.0162: sin through d^7 (d^9 / 9! < 3e-22), cos through d^6 (d^8 / 8! < 2e-19)
+        // rotation by |d| < 0.0162 (typically 4e-3): sin through d^5 (d^7 / 7! < 6e-16, typically 3e-21), cos through d^6
+        // (d^8 / 8! < 2e-19)
         const double d2 = d * d;
-        const double ps = fma_rn(fma_rn(d2, kTrigTab[2], kTrigTab[1]), d2, kTrigTab[0]);
+        const double ps = fma_rn(d2, kTrigTab[1], kTrigTab[0]);
         const double sd = fma_rn(ps * d2, d, d);
         const double cd = fma_rn(fma_rn(fma_rn(d2, kTrigTab[6], kTrigTab[5]), d2, kTrigTab[4]), d2, 1.0);
         const double s0 = se, c0 = ce;
@@ -826,16 +831,34 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
 
     // (sinu, cosu) is a unit vector to rounding (the last, first-order rotation is by < 1e-9)
     double sinsu = sinu, cossu = cosu;
-    rotate_micro(dsu, sinsu, cossu);
+    if (small_e) {      // |dsu| <= 1/8 J2 |x7thm1| / pl^2 < 8.2e-4 (4e-4 at 40 deg): cos through d^2 leaves d^4 / 24 < 2e-14 (1e-15)
+        const double q2 = dsu * dsu;
+        const double sd = fma_rn(q2 * kTrigTab[0], dsu, dsu);
+        const double cd = fma_rn(q2, kTrigTab[4], 1.0);
+        sinsu = fma_rn(sinu, cd, cosu * sd);
+        cossu = fma_rn(cosu, cd, -(sinu * sd));
+    } else {
+        rotate_micro(dsu, sinsu, cossu);
+    }
     double snod, cnod;
     sincos_grid(nodem + dnode, grid, snod, cnod);   // xnode, as the reference forms it
     double sini = c(KSL_C_SINIO), cosi = c(KSL_C_COSIO);
-    rotate_micro(dinc, sini, cosi);
-    const double xmx = -snod * cosi, xmy = cnod * cosi;
+    if (small_e) {      // pl > 0.9999 am >= ~1: |dinc| <= 3/8 J2 / pl^2 < 4.1e-4, cos through d^2 leaves d^4 / 24 < 1.2e-15
+        const double q2 = dinc * dinc;
+        const double sd = fma_rn(q2 * kTrigTab[0], dinc, dinc);
+        const double cd = fma_rn(q2, kTrigTab[4], 1.0);
+        const double s0 = sini, c0 = cosi;
+        sini = fma_rn(s0, cd, c0 * sd);
+        cosi = fma_rn(c0, cd, -(s0 * sd));
+    } else {
+        rotate_micro(dinc, sini, cosi);
+    }
+    const double xmx = -snod * cosi, xmy = cnod * cosi;     // (only the velocity needs these two)
     const double mr = mrt * kRe;
     const double rs = mr * sinsu, rcs = mr * cossu;
-    r[0] = fma_rn(xmx, rs, cnod * rcs);
-    r[1] = fma_rn(xmy, rs, snod * rcs);
+    const double rsc = rs * cosi;
+    r[0] = fma_rn(-snod, rsc, cnod * rcs);
+    r[1] = fma_rn(cnod, rsc, snod * rcs);
     r[2] = sini * rs;
     if (kVel) {
         // sqrt(am) / rl = (am / rl) am^-1/2 and sqrt(pl) / rl = sqrt(1 - el2) (am / rl) am^-1/2: one reciprocal square

@@ -60,6 +60,21 @@ def sgp4_prop(consts, tsince, per_sample_t=False, err=None):
     return rv, err
 
 
+def sgp4_prop_counted(consts, tsince, per_sample_t=False):
+    """sgp4_prop + the number of evaluations that left the fast path: (rv [n, m, 6], err [n], n_exact int)."""
+    dev = _dev()
+    consts = _cf64(consts, dev)
+    tsince = _cf64(tsince, dev)
+    n = consts.shape[1]
+    m = tsince.shape[-1] if tsince.dim() > 0 else 1
+    rv = torch.empty((n, m, 6), dtype=F64, device=dev)
+    err = torch.zeros(n, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    N.check(N.lib().ksl_sgp4_prop_counted(ptr(consts), n, ptr(tsince), m, 1 if per_sample_t else 0, ptr(rv), ptr(err), ptr(cnt),
+                                          stream_ptr()), "ksl_sgp4_prop_counted")
+    return rv, err, int(cnt[0])
+
+
 # --- util.upsample ---------------------------------------------------------------------
 def upsample(x, n_out):
     dev = _dev()

@@ -112,6 +112,47 @@ def test_sgp4_prop_parity_catalog_and_flags(eng):
     assert np.array_equal(np.isnan(rv[bad]), np.isnan(rv_ref[bad]))
 
 
+def test_sgp4_fast_path_sweep_ten_million_points(eng):
+    """1e7 (elements, tsince) points through ksl_sgp4_prop against the C oracle, concentrated where the fast path's validity
+    predicates sit (e in [0.10, 0.14] around its 0.12 bound and in [0.006, 0.012] around the near-circular form's bound,
+    perigee 180-260 km where drag terms are largest, |B*| up to 0.3, |tsince| up to 6e4 min) on top of the prior's bulk:
+    every evaluation the oracle accepts agrees to the tolerance of record (1e-6 km), flags agree, and the share of
+    evaluations the fast path hands to the exact route is reported."""
+    rng = np.random.default_rng(2026)
+    n, m = 20000, 512
+    el = common.synthetic_catalog(n, seed=77, include_edge=False)
+    k = n // 5
+    el[1, :k] = rng.uniform(0.10, 0.14, k)                                    # around the fast path's eccentricity bound
+    el[1, k:2 * k] = rng.uniform(0.006, 0.012, k)                             # around the near-circular form's bound
+    per = rng.uniform(180.0, 260.0, k)                                        # low perigees: a (1 - e) = re + perigee
+    a_er = (6378.137 + per) / 6378.137 / (1.0 - el[1, 2 * k:3 * k])
+    el[0, 2 * k:3 * k] = 0.07436685316871385 / a_er ** 1.5
+    el[6, 3 * k:4 * k] = rng.uniform(-0.3, 0.3, k)                            # huge drag terms
+    ts = rng.uniform(-6.0e4, 6.0e4, (n, m))
+    ts[:, :8] = rng.uniform(-30.0, 30.0, (n, 8))                              # ... and right at the epoch
+    c_ref, e0 = C.sgp4_init(el)
+    rv_ref, e_ref = C.sgp4_prop(c_ref, ts, per_sample_t=True)
+    c_own, e0g = eng.sgp4_init(el)
+    assert np.array_equal(_np(e0g), e0)
+    rv, e, n_exact = eng.sgp4_prop_counted(c_own, ts, per_sample_t=True)
+    rv, e = _np(rv), _np(e)
+    ok = e0 == 0
+    assert np.array_equal(e[ok], e_ref[ok])                                   # Vallado error bits: record-level flag parity
+    good = ok & (e_ref == 0)
+    assert good.sum() > 0.5 * n
+    dpos = np.abs(rv[good][..., :3] - rv_ref[good][..., :3]).max(axis=-1)
+    dvel = np.abs(rv[good][..., 3:] - rv_ref[good][..., 3:]).max(axis=-1)
+    assert dpos.max() < POS_TOL_KM and np.median(dpos) < 1e-10, (dpos.max(), np.median(dpos))
+    assert dvel.max() < 1e-9
+    assert (dpos > 1e-7).mean() < 1e-3                                        # the tail beyond 1e-7 km is thin
+    share = n_exact / float(n * m)
+    print(f"fast-path sweep: {good.sum() * m:.3g} clean evaluations, max |dr| {dpos.max():.2e} km, median {np.median(dpos):.1e} km, "
+          f"exact-route share {share:.3f}")
+    assert 0.05 < share < 0.6                                                 # the sweep really straddles the predicates
+    bad = ok & (e_ref != 0)
+    assert np.array_equal(np.isnan(rv[bad]), np.isnan(rv_ref[bad]))
+
+
 def test_reference_unit_test_state_at_epoch(eng):
     """tests/test_util.py:105-131 through the GPU: sgp4(tle, 0) -> Kepler elements, 5 places."""
     from oracle import sgp4_ref as S
