@@ -631,52 +631,44 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
         }
         BestW best = {INFINITY, 0.0, kNoIndexW, kNoIndexW, kNoIndexW};
         int e_t = 0, e_c = 0;
-        // lane i of a chunk evaluates epoch k = base + i and owns the segment [k-1, k] that ENDS there; lane 0
-        // finds the left end, lane 31 of the previous chunk, in the warp's carry slot (no epoch evaluated twice)
-        double rt[3] = {0.0, 0.0, 0.0}, rc[3] = {0.0, 0.0, 0.0};
         double cutoff = INFINITY;   // warp-wide running minimum (m^2), refreshed whenever a lane visited a segment
         float want_f = INFINITY;    // what a segment's lower bound has to exceed to be skipped (km^2), follows cutoff
-        int k = lane;
-        // Pilot chunk (it = -1): the 32 epochs around the PREVIOUS trace's closest approach are searched first.  In a
-        // Monte Carlo batch consecutive traces are perturbations of one pair, so this seeds the warp-wide running
-        // minimum (`cutoff`) close to the final one and the skip test below then prunes nearly every other segment.  It only
-        // changes the order in which segments are visited (the pilot's epochs are evaluated again in their turn),
-        // never the result: arg-min and first crossing are order-independent (ties go to the smaller index).
-        // It is used once two consecutive traces of this warp bottomed out within 64 epochs of each other (related
-        // traces); for unrelated ones (a catalog) it would be a wasted chunk.
-        for (int it = (hint >= 0) ? -1 : 0, base; (base = (it < 0) ? hint : it * 32) <= last; ++it) {
-            const bool pilot = it < 0;
-            k = base + lane;
-            if (k <= last) {
-                const double tm = grid_in_smem ? s_times[k] : __ldg(p.times_coarse + k);
-                // both fast evaluations back to back: one straight-line block with two independent
-                // dependency chains for the scheduler; the (rare) exact fallbacks come after
-                const double ts_c = (tm - epoch_c) * 1440.0, ts_t = (tm - epoch_t) * 1440.0;
-                bool ok_c, ok_t = true;
-                auto ld_c = [&](int q) { return s_cc[q]; };
-                auto ld_t = [&](int q) { return s_ct[q]; };
-                if (kSharedTarget) {
-                    rt[0] = __ldg(p.target_pos + 3 * k); rt[1] = __ldg(p.target_pos + 3 * k + 1); rt[2] = __ldg(p.target_pos + 3 * k + 2);
-                    ok_c = small_c ? ksl::sgp4_prop_fast<true>(ld_c, ts_c, rc, s_grid) : ksl::sgp4_prop_fast<false>(ld_c, ts_c, rc, s_grid);
-                } else if (small_c && small_t) {     // one uniform branch per chunk; each arm is one straight-line block
-                    ok_c = ksl::sgp4_prop_fast<true>(ld_c, ts_c, rc, s_grid);
-                    ok_t = ksl::sgp4_prop_fast<true>(ld_t, ts_t, rt, s_grid);
-                } else {
-                    ok_c = ksl::sgp4_prop_fast<false>(ld_c, ts_c, rc, s_grid);
-                    ok_t = ksl::sgp4_prop_fast<false>(ld_t, ts_t, rt, s_grid);
-                }
-                // (through a scratch array: the out-of-line call takes an address, and rc / rt must stay in registers)
-                if (!ok_c) {
-                    double rx[3];
-                    e_c |= ksl::sgp4_position_exact(s_cc, 1, ts_c, rx);
-                    rc[0] = rx[0]; rc[1] = rx[1]; rc[2] = rx[2];
-                }
-                if (!ok_t) {
-                    double rx[3];
-                    e_t |= ksl::sgp4_position_exact(s_ct, 1, ts_t, rx);
-                    rt[0] = rx[0]; rt[1] = rx[1]; rt[2] = rx[2];
-                }
+        // lane i of a chunk evaluates epoch k = base + i and owns the segment [k-1, k] that ENDS there; lane 0
+        // finds the left end, lane 31 of the previous chunk, in the warp's carry slot (no epoch evaluated twice).
+        // -- SGP4 of one epoch per lane: both objects (the shared target's position is looked up) ----------------------
+        auto evaluate = [&](int k, double rt[3], double rc[3]) {
+            if (k > last) return;
+            const double tm = grid_in_smem ? s_times[k] : __ldg(p.times_coarse + k);
+            // both fast evaluations back to back: one straight-line block with two independent
+            // dependency chains for the scheduler; the (rare) exact fallbacks come after
+            const double ts_c = (tm - epoch_c) * 1440.0, ts_t = (tm - epoch_t) * 1440.0;
+            bool ok_c, ok_t = true;
+            auto ld_c = [&](int q) { return s_cc[q]; };
+            auto ld_t = [&](int q) { return s_ct[q]; };
+            if (kSharedTarget) {
+                rt[0] = __ldg(p.target_pos + 3 * k); rt[1] = __ldg(p.target_pos + 3 * k + 1); rt[2] = __ldg(p.target_pos + 3 * k + 2);
+                ok_c = small_c ? ksl::sgp4_prop_fast<true>(ld_c, ts_c, rc, s_grid) : ksl::sgp4_prop_fast<false>(ld_c, ts_c, rc, s_grid);
+            } else if (small_c && small_t) {     // one uniform branch per chunk; each arm is one straight-line block
+                ok_c = ksl::sgp4_prop_fast<true>(ld_c, ts_c, rc, s_grid);
+                ok_t = ksl::sgp4_prop_fast<true>(ld_t, ts_t, rt, s_grid);
+            } else {
+                ok_c = ksl::sgp4_prop_fast<false>(ld_c, ts_c, rc, s_grid);
+                ok_t = ksl::sgp4_prop_fast<false>(ld_t, ts_t, rt, s_grid);
             }
+            // (through a scratch array: the out-of-line call takes an address, and rc / rt must stay in registers)
+            if (!ok_c) {
+                double rx[3];
+                e_c |= ksl::sgp4_position_exact(s_cc, 1, ts_c, rx);
+                rc[0] = rx[0]; rc[1] = rx[1]; rc[2] = rx[2];
+            }
+            if (!ok_t) {
+                double rx[3];
+                e_t |= ksl::sgp4_position_exact(s_ct, 1, ts_t, rx);
+                rt[0] = rx[0]; rt[1] = rx[1]; rt[2] = rx[2];
+            }
+        };
+        // -- the segments that end at the chunk's epochs -----------------------------------------------------------------
+        auto search = [&](int k, bool pilot, const double rt[3], const double rc[3]) {
             // stage 1, in FP32 (conservative, see segment_skippable_f32): relative position at this epoch (d1) and
             // at the left-hand neighbour (d0: 3 shuffles)
             const bool owner = k >= 1 && k <= last && !(pilot && lane == 0);   // the pilot's lane 0 has no left neighbour
@@ -723,15 +715,31 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
                 for (int x = 0; x < 3; ++x) { s_carry[x] = rt[x]; s_carry[3 + x] = rc[x]; s_carry_f[x] = d1[x]; }
             }
             __syncwarp();
-        }
-        // torch's clamped tail segment [last, last]: both ends are the last epoch
-        if (k == last) {
-            const double dl[3] = {rt[0] - rc[0], rt[1] - rc[1], rt[2] - rc[2]};
-            if (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable(dl, dl, cutoff, best.conj_j == kNoIndexW, p.thr2)) {
-                Best b = best_expand(best);
-                ksl::segment_search<kMode>(last, last, p.scale, p.n_coarse, p.n_fine, p.thr2, rt, rt, rc, rc, b, ja_tab);
-                best = best_compact(b);
+            // torch's clamped tail segment [last, last]: both ends are the last epoch (its owner is the lane that holds it)
+            if (k == last && !pilot) {
+                const double dl[3] = {rt[0] - rc[0], rt[1] - rc[1], rt[2] - rc[2]};
+                if (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable(dl, dl, cutoff, best.conj_j == kNoIndexW, p.thr2)) {
+                    Best b = best_expand(best);
+                    ksl::segment_search<kMode>(last, last, p.scale, p.n_coarse, p.n_fine, p.thr2, rt, rt, rc, rc, b, ja_tab);
+                    best = best_compact(b);
+                }
             }
+        };
+        double rt[3] = {0.0, 0.0, 0.0}, rc[3] = {0.0, 0.0, 0.0};
+        // Pilot chunk: the 32 epochs around the PREVIOUS trace's closest approach are searched first.  In a
+        // Monte Carlo batch consecutive traces are perturbations of one pair, so this seeds the warp-wide running
+        // minimum (`cutoff`) close to the final one and the skip test then prunes nearly every other segment.  It only
+        // changes the order in which segments are visited (the pilot's epochs are evaluated again in their turn),
+        // never the result: arg-min and first crossing are order-independent (ties go to the smaller index).
+        // It is used once two consecutive traces of this warp bottomed out within 64 epochs of each other (related
+        // traces); for unrelated ones (a catalog) it would be a wasted chunk.
+        if (hint >= 0) {
+            evaluate(hint + lane, rt, rc);
+            search(hint + lane, true, rt, rc);
+        }
+        for (int base = 0; base <= last; base += 32) {
+            evaluate(base + lane, rt, rc);
+            search(base + lane, false, rt, rc);
         }
         e_t = __reduce_or_sync(0xffffffffu, e_t);
         e_c = __reduce_or_sync(0xffffffffu, e_c);
