@@ -713,22 +713,31 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
         t2 * fma_rn(t, fma_rn(t, fma_rn(t, c(KSL_C_T5COF), c(KSL_C_T4COF)), c(KSL_C_T3COF)), c(KSL_C_T2COF));
     // sin(mm0) = sin(xmdf + temp0), |temp0| < 2^-4, to 1e-8 (sin through d^3, cos through d^4): it only feeds the
     // bstar*cc5 term of the eccentricity, and bstar*cc5 < 1e-5 even for bstar = 1e-2
+    // (general form: |temp0| < 1 -- a high-drag record weeks from its epoch --, sin through d^9, cos through d^10: 2e-9)
     const double q2 = temp0 * temp0;
-    const double sd0 = fma_rn(q2 * kTrigTab[0], temp0, temp0);
-    const double cd0 = fma_rn(fma_rn(q2, kTrigTab[5], kTrigTab[4]), q2, 1.0);
+    double sd0, cd0;
+    if (small_e) {
+        sd0 = fma_rn(q2 * kTrigTab[0], temp0, temp0);
+        cd0 = fma_rn(fma_rn(q2, kTrigTab[5], kTrigTab[4]), q2, 1.0);
+    } else {
+        sd0 = fma_rn(fma_rn(fma_rn(fma_rn(q2, kTrigTab[3], kTrigTab[2]), q2, kTrigTab[1]), q2, kTrigTab[0]) * q2, temp0, temp0);
+        cd0 = fma_rn(fma_rn(fma_rn(fma_rn(fma_rn(q2, kTrigTab[8], kTrigTab[7]), q2, kTrigTab[6]), q2, kTrigTab[5]), q2, kTrigTab[4]), q2, 1.0);
+    }
     const double smm = fma_rn(sx, cd0, cx * sd0);
     const double tempe = fma_rn(c(KSL_F_BC5), smm - c(KSL_C_SINMAO), c(KSL_F_BC4) * t);
     const double am = c(KSL_C_AOBASE) * tempa * tempa;
-    const double em = c(KSL_C_ECCO) - tempe;
-    // validity: sincos_grid needs < 2^18; |argpm| < 32 and |nodem| < 8 keep |u| < pi + 8 + 0.1; |temp0| < 2^-4 for the
-    // kernels above; em < 1e-6 is clamped by the reference
-    bool ok = abs_below_pow2(xmdf, 16) && abs_below_pow2(argpm, 5) && abs_below_pow2(nodem, 3) &&
-              abs_below_pow2(temp0, -4) && (em >= 1.0e-6);
+    const double em_raw = c(KSL_C_ECCO) - tempe;
+    const double em = fmax(em_raw, 1.0e-6);        // the reference's clamp; below -0.001 it raises error 1 (exact route)
+    // validity: sincos_grid needs < 2^18; |argpm| < 32 and |nodem| < 64 keep |u| small and bound what reducing these
+    // UNWRAPPED angles by 2 pi instead of the reference's 2pi_d costs (2.4e-16 rad per turn: < 3e-15); |temp0| within
+    // the kernels above
+    bool ok = abs_below_pow2(xmdf, 16) && abs_below_pow2(argpm, 5) && abs_below_pow2(nodem, 6) &&
+              abs_below_pow2(temp0, small_e ? -4 : 0) && (em_raw >= -1.0e-3);
     const double mm = mad_2r(c(KSL_C_NO), templ, mm0);
     const double xlm = add_rn(add_rn(mm, argpm), nodem);
     // The reference wraps nodem, argpm, xlm and mm = xlm - argpm - nodem to [0, 2 pi) with exact remainders
     // and rebuilds u = (mm + argpm + nodem + long-period term) - nodem from them: modulo 2pi_d that is
-    // (nodem itself stays unwrapped: |nodem| < 3 pi, where reducing by 2pi_d or by 2 pi differs by 2e-16 rad)
+    // (nodem itself stays unwrapped: |nodem| < 64, where reducing by 2pi_d or by 2 pi differs by < 3e-15 rad)
     const double lm = wrap_pm_pi(xlm) - nodem;
 
     double sarg, carg;
@@ -898,7 +907,10 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3], const double *grid) 
 template <typename Load>
 KSL_HD bool fast_record_is_small_e(Load &&c, double tmax) {
     const double bound = c(KSL_C_ECCO) + fabs(c(KSL_F_BC4)) * tmax + 2.0 * fabs(c(KSL_F_BC5)) + 1.5e-3;
-    return bound < 0.0095;
+    // ... and the drag angle temp0 = omgcof t + xmcof ((1 + eta cos M)^3 - delmo) must stay inside that form's short kernels
+    const double ae = 1.0 + fabs(c(KSL_C_ETA));
+    const double drag_angle = fabs(c(KSL_C_OMGCOF)) * tmax + fabs(c(KSL_C_XMCOF)) * (ae * ae * ae + fabs(c(KSL_C_DELMO)));
+    return bound < 0.0095 && drag_angle < 0.06;
 }
 
 // In-place preparation of a private (shared-memory / local) copy of a record, KSL_NFAST entries of `stride`

@@ -26,7 +26,7 @@ import torch
 from . import engine, util
 from . import _native as N
 from .cdm import ConjunctionDataMessage
-from .model import quantize_sgp4_inputs
+from .model import _quantize_exp_field, quantize_sgp4_inputs, quantize_sgp4_inputs_torch  # noqa: F401
 from .tle import MU_EARTH, epoch_to_datetime, from_datetime_to_mjd, from_mjd_to_datetime, from_mjd_to_epoch_days_after_1_jan
 
 
@@ -124,13 +124,17 @@ def generate_cdm_batch(model, batch, hits, seed=0, t_new_obs=None, c_new_obs=Non
     ev, ci, ob = np.nonzero(obs)                                         # items: one per new observation
     n_items = len(ev)
     # ---- records: initialised target / chaser of every event ----------------------------------------
+    # From here to the RTN covariances everything lives on the device as torch tensors (torch = plumbing: batched 6 x 6
+    # algebra between the launches); one packed transfer at the end brings the per-item results back.
+    dev = torch.device("cuda", torch.cuda.current_device())
+    D = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     el = np.concatenate([batch["elems_t"][:, hits], batch["elems_c"][:, hits]], axis=1)      # [7, 2E]
     ep = np.concatenate([batch["epoch_t"][hits], batch["epoch_c"][hits]])
     consts, _ = engine.sgp4_init(el)
     rec = ob * E + ev
+    rec_d = D(rec)
     tc = np.ascontiguousarray(times[::max(int(model._time_upsample_factor), 1)])
-    truth, _ = engine.states_at_fine(consts, rec, ep[rec], idx_cdm[ci], tc, len(times))
-    truth = truth.cpu().numpy()
+    truth_d, _ = engine.states_at_fine(consts, rec, ep[rec], idx_cdm[ci], tc, len(times))
     # instruments (model.py:655-676): mean over the object's instruments of (state + bias, diagonal RTN covariance)
     def inst(instruments):
         bias = np.mean([np.asarray(x._instrument_characteristics["bias_xyz"], dtype=np.float64).reshape(6) for x in instruments], axis=0)
@@ -138,51 +142,80 @@ def generate_cdm_batch(model, batch, hits, seed=0, t_new_obs=None, c_new_obs=Non
         return bias, cov
     bias_t, cov_t = inst(model._t_observing_instruments)
     bias_c, cov_c = inst(model._c_observing_instruments)
-    state_obs = truth + np.where(ob[:, None] == 0, bias_t[None, :], bias_c[None, :])
-    cov_diag = np.where(ob[:, None] == 0, cov_t[None, :], cov_c[None, :])
+    is_c = D(ob.astype(np.float64))[:, None]
+    state_obs_d = truth_d + (1.0 - is_c) * D(bias_t)[None, :] + is_c * D(bias_c)[None, :]
+    cov_diag_d = (1.0 - is_c) * D(cov_t)[None, :] + is_c * D(cov_c)[None, :]
     # ---- newton_method (model.py:399,411): target = the TLE's own SGP4 state at the observation time -----
     tsince_obs = (time_cdm[ci] - ep[rec]) * 1440.0
-    rv, _ = engine.sgp4_prop(consts[:, torch.as_tensor(rec)], tsince_obs.reshape(-1, 1), per_sample_t=True)
+    rv, _ = engine.sgp4_prop(consts[:, rec_d], D(tsince_obs).reshape(-1, 1), per_sample_t=True)
     bstar = el[6, rec]
-    y, resid, _ = engine.newton_elements(rv[:, 0, :], bstar)
-    y = y.cpu().numpy()
-    wrap = lambda a: np.mod(a, 2 * np.pi)
-    raw_mm = y[:, 0] / 60.0
-    q = quantize_sgp4_inputs(raw_mm, y[:, 1], wrap(y[:, 2]), wrap(y[:, 3]), wrap(y[:, 4]), wrap(y[:, 5]), bstar)   # TLE(dict)
+    bstar_q = D(_quantize_exp_field(bstar))
+    y_d, resid_d, _ = engine.newton_elements(rv[:, 0, :], D(bstar))
+    two_pi = 2 * math.pi
+    wrap = lambda a: torch.remainder(a, two_pi)
+    raw_mm_d = y_d[:, 0] / 60.0
+    q_d = quantize_sgp4_inputs_torch(raw_mm_d, y_d[:, 1], wrap(y_d[:, 2]), wrap(y_d[:, 3]), wrap(y_d[:, 4]), wrap(y_d[:, 5]), bstar_q)   # TLE(dict)
     epoch_obs_by_slot = np.array([obs_epoch_mjd(t) for t in time_cdm])
     epoch_obs = epoch_obs_by_slot[ci]
     # ---- element covariance (model.py:461-478) -----------------------------------------------------------
-    R = _rotation_matrices(state_obs)
-    T = _blockdiag2(R)
-    C_xyz = np.einsum("nji,nj,njk->nik", T, cov_diag, T)
-    _, J = engine.kepler_partials(state_obs, model._mu_earth)
-    J = J.cpu().numpy()
-    Cov = np.einsum("nij,njk,nlk->nil", J, C_xyz, J)
-    eig_ok = np.all(np.real(np.linalg.eigvals(Cov)) > 1e-11, axis=1)
-    fix = ~eig_ok
-    Cov[fix] = 0.5 * (Cov[fix] + np.transpose(Cov[fix], (0, 2, 1))) + 1e-10 * np.eye(6)
-    mean_els = np.stack([(MU_EARTH / raw_mm ** 2) ** (1.0 / 3.0), q[1], q[2], q[3], q[4], q[5]], axis=1)
+    def rot(states):                               # util.rotation_matrix, batched: rows u, t, w
+        r, v = states[:, :3], states[:, 3:]
+        u = r / torch.linalg.norm(r, dim=1, keepdim=True)
+        w = torch.linalg.cross(r, v)
+        w = w / torch.linalg.norm(w, dim=1, keepdim=True)
+        return torch.stack([u, torch.linalg.cross(w, u), w], dim=1)
+    R = rot(state_obs_d)
+    T = torch.zeros((n_items, 6, 6), dtype=torch.float64, device=dev)
+    T[:, :3, :3] = R
+    T[:, 3:, 3:] = R
+    C_xyz = torch.einsum("nji,nj,njk->nik", T, cov_diag_d, T)
+    _, J = engine.kepler_partials(state_obs_d, model._mu_earth)
+    Cov = torch.einsum("nij,njk,nlk->nil", J, C_xyz, J)
+    # model.py:474-477: "all eigenvalues > 1e-11, else symmetrise and add 1e-10 I".  Cov = J C J^T is symmetric up to
+    # rounding, so the eigenvalues of its symmetric part decide (batched, on the device); non-finite rows count as failing
+    sym = 0.5 * (Cov + Cov.transpose(1, 2))
+    finite = torch.isfinite(sym).all(dim=2).all(dim=1)
+    # (all eigenvalues of a symmetric matrix exceed 1e-11  <=>  the matrix minus 1e-11 I is positive definite  <=>  its
+    # Cholesky factorisation succeeds: one batched factorisation instead of an eigen-decomposition)
+    eye = torch.eye(6, dtype=torch.float64, device=dev)[None]
+    _, info_pd = torch.linalg.cholesky_ex(torch.where(finite[:, None, None], sym, eye) - 1e-11 * eye)
+    fix = ~((info_pd == 0) & finite)
+    Cov = torch.where(fix[:, None, None], sym + 1e-10 * torch.eye(6, dtype=torch.float64, device=dev)[None], Cov)
+    mean_els = torch.stack([(MU_EARTH / raw_mm_d ** 2) ** (1.0 / 3.0), q_d[1], q_d[2], q_d[3], q_d[4], q_d[5]], dim=1)
     # ---- element clouds (model.py:497-541) ------------------------------------------------------------------
-    L, chol_ok = _batched_cholesky(Cov)       # not PD: the reference's "Expected parameter covariance_matrix" branch
+    # not PD: the reference's "Expected parameter covariance_matrix" branch (the instrument's own covariance is kept)
+    L, info = torch.linalg.cholesky_ex(torch.where(torch.isfinite(Cov), Cov, torch.zeros_like(Cov)))
+    chol_ok = (info == 0) & torch.isfinite(Cov).all(dim=2).all(dim=1)
     if z_elements is None:
-        z_elements = torch.randn((n_items, S, 6), dtype=torch.float64, generator=g).numpy()
-    samples = mean_els[:, None, :] + np.matmul(z_elements, np.transpose(L, (0, 2, 1)))
-    samples[~chol_ok] = mean_els[~chol_ok][:, None, :]
+        gd = torch.Generator(device=dev).manual_seed(int(seed) + 104729)
+        z_d = torch.randn((n_items, S, 6), dtype=torch.float64, device=dev, generator=gd)
+    else:
+        z_d = D(np.asarray(z_elements, dtype=np.float64))
+    samples = mean_els[:, None, :] + torch.matmul(z_d, L.transpose(1, 2))
+    samples = torch.where(chol_ok[:, None, None], samples, mean_els[:, None, :].expand(-1, S, -1))
     flat = samples.reshape(-1, 6)
     mm = (MU_EARTH / flat[:, 0] ** 3) ** 0.5
-    el_s = quantize_sgp4_inputs(mm, np.where(flat[:, 1] < 0.0, 0.0, flat[:, 1]), flat[:, 2], flat[:, 3], flat[:, 4], flat[:, 5],
-                                np.repeat(bstar, S))
-    tsince_ca = np.repeat((time_min[ev] - epoch_obs) * 1440.0, S)
+    el_s = quantize_sgp4_inputs_torch(mm, torch.where(flat[:, 1] < 0.0, torch.zeros_like(flat[:, 1]), flat[:, 1]), flat[:, 2], flat[:, 3],
+                                      flat[:, 4], flat[:, 5], bstar_q.repeat_interleave(S))
+    tsince_ca = D((time_min[ev] - epoch_obs) * 1440.0).repeat_interleave(S)
     c_s, _ = engine.sgp4_init(el_s)
     rv_s, _ = engine.sgp4_prop(c_s, tsince_ca.reshape(-1, 1), per_sample_t=True)
-    mc = rv_s[:, 0, :].cpu().numpy().reshape(n_items, S, 6) * 1e3
-    mean_state = mc.mean(axis=1)
-    Rm = _rotation_matrices(mean_state)
-    RmT = np.transpose(Rm, (0, 2, 1))
-    rtn = np.concatenate([np.matmul(mc[:, :, :3], RmT), np.matmul(mc[:, :, 3:], RmT)], axis=2)
-    d = rtn - rtn.mean(axis=1, keepdims=True)
-    cov_rtn = np.matmul(np.transpose(d, (0, 2, 1)), d) / (S - 1)
-    cov_rtn[~chol_ok] = np.einsum("ni,ij->nij", cov_diag[~chol_ok], np.eye(6))
+    del c_s
+    mc = rv_s[:, 0, :].reshape(n_items, S, 6) * 1e3
+    mean_state_d = mc.mean(dim=1)
+    RmT = rot(mean_state_d).transpose(1, 2)
+    rtn = torch.cat([torch.matmul(mc[:, :, :3], RmT), torch.matmul(mc[:, :, 3:], RmT)], dim=2)
+    d = rtn - rtn.mean(dim=1, keepdim=True)
+    cov_rtn_d = torch.matmul(d.transpose(1, 2), d) / (S - 1)
+    cov_rtn_d = torch.where(chol_ok[:, None, None], cov_rtn_d, torch.diag_embed(cov_diag_d))
+    # ---- one packed transfer of the per-item results -----------------------------------------------------------
+    packed = torch.cat([truth_d, state_obs_d, y_d, resid_d[:, None], q_d.t(), Cov.reshape(n_items, 36), mean_state_d,
+                        cov_rtn_d.reshape(n_items, 36)], dim=1).cpu().numpy()
+    truth, state_obs, y, resid_h = packed[:, 0:6], packed[:, 6:12], packed[:, 12:18], packed[:, 18]
+    q = np.ascontiguousarray(packed[:, 19:26].T)
+    Cov_h = packed[:, 26:62].reshape(n_items, 6, 6)
+    mean_state = np.ascontiguousarray(packed[:, 62:68])
+    cov_rtn = packed[:, 68:104].reshape(n_items, 6, 6).copy()
     tca_jd = util.from_mjd_to_jd(time_min)
     state_itrf_km = _teme_to_itrf(mean_state, tca_jd[ev]) / 1e3
     # ---- carry-forward (model.py:345-346): an un-observed object keeps the previous CDM's numbers ------------
@@ -208,8 +241,8 @@ def generate_cdm_batch(model, batch, hits, seed=0, t_new_obs=None, c_new_obs=Non
     pc[e_i, c_i] = np.where(pc_ok, counts / float(n_pc * n_pc), np.nan)
     return dict(hits=hits, max_ncdm=max_ncdm, time_cdm=time_cdm, idx_cdm=idx_cdm, issued=issued, new_obs=obs,
                 state_itrf_km=st, cov_rtn=cv, pc=pc, tca_mjd=time_min,
-                items=dict(event=ev, slot=ci, obj=ob, truth_m=truth, state_obs_m=state_obs, newton_y=y, newton_resid=resid.cpu().numpy(),
-                           obs_elements=q, obs_epoch_mjd=epoch_obs, cov_tle=Cov, mean_state_tca_m=mean_state, cov_rtn=cov_rtn))
+                items=dict(event=ev, slot=ci, obj=ob, truth_m=truth, state_obs_m=state_obs, newton_y=y, newton_resid=resid_h,
+                           obs_elements=q, obs_epoch_mjd=epoch_obs, cov_tle=Cov_h, mean_state_tca_m=mean_state, cov_rtn=cov_rtn))
 
 
 def to_cdms(model, res, e, t_tle=None, c_tle=None):
@@ -322,7 +355,7 @@ def _concat_hits(parts):
     return out
 
 
-def generate_events(model, n_events, batch_size=65536, seed=0, max_batches=100000, events_per_pass=4096):
+def generate_events(model, n_events, batch_size=65536, seed=0, max_batches=100000, events_per_pass=8192, device_batches=True):
     """Rejection-sample conjunctions `batch_size` candidates at a time (one fused screen launch each), collect the
     accepted draws, and run the batched ground segment on up to `events_per_pass` of them at once.  Returns
     (list of generate_cdm_batch results -- each with its compact `batch` under key "batch" --, candidates screened)."""
@@ -342,14 +375,22 @@ def generate_events(model, n_events, batch_size=65536, seed=0, max_batches=10000
     for _ in range(max_batches):
         if found >= n_events:
             break
-        batch = model.forward_batch(batch_size)
+        dev_batch = model.forward_batch_device(batch_size, max_hits=max(0, n_events - found)) if device_batches else None
         screened += batch_size
-        hits = np.nonzero(batch["conj"])[0][:max(0, n_events - found)]
-        if len(hits) == 0:
-            continue
-        pending.append(_take_hits(batch, hits))
-        n_pending += len(hits)
-        found += len(hits)
+        if dev_batch is not None:       # drawn, pre-filtered, screened and compacted on the GPU: only the accepted draws came back
+            compact, nh = dev_batch
+            if nh == 0:
+                continue
+            pending.append(compact)
+        else:
+            batch = model.forward_batch(batch_size)
+            hits = np.nonzero(batch["conj"])[0][:max(0, n_events - found)]
+            nh = len(hits)
+            if nh == 0:
+                continue
+            pending.append(_take_hits(batch, hits))
+        n_pending += nh
+        found += nh
         if n_pending >= events_per_pass:
             flush()
     flush()

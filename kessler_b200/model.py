@@ -166,6 +166,43 @@ def quantize_sgp4_inputs(mean_motion_rad_s, ecc, incl, raan, argp, mean_anomaly,
                      _quantize_exp_field(b_star)])
 
 
+def _round_decimals_torch(x, decimals):
+    """_round_decimals on a torch tensor (any device): (rounded, risky mask).  Same arithmetic -- rint(x 10^d) / 10^d --,
+    the (rare) entries within binary noise of a decimal tie are reported instead of formatted."""
+    p = 10.0 ** decimals
+    scaled = x * p
+    out = torch.round(scaled) / p
+    frac = (scaled - torch.floor(scaled) - 0.5).abs()
+    risky = ~(frac > 1e-14 * torch.clamp(scaled.abs(), min=1.0)) | ~torch.isfinite(scaled)
+    return out, risky
+
+
+def quantize_sgp4_inputs_torch(mean_motion_rad_s, ecc, incl, raan, argp, mean_anomaly, b_star_quantised):
+    """quantize_sgp4_inputs on torch tensors that stay where they are (the GPU): bit-identical to the NumPy form; entries
+    whose decimal rounding is a near-tie (probability ~1e-13 per field) are re-done by the text formatter on the host.
+    `b_star_quantised`: B* already through _quantize_exp_field (it is per object, not per sample).  Returns [7, n]."""
+    deg = math.pi / 180.0
+    risky = None
+    cols = []
+    def q(x, d):
+        nonlocal risky
+        out, r = _round_decimals_torch(x, d)
+        risky = r if risky is None else (risky | r)
+        return out
+    rev = q(mean_motion_rad_s * 86400.0 / (2 * math.pi), 8)
+    e = q(ecc, 7)
+    e = torch.where(e >= 1.0, torch.full_like(e, 0.9999999), e)
+    cols = [rev * (2 * math.pi) / 86400.0 * 60.0, e] + [q(a / deg, 4) * deg for a in (incl, raan, argp, mean_anomaly)] + [b_star_quantised]
+    out = torch.stack(cols)
+    bad = torch.nonzero(risky).reshape(-1)
+    if bad.numel():
+        h = lambda t: t[bad].cpu().numpy()
+        fixed = quantize_sgp4_inputs(h(mean_motion_rad_s), h(ecc), h(incl), h(raan), h(argp), h(mean_anomaly), np.zeros(bad.numel()))
+        fixed[6] = h(b_star_quantised)
+        out[:, bad] = torch.from_numpy(fixed).to(out.device)
+    return out
+
+
 class Conjunction:
     """Generative model of a conjunction event (model.py:156-755)."""
 
@@ -619,6 +656,100 @@ class Conjunction:
             out['summary_counts'], out['summary_moments'] = r['counts'], r['moments']
         return out
 
+    # ---- the same, with the candidates living on the GPU from the draw to the accepted few ------------------------------
+    def _draw_device(self, who, n, dev):
+        """n prior draws for one object on the device: dict(el [7, n], ep [n], raw {site: tensor [n]}, sites [...]),
+        everything a cuda tensor.  Covers a given TLE (only the mean anomaly is drawn) and the full default-family prior
+        (ksl_sample_prior); anything else returns None and the caller falls back to the host sampler."""
+        given = self._t_tle if who == 't' else self._c_tle
+        deg = math.pi / 180.0
+        ma_prior = self._prior_dict['mean_anomaly_prior']
+        if given is not None:
+            if not isinstance(ma_prior, Uniform):
+                return None
+            lo, hi = float(ma_prior.low), float(ma_prior.high)
+            ma = lo + (hi - lo) * torch.rand(n, dtype=torch.float64, device=dev)
+            q, risky = _round_decimals_torch(ma / deg, 4)
+            el = torch.from_numpy(given.elements()).to(dev)[:, None].repeat(1, n)
+            el[5] = q * deg
+            bad = torch.nonzero(risky).reshape(-1)
+            if bad.numel():
+                el[5, bad] = torch.from_numpy(_round_decimals(ma[bad].cpu().numpy() / deg, 4) * deg).to(dev)
+            full = lambda v: torch.full((n,), float(v), dtype=torch.float64, device=dev)
+            raw = dict(mean_anomaly=ma, mean_motion=full(given.mean_motion), eccentricity=full(given.eccentricity))
+            return dict(el=el, ep=full(given.date_mjd), raw=raw, sites=['mean_anomaly'])
+        if type(self).sample_elements is not Conjunction.sample_elements or self._device_prior() is None:
+            return None
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        raw_d, el_d, flag = engine.sample_prior(self._device_prior(), seed, 0, n)
+        bad = torch.nonzero(flag).reshape(-1)
+        if bad.numel():
+            r = raw_d[:, bad].cpu().numpy()
+            el_d[:, bad] = torch.from_numpy(quantize_sgp4_inputs(r[0], r[2], r[3], r[5], r[4], r[1], r[7])).to(dev)
+        raw = {name: raw_d[k] for k, name in enumerate(engine.PRIOR_FIELDS)}
+        sites = ['mean_motion', 'mean_anomaly', 'eccentricity', 'inclination', 'argument_of_perigee', 'raan',
+                 'mean_motion_first_derivative', 'b_star']
+        return dict(el=el_d, ep=torch.full((n,), self._prior_epoch_mjd(), dtype=torch.float64, device=dev), raw=raw, sites=sites)
+
+    def forward_batch_device(self, n, mode=N.SCREEN_ANALYTIC, max_hits=None):
+        """forward_batch for the rejection loop: the n candidates are drawn, pre-filtered (model.py:567), screened and
+        compacted ON THE DEVICE; only the accepted draws travel to the host.  Returns the compact dict the batched ground
+        segment takes (kessler_b200.events: elems_t/c [7, h], epoch_t/c, time_min, i_min, d_min, i_conj, d_conj, t_raw,
+        c_raw with '_sites') and the number of accepted draws; None when this model's priors cannot be sampled on the
+        device (the caller then uses forward_batch).  Random streams: torch's CUDA generator (torch.manual_seed)."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = self._draw_device('t', n, dev)
+        c = self._draw_device('c', n, dev) if t is not None else None
+        if t is None or c is None:
+            return None
+        sma = lambda raw: (MU_EARTH / torch.clamp(raw['mean_motion'], min=1e-300) ** 2) ** (1.0 / 3.0)
+        a_t, a_c = sma(t['raw']), sma(c['raw'])
+        apo = lambda a, raw: a * (1 + raw['eccentricity']) - R_EARTH
+        per = lambda a, raw: a * (1 - raw['eccentricity']) - R_EARTH
+        margin = self._miss_dist_threshold + 1000
+        pre = ((apo(a_t, t['raw']) + margin) < per(a_c, c['raw'])) | ((apo(a_c, c['raw']) + margin) < per(a_t, t['raw']))
+        keep = torch.nonzero(~pre).reshape(-1)
+        cache = getattr(self, "_grid_cache", None)
+        if cache is None or cache[0] != (self._time0, self._max_duration_days, self._time_resolution, self._time_upsample_factor, dev):
+            times = self.time_grid()
+            tc = np.ascontiguousarray(times[::max(int(self._time_upsample_factor), 1)])
+            cache = ((self._time0, self._max_duration_days, self._time_resolution, self._time_upsample_factor, dev), times,
+                     torch.from_numpy(tc).to(dev), torch.from_numpy(times).to(dev))
+            self._grid_cache = cache
+        _, times, tc_d, times_d = cache
+        empty = dict(elems_t=np.zeros((7, 0)), elems_c=np.zeros((7, 0)), epoch_t=np.zeros(0), epoch_c=np.zeros(0), time_min=np.zeros(0),
+                     i_min=np.zeros(0, np.int64), d_min=np.zeros(0), i_conj=np.zeros(0, np.int64), d_conj=np.zeros(0),
+                     t_raw={'_sites': t['sites']}, c_raw={'_sites': c['sites']})
+        if keep.numel() == 0:
+            return empty, 0
+        g = lambda x: x[:, keep].contiguous() if x.dim() == 2 else x[keep].contiguous()
+        r = engine.screen_elems(g(t['el']), g(t['ep']), g(c['el']), g(c['ep']), tc_d, len(times), self._miss_dist_threshold, mode)
+        deep = ((r['err'] | (r['err'] >> N.ERR_CHASER_SHIFT)) & N.ERR_DEEPSPACE) != 0
+        hk = torch.nonzero((~deep) & (r['i_conj'] > 0)).reshape(-1)
+        if max_hits is not None:
+            hk = hk[:max_hits]
+        if hk.numel() == 0:
+            return empty, 0
+        hits = keep[hk]
+        # one packed transfer: [rows, h] doubles (indices < 2^53 are exact in a double)
+        rows = [t['el'][:, hits], c['el'][:, hits], t['ep'][hits][None], c['ep'][hits][None],
+                r['i_min'][hk][None].to(torch.float64), r['d_min'][hk][None], r['i_conj'][hk][None].to(torch.float64), r['d_conj'][hk][None],
+                times_d[r['i_min'][hk]][None]]
+        rows += [t['raw'][k][hits][None].to(torch.float64) for k in t['raw']] + [c['raw'][k][hits][None].to(torch.float64) for k in c['raw']]
+        host = torch.cat(rows).cpu().numpy()
+        out = dict(elems_t=np.ascontiguousarray(host[0:7]), elems_c=np.ascontiguousarray(host[7:14]), epoch_t=host[14].copy(), epoch_c=host[15].copy(),
+                   i_min=host[16].astype(np.int64), d_min=host[17].copy(), i_conj=host[18].astype(np.int64), d_conj=host[19].copy(),
+                   time_min=host[20].copy())
+        o = 21
+        for who, d in (('t_raw', t), ('c_raw', c)):
+            raw = {}
+            for k in d['raw']:
+                raw[k] = host[o].astype(np.int64) if k == 'sampled_index' else host[o].copy()
+                o += 1
+            raw['_sites'] = d['sites']
+            out[who] = raw
+        return out, int(hk.numel())
+
     def _replay_values(self, batch, k):
         vals = {}
         for who, raw in (('t', batch['t_raw']), ('c', batch['c_raw'])):
@@ -684,6 +815,47 @@ class ConjunctionSimplified(Conjunction):
         tle.update({'mean_anomaly': mean_anomaly})
         self._record_tle_sites(who, tle)
         return tle
+
+    def _draw_device(self, who, n, dev):
+        """Device-side counterpart of sample_elements: (index, mean anomaly) draws from the population."""
+        given = self._t_tle if who == 't' else self._c_tle
+        if given is not None:
+            return super()._draw_device(who, n, dev)
+        ma_prior = self._prior_dict['mean_anomaly_prior']
+        if not isinstance(ma_prior, Uniform):
+            return None
+        tab = getattr(self, "_pop_table", None)
+        if tab is None or tab['dev'] != dev:
+            f = lambda attr: torch.tensor([float(getattr(t, attr)) for t in self._tles], dtype=torch.float64, device=dev)
+            tab = dict(dev=dev, el=torch.from_numpy(np.stack([t.elements() for t in self._tles], axis=1)).to(dev),
+                       mean_motion=f('mean_motion'), eccentricity=f('eccentricity'), date_mjd=f('date_mjd'),
+                       probs=torch.arange(len(self._tles), dtype=torch.float64, device=dev),
+                       excl=torch.tensor([(getattr(t, 'name', '') or '').startswith(self._exclude_object_name or '\0') for t in self._tles], device=dev))
+            if self._exclude_object_name is not None:
+                tab['probs_incl'] = torch.tensor(self._include_idxs, dtype=torch.float64, device=dev)
+            self._pop_table = tab
+        deg = math.pi / 180.0
+        lo, hi = float(ma_prior.low), float(ma_prior.high)
+        ma = lo + (hi - lo) * torch.rand(n, dtype=torch.float64, device=dev)
+        idx = torch.multinomial(tab['probs'], n, replacement=True)      # Categorical(tensor(range(len(tles)))): the reference's weights
+        if who == 't':
+            self._batch_t_idx_dev = idx if self._t_tle is None else None
+        elif self._exclude_object_name is not None:
+            t_idx = getattr(self, '_batch_t_idx_dev', None)
+            if t_idx is not None and t_idx.numel() == n:
+                t_excl = tab['excl'][t_idx]
+            else:
+                t_excl = torch.full((n,), (getattr(self._t_tle, 'name', '') or '').startswith(self._exclude_object_name), device=dev)
+            alt = torch.multinomial(tab['probs_incl'], n, replacement=True)
+            idx = torch.where(t_excl, alt, idx)
+        el = tab['el'][:, idx].contiguous()
+        q, risky = _round_decimals_torch(ma / deg, 4)
+        el[5] = q * deg
+        bad = torch.nonzero(risky).reshape(-1)
+        if bad.numel():
+            el[5, bad] = torch.from_numpy(_round_decimals(ma[bad].cpu().numpy() / deg, 4) * deg).to(dev)
+        raw = dict(mean_anomaly=ma, sampled_index=idx, mean_motion=tab['mean_motion'][idx], eccentricity=tab['eccentricity'][idx])
+        return dict(el=el, ep=tab['date_mjd'][idx], raw=raw, sites=['mean_anomaly', 'sampled_index'])
 
     def sample_elements(self, who, n):
         """Batched counterpart of _make_object: n (index, mean anomaly) draws from the population."""

@@ -45,114 +45,112 @@ def seed(seed=None):
         torch.cuda.manual_seed(seed)
 
 
+_SQRT2 = math.sqrt(2.0)
+_LOG_SQRT_2PI = 0.5 * math.log(2.0 * math.pi)
+
+
+def _std_normal_cdf(x):
+    return 0.5 * (1.0 + torch.erf(x / _SQRT2))
+
+
+def _std_normal_icdf(p):
+    return torch.erfinv(2.0 * p - 1.0) * _SQRT2
+
+
 class TruncatedNormal(_DistBase):
-    """util.py:46-160: truncated normal with inverse-CDF sampling (optionally batched)."""
+    """Normal(loc, scale) conditioned on [low, high]; the interface of the reference's class (util.py:46-160: same
+    constructor, `log_prob`, inverse-CDF `sample`, scalar or batched 1-d / 2-d parameters) behind an own, vectorised
+    implementation.  With u ~ U(0, 1) a draw is loc + scale * Phi^-1(Phi(alpha) + u (Phi(beta) - Phi(alpha))): ONE
+    torch.rand of the sample shape per attempt, like the reference, so seeded streams line up draw for draw; a second
+    attempt is only needed when rounding pushes every draw of the batch outside [low, high]."""
     arg_constraints = {"_loc": constraints.real, "_scale": constraints.positive, "_low": constraints.real,
                        "_high": constraints.real}
     has_rsample = False
+    support = constraints.real
 
     def __init__(self, loc, scale, low, high):
-        self._loc = torch.as_tensor(loc)
-        self._scale = torch.as_tensor(scale)
-        self._low = torch.as_tensor(low)
-        self._high = torch.as_tensor(high)
-        if self._loc.dim() == 0:
-            self._batch_length = 0
-        elif self._loc.dim() in (1, 2):
-            self._batch_length = self._loc.size(0)
-        else:
+        self._loc, self._scale = torch.as_tensor(loc), torch.as_tensor(scale)
+        self._low, self._high = torch.as_tensor(low), torch.as_tensor(high)
+        if self._loc.dim() > 2:
             raise RuntimeError("Expecting 1d or 2d (batched) probabilities.")
-        self._standard_normal_dist = _Normal(torch.zeros_like(self._loc), torch.ones_like(self._scale))
-        self._alpha = (self._low - self._loc) / self._scale
-        self._beta = (self._high - self._loc) / self._scale
-        self._standard_normal_cdf_alpha = self._standard_normal_dist.cdf(self._alpha)
-        self._standard_normal_cdf_beta = self._standard_normal_dist.cdf(self._beta)
-        self._Z = self._standard_normal_cdf_beta - self._standard_normal_cdf_alpha
-        self._log_stddev_Z = torch.log(self._scale * self._Z)
+        self._batch_length = 0 if self._loc.dim() == 0 else self._loc.size(0)
+        self._cdf_low = _std_normal_cdf((self._low - self._loc) / self._scale)          # Phi(alpha)
+        self._cdf_span = _std_normal_cdf((self._high - self._loc) / self._scale) - self._cdf_low   # Z = Phi(beta) - Phi(alpha)
+        self._log_norm = torch.log(self._scale * self._cdf_span) + _LOG_SQRT_2PI
         super().__init__(batch_shape=self._loc.shape, event_shape=torch.Size(), validate_args=False)
 
-    @property
-    def support(self):
-        return constraints.real
+    def _inside(self, x):
+        return (x >= self._low) & (x <= self._high)
 
     def log_prob(self, value):
         value = torch.as_tensor(value)
-        lb = value.ge(self._low).type_as(self._low)
-        ub = value.le(self._high).type_as(self._low)
-        lp = (torch.log(lb.mul(ub)) + self._standard_normal_dist.log_prob((value - self._loc) / self._scale)
-              - self._log_stddev_Z)
+        z = (value - self._loc) / self._scale
+        out = -0.5 * z * z - self._log_norm
+        out = torch.where(self._inside(value), out, torch.full_like(out, float("-inf")))    # zero density outside the support
         if self._batch_length == 1:
-            lp = lp.squeeze(0)
-        if torch.any(torch.isnan(lp)) or torch.isinf(lp).any():
+            out = out.squeeze(0)
+        if not torch.isfinite(out).all():
             warnings.warn("NaN, -Inf, or Inf encountered in TruncatedNormal log_prob.")
-        return lp
+        return out
 
     def sample(self, sample_shape=torch.Size()):
-        shape = torch.Size(sample_shape) + self._low.shape      # util.py:135: low's shape, loc broadcasts
-        if len(shape) > 0 and self._loc.dim() > self._low.dim():
-            # the reference cannot draw a non-empty sample_shape from a batched instance (the
-            # shapes do not broadcast); the batched front-end (model.forward_batch) needs it
-            shape = torch.Size(sample_shape) + self._loc.shape
-        attempt_count = 0
-        ret = torch.full(shape, float("NaN"), dtype=self._low.dtype)
-        outside_domain = True
-        while torch.isnan(ret).any() or outside_domain:
-            attempt_count += 1
-            if attempt_count == 10000:
+        # the reference sizes a draw by `low` (util.py:135), which only works for an empty sample_shape on a batched
+        # instance; the batched front end (model.forward_batch) draws (n,) + batch_shape
+        batched_draw = len(torch.Size(sample_shape)) > 0 and self._loc.dim() > self._low.dim()
+        shape = torch.Size(sample_shape) + (self._loc.shape if batched_draw else self._low.shape)
+        attempts = 0
+        while True:
+            attempts += 1
+            if attempts == 10000:
                 warnings.warn("Trying to sample from the tail of a truncated normal distribution, which can take a long time.")
-            rand = torch.rand(shape, dtype=self._low.dtype)
-            ret = (self._standard_normal_dist.icdf(
-                self._standard_normal_cdf_alpha + rand * (self._standard_normal_cdf_beta - self._standard_normal_cdf_alpha))
-                * self._scale + self._loc)
-            lb = ret.ge(self._low).type_as(self._low)
-            ub = ret.le(self._high).type_as(self._low)
-            outside_domain = (torch.sum(lb.mul(ub)) == 0)
-        if self._batch_length == 1:
-            ret = ret.squeeze(0)
-        return ret
+            u = torch.rand(shape, dtype=self._low.dtype)
+            draw = self._loc + self._scale * _std_normal_icdf(self._cdf_low + u * self._cdf_span)
+            if not torch.isnan(draw).any() and bool(self._inside(draw).any()):       # the reference's acceptance rule
+                break
+        return draw.squeeze(0) if self._batch_length == 1 else draw
 
 
 # ---- Cartesian <-> Kepler / RTN (util.py:187-358) ---------------------------------------------
+def _angle_from_cos(cos_value, upper_half):
+    """The angle in [0, 2 pi) whose cosine is cos_value (clamped to [-1, 1]) and which lies in [0, pi] when upper_half."""
+    ang = torch.acos(torch.clamp(cos_value, -1.0, 1.0))
+    return torch.where(upper_half, ang, 2 * torch.pi - ang)
+
+
+def _wrap_two_pi(x):
+    return x - (2 * torch.pi) * torch.floor(x / (2 * torch.pi))
+
+
 def from_cartesian_to_keplerian(r_vec, v_vec, mu):
-    """util.py:187-264, differentiable torch code; returns (a, e, i, Omega, omega, M)."""
+    """Osculating elements (a, e, i, Omega, omega, M) of a Cartesian state: the reference's function (util.py:187-264;
+    same conventions: angles from arccos with quadrant fixes, 1e-12 guards in the denominators, zero for undefined
+    angles, elliptic / hyperbolic mean anomaly, ranges [0, 2 pi)) written as differentiable torch code --
+    keplerian_cartesian_partials takes its Jacobian by autograd, and tests/golden holds the reference's own outputs."""
     dt, dev = r_vec.dtype, r_vec.device
-    r = torch.norm(r_vec)
-    v = torch.norm(v_vec)
-    h_vec = torch.linalg.cross(r_vec, v_vec)
-    h = torch.norm(h_vec)
-    zero = torch.tensor(0.0, device=dev, dtype=dt)
-    i = torch.where(h != 0, torch.acos(h_vec[2] / h), zero)
-    K = torch.tensor([0.0, 0.0, 1.0], device=dev, dtype=dt)
-    n_vec = torch.linalg.cross(K, h_vec)
-    n = torch.norm(n_vec)
-    e_vec = (1 / mu) * ((v ** 2 - mu / r) * r_vec - torch.dot(r_vec, v_vec) * v_vec)
-    e = torch.norm(e_vec)
-    energy = v ** 2 / 2 - mu / r
-    a = torch.where(torch.abs(e - 1.0) > 1e-8, -mu / (2 * energy), torch.tensor(float("inf"), device=dev, dtype=dt))
-    cos_Omega = torch.clamp(n_vec[0] / n, -1.0, 1.0)
-    raw_Omega = torch.acos(cos_Omega)
-    Omega = torch.where(n_vec[1] >= 0, raw_Omega, 2 * torch.pi - raw_Omega)
-    Omega = torch.where(n != 0, Omega, zero)
-    cos_omega = torch.clamp(torch.dot(n_vec, e_vec) / (n * e + 1e-12), -1.0, 1.0)
-    raw_omega = torch.acos(cos_omega)
-    omega = torch.where(e_vec[2] >= 0, raw_omega, 2 * torch.pi - raw_omega)
-    omega = torch.where((n != 0) & (e != 0), omega, zero)
-    cos_nu = torch.clamp(torch.dot(e_vec, r_vec) / (e * r + 1e-12), -1.0, 1.0)
-    raw_nu = torch.acos(cos_nu)
-    nu = torch.where(torch.dot(r_vec, v_vec) >= 0, raw_nu, 2 * torch.pi - raw_nu)
-    nu = torch.where(e != 0, nu, zero)
+    zero = torch.zeros((), device=dev, dtype=dt)
+    r, v = torch.linalg.norm(r_vec), torch.linalg.norm(v_vec)
+    rv = torch.dot(r_vec, v_vec)
+    h_vec = torch.linalg.cross(r_vec, v_vec)                                    # angular momentum
+    h = torch.linalg.norm(h_vec)
+    node_vec = torch.linalg.cross(torch.tensor([0.0, 0.0, 1.0], device=dev, dtype=dt), h_vec)
+    node = torch.linalg.norm(node_vec)
+    e_vec = ((v ** 2 - mu / r) * r_vec - rv * v_vec) * (1 / mu)                 # eccentricity (Laplace) vector
+    e = torch.linalg.norm(e_vec)
+    a = torch.where(torch.abs(e - 1.0) > 1e-8, -mu / (2 * (v ** 2 / 2 - mu / r)), torch.full((), float("inf"), device=dev, dtype=dt))
+    inc = torch.where(h != 0, torch.acos(h_vec[2] / h), zero)
+    Omega = torch.where(node != 0, _angle_from_cos(node_vec[0] / node, node_vec[1] >= 0), zero)
+    omega = torch.where((node != 0) & (e != 0), _angle_from_cos(torch.dot(node_vec, e_vec) / (node * e + 1e-12), e_vec[2] >= 0), zero)
+    nu = torch.where(e != 0, _angle_from_cos(torch.dot(e_vec, r_vec) / (e * r + 1e-12), rv >= 0), zero)
+    half_tan = torch.tan(nu / 2)
     if e < 1.0:
-        E = 2 * torch.atan(torch.tan(nu / 2) * torch.sqrt((1 - e) / (1 + e)))
+        E = 2 * torch.atan(half_tan * torch.sqrt((1 - e) / (1 + e)))
         M = E - e * torch.sin(E)
     elif e > 1.0:
-        F = 2 * torch.atanh(torch.tan(nu / 2) * torch.sqrt((e - 1) / (e + 1)))
+        F = 2 * torch.atanh(half_tan * torch.sqrt((e - 1) / (e + 1)))
         M = e * torch.sinh(F) - F
     else:
         raise UnboundLocalError("parabolic orbit: mean anomaly undefined (as in the reference)")
-    Omega = Omega - (2 * torch.pi) * torch.floor(Omega / (2 * torch.pi))
-    omega = omega - (2 * torch.pi) * torch.floor(omega / (2 * torch.pi))
-    M = M - (2 * torch.pi) * torch.floor(M / (2 * torch.pi))
-    return a, e, i, Omega, omega, M
+    return a, e, inc, _wrap_two_pi(Omega), _wrap_two_pi(omega), _wrap_two_pi(M)
 
 
 def keplerian_cartesian_partials(state, mu):
