@@ -727,12 +727,14 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
     const double tempe = fma_rn(c(KSL_F_BC5), smm - c(KSL_C_SINMAO), c(KSL_F_BC4) * t);
     const double am = c(KSL_C_AOBASE) * tempa * tempa;
     const double em_raw = c(KSL_C_ECCO) - tempe;
-    const double em = fmax(em_raw, 1.0e-6);        // the reference's clamp; below -0.001 it raises error 1 (exact route)
+    // the reference clamps em at 1e-6 and raises error 1 below -0.001: the general form follows it (a near-circular,
+    // high-drag record weeks from its epoch), the near-circular form simply declines below 1e-6 (one compare)
+    const double em = small_e ? em_raw : fmax(em_raw, 1.0e-6);
     // validity: sincos_grid needs < 2^18; |argpm| < 32 and |nodem| < 64 keep |u| small and bound what reducing these
     // UNWRAPPED angles by 2 pi instead of the reference's 2pi_d costs (2.4e-16 rad per turn: < 3e-15); |temp0| within
     // the kernels above
     bool ok = abs_below_pow2(xmdf, 16) && abs_below_pow2(argpm, 5) && abs_below_pow2(nodem, 6) &&
-              abs_below_pow2(temp0, small_e ? -4 : 0) && (em_raw >= -1.0e-3);
+              abs_below_pow2(temp0, small_e ? -4 : 0) && (em_raw >= (small_e ? 1.0e-6 : -1.0e-3));
     const double mm = mad_2r(c(KSL_C_NO), templ, mm0);
     const double xlm = add_rn(add_rn(mm, argpm), nodem);
     // The reference wraps nodem, argpm, xlm and mm = xlm - argpm - nodem to [0, 2 pi) with exact remainders
