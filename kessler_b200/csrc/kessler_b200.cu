@@ -633,6 +633,21 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
         int e_t = 0, e_c = 0;
         double cutoff = INFINITY;   // warp-wide running minimum (m^2), refreshed whenever a lane visited a segment
         float want_f = INFINITY;    // what a segment's lower bound has to exceed to be skipped (km^2), follows cutoff
+        // Lazy search (one object against a catalog: consecutive traces are unrelated, the pilot chunk is off, and a
+        // trace sets a new running minimum at almost every orbit -- a third of the chunks would enter the exact-candidate
+        // stage).  A segment that may hold the minimum but cannot hold a threshold crossing is not searched at once: its
+        // lane keeps its index and lower bound, and the warp keeps `cut_f`, an UPPER bound of the trace's final minimum
+        // (every such segment holds a fine point below its ub).  Segments whose lower bound exceeds cut_f are skipped
+        // like those that exceed the running minimum; a lane that meets a second candidate drops the first when it is
+        // dead (lb above cut_f) and otherwise searches the new one on the spot.  After the last chunk the surviving
+        // candidates -- typically one or two per trace -- are searched: their two end points are evaluated again (same
+        // function of (record, epoch): same positions).  The result is exactly the eager one.
+        constexpr bool kLazy = kSharedTarget && kMode == KSL_SCREEN_ANALYTIC;
+        const bool lazy = kLazy && ja_tab != nullptr && p.scale <= 0.125 && (double)p.n_coarse * 1.2e-7 <= 0.25 * p.scale;
+        const float dl_f = (float)(2.0 * p.scale), thr2_f = (float)(p.thr2 * 1e-6), thr2_want_f = ksl::segment_want_f32(0.0, true, p.thr2);
+        int kd = -1;                // the lane's deferred segment ends at epoch kd (-1: none)
+        float lbd = 0.0f;           // its lower bound (km^2)
+        float cut_f = INFINITY;     // warp-wide upper bound of the final minimum from deferred segments (km^2)
         // lane i of a chunk evaluates epoch k = base + i and owns the segment [k-1, k] that ENDS there; lane 0
         // finds the left end, lane 31 of the previous chunk, in the warp's carry slot (no epoch evaluated twice).
         // -- SGP4 of one epoch per lane: both objects (the shared target's position is looked up) ----------------------
@@ -679,7 +694,30 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
                 d0[x] = __shfl_up_sync(0xffffffffu, d1[x], 1);
                 if (lane == 0) d0[x] = s_carry_f[x];
             }
-            const bool need = owner && (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable_f32(d0, d1, want_f));
+            // what a segment's lower bound has to exceed to be skipped: the running minimum -- or the upper bound of the
+            // final one the deferred segments give --, but never less than the threshold while this lane still looks for
+            // its first crossing
+            const float eff_f = (kLazy && lazy) ? fmaxf(fminf(want_f, cut_f), best.conj_j == kNoIndexW ? thr2_want_f : 0.0f) : want_f;
+            bool need = owner && (kMode == KSL_SCREEN_BRUTE || !ksl::segment_skippable_f32(d0, d1, eff_f));
+            if (kLazy && lazy && __any_sync(0xffffffffu, need)) {
+                bool tightened = false;
+                float lb, ub;
+                if (need && ksl::segment_bounds_f32(d0, d1, dl_f, &lb, &ub) &&
+                    !(best.conj_j == kNoIndexW && lb < thr2_f * 1.0001f + 1e-6f)) {     // no crossing possible in it (or none needed)
+                    const float cut_new = fminf(cut_f, ub);
+                    if (kd < 0 || lbd > cut_new) {       // nothing deferred yet, or what is deferred is dead: keep this one instead
+                        kd = k;
+                        lbd = lb;
+                        need = false;
+                    }
+                    tightened = cut_new < cut_f;
+                    cut_f = cut_new;
+                }
+                if (__any_sync(0xffffffffu, tightened)) {
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) cut_f = fminf(cut_f, __shfl_xor_sync(0xffffffffu, cut_f, d));
+                }
+            }
             // stage 2 (rare): the neighbour's full positions, then the exact candidate evaluation
             if (__any_sync(0xffffffffu, need)) {
                 double t0[3], c0[3];
@@ -740,6 +778,22 @@ __global__ void __launch_bounds__(kScreenThreads, KSL_SCREEN_MIN_CTAS) k_screen_
         for (int base = 0; base <= last; base += 32) {
             evaluate(base + lane, rt, rc);
             search(base + lane, false, rt, rc);
+        }
+        if (kLazy && lazy) {
+            // the deferred segments that can still hold the minimum: lower bound not above what is known by now
+            const float known = fminf(cut_f, ksl::segment_want_f32(cutoff, false, p.thr2));
+            const bool alive = kd >= 1 && lbd <= known;
+            if (__any_sync(0xffffffffu, alive)) {
+                double t0[3] = {0.0, 0.0, 0.0}, c0[3] = {0.0, 0.0, 0.0};
+                const int ke = alive ? kd : 1;
+                evaluate(ke - 1, t0, c0);
+                evaluate(ke, rt, rc);
+                if (alive) {
+                    Best b = best_expand(best);
+                    ksl::segment_search<kMode>(ke - 1, last, p.scale, p.n_coarse, p.n_fine, p.thr2, t0, rt, c0, rc, b, ja_tab);
+                    best = best_compact(b);
+                }
+            }
         }
         e_t = __reduce_or_sync(0xffffffffu, e_t);
         e_c = __reduce_or_sync(0xffffffffu, e_c);

@@ -151,6 +151,34 @@ KSL_HD bool segment_skippable_f32(const float d0[3], const float d1[3], float wa
     const bool out = rising ? (a0 > want) : (falling ? (q1 > want) : ((a0 - want) * a2 > a1 * a1));
     return out && (a0 < INFINITY) && (a2 < INFINITY);
 }
+// Bounds of the squared distance over the fine points of one segment, in FP32 (km^2), for the lazy search of the warp
+// kernel: lb <= every fine point of the segment (the quadratic's minimum over [0, 1] minus the FP32 margin), and
+// ub >= AT LEAST ONE fine point of the segment: the quadratic at most `dl` away from its minimiser on [0, 1], where dl
+// (in units of the interpolation weight) is a distance within which the segment is guaranteed to hold a fine point
+// (the callers pass 2 fine steps: torch's float32 floor can move a boundary point into the neighbouring segment), plus
+// the margin.  q(l* + d) - q(l*) = q'(l*) d + a2 d^2 with q'(l*) = 0 at an interior minimiser, 2 a1 at l* = 0, 2 (a1 + a2)
+// at l* = 1.  Returns false when the segment is not finite (then nothing is bounded).
+KSL_HD bool segment_bounds_f32(const float d0[3], const float d1[3], float dl, float *lb, float *ub) {
+    const float bx = d1[0] - d0[0], by = d1[1] - d0[1], bz = d1[2] - d0[2];
+    const float a0 = fmaf(d0[0], d0[0], fmaf(d0[1], d0[1], d0[2] * d0[2]));
+    const float a1 = fmaf(d0[0], bx, fmaf(d0[1], by, d0[2] * bz));
+    const float a2 = fmaf(bx, bx, fmaf(by, by, bz * bz));
+    const float margin = 1e-4f * (a0 + a2);
+    float qmin, slope;
+    if (a1 >= 0.0f) {                      // rising: minimum at the segment's start
+        qmin = a0;
+        slope = a1 + a1;
+    } else if (a1 + a2 <= 0.0f) {          // falling: at its end
+        qmin = a0 + (a1 + a1) + a2;
+        slope = -2.0f * (a1 + a2);
+    } else {                               // interior vertex (a2 > -a1 > 0)
+        qmin = a0 - a1 * a1 / a2;
+        slope = 0.0f;
+    }
+    *lb = qmin - margin;
+    *ub = qmin + fmaf(slope, dl, a2 * dl * dl) + margin;
+    return (a0 < INFINITY) && (a2 < INFINITY) && (*ub == *ub);
+}
 // the target of the FP32 test: what the bound has to exceed, km^2 (cur in m^2; +inf until the first visit)
 KSL_HD float segment_want_f32(double cur, bool conj_open, double thr2) {
     return (float)((fmax(cur, conj_open ? thr2 : 0.0) * (1.0 + 1e-9) + 1.0) * 1e-6);

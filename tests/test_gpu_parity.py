@@ -299,6 +299,43 @@ def test_screen_shared_target_catalog(eng):
     assert np.isnan(ref["d_min"][ref["i_min"] >= 0]).any()   # NaN states: first-NaN index semantics exercised
 
 
+def test_screen_catalog_lazy_search_equals_enumeration(eng):
+    """One target against a catalog through the warp kernel, whose shared-target form defers the exact search of a
+    segment until it is known to survive (the lazy search): indices and distances equal the enumeration of all fine
+    points by the same kernel and the CTA kernel's eager search, bit for bit, on the default 7-day grid, with
+    thresholds that produce no / some / many first crossings, on a short grid, and on grids where laziness must
+    switch itself off (few fine points per segment)."""
+    from kessler_b200 import _native as NV
+    gt, ept, _, _, s = common.golden_pair()
+    n = 6000
+    cat = common.synthetic_catalog(n, seed=51)
+    rng = np.random.default_rng(6)
+    # a third of the catalog in the target's own shell and plane family: close approaches and real crossings
+    k = n // 3
+    cat[0, :k] = gt[0] * (1 + rng.normal(size=k) * 2e-3)
+    cat[1, :k] = np.abs(rng.normal(size=k)) * 2e-3
+    cat[2, :k] = gt[2] + rng.normal(size=k) * 0.02
+    epc = np.full(n, ept) + rng.uniform(-2, 2, n)
+    times = K.time_grid(s["time0"], 7.0, 6e5)
+    for tc, nf, thrs in ((np.ascontiguousarray(times[::100]), len(times), (5e3, 2e5, 3e6)),
+                         (np.ascontiguousarray(times[::100][:700]), 69901, (5e4,)),
+                         (np.ascontiguousarray(times[::100][:257]), 1025, (5e4,)),          # 4 fine points per segment: lazy off
+                         (np.ascontiguousarray(times[::100][:300]), 200, (5e4,))):          # down-sampling
+        for thr in thrs:
+            lazy = _screen(eng, gt[:, None], [ept], cat, epc, tc, nf, thr, NV.SCREEN_FORCE_WARP)
+            brute = _screen(eng, gt[:, None], [ept], cat, epc, tc, nf, thr, NV.SCREEN_FORCE_WARP | 1)
+            for key in ("i_min", "i_conj", "err"):
+                assert np.array_equal(lazy[key], brute[key]), (len(tc), nf, thr, key)
+            assert np.array_equal(lazy["d_min"], brute["d_min"], equal_nan=True), (len(tc), nf, thr)
+            assert np.array_equal(lazy["d_conj"], brute["d_conj"], equal_nan=True), (len(tc), nf, thr)
+        sub = slice(0, 1500)
+        cta = _screen(eng, gt[:, None], [ept], cat[:, sub].copy(), epc[sub], tc, nf, thrs[-1], NV.SCREEN_FORCE_CTA)
+        for key in ("i_min", "i_conj", "d_min"):
+            assert np.array_equal(cta[key], lazy[key][sub], equal_nan=True), (len(tc), nf, key)
+    ok = lazy["err"] == 0
+    assert ok.sum() > 0.7 * n
+
+
 def test_screen_degenerate_identical_objects(eng):
     el, ep = common.population_elems()
     tc = ep[0] + np.arange(300) * 0.001
