@@ -40,9 +40,11 @@ def _world():
 
 def exchange_packed(ints, sums, mins=None):
     """The one collective of this package: every rank contributes integer counts (summed exactly), FP64 partial
-    sums (added in RANK ORDER, so the result does not depend on the reduction tree) and FP64 minima, packed into
-    ONE int64 buffer (the doubles travel as their bit patterns) and exchanged with a single all-gather -- <= 1 KB per
-    rank, latency-bound.  Returns new tensors (ints_total, sums_total, mins_total | None); identical on every rank."""
+    sums and FP64 minima, packed into ONE int64 buffer (the doubles travel as their bit patterns) and exchanged with a
+    single all-gather -- <= 1 KB per rank, latency-bound.  Every rank then reduces the same [world, k] table with the
+    same three kernels (sum / sum / min over the rank axis), so the result is bit-identical on all ranks and does not
+    depend on a reduction tree or on message arrival order.  Returns new tensors (ints_total, sums_total,
+    mins_total | None)."""
     if _world() == 1:
         return ints, sums, mins
     ki, ks = ints.numel(), sums.numel()
@@ -50,16 +52,16 @@ def exchange_packed(ints, sums, mins=None):
     if mins is not None:
         pieces.append(mins.reshape(-1).contiguous().view(torch.int64))
     buf = torch.cat(pieces)
-    parts = [torch.empty_like(buf) for _ in range(_world())]
-    dist.all_gather(parts, buf)
-    ints_out = parts[0][:ki].clone()
-    sums_out = parts[0][ki:ki + ks].clone().view(torch.float64)
-    mins_out = parts[0][ki + ks:].clone().view(torch.float64) if mins is not None else None
-    for p in parts[1:]:
-        ints_out += p[:ki]
-        sums_out += p[ki:ki + ks].view(torch.float64)
-        if mins is not None:
-            mins_out = torch.minimum(mins_out, p[ki + ks:].view(torch.float64))
+    table = torch.empty((_world(), buf.numel()), dtype=torch.int64, device=buf.device)
+    try:
+        dist.all_gather_into_tensor(table, buf)
+    except (RuntimeError, NotImplementedError):          # a backend without the flat form
+        parts = [torch.empty_like(buf) for _ in range(_world())]
+        dist.all_gather(parts, buf)
+        table = torch.stack(parts)
+    ints_out = table[:, :ki].sum(dim=0)
+    sums_out = table[:, ki:ki + ks].contiguous().view(torch.float64).sum(dim=0)
+    mins_out = table[:, ki + ks:].contiguous().view(torch.float64).amin(dim=0) if mins is not None else None
     return ints_out.reshape(ints.shape), sums_out.reshape(sums.shape), (mins_out.reshape(mins.shape) if mins is not None else None)
 
 
@@ -83,7 +85,7 @@ def allreduce_counts(counts):
 
 
 def allgather_moments(moments):
-    """Shifted moments about a shared reference state add across ranks, summed in rank order."""
+    """Shifted moments about a shared reference state add across ranks (one fixed-order reduction, identical on every rank)."""
     if _world() == 1:
         return moments
     _, s, _ = exchange_packed(torch.zeros(0, dtype=torch.int64, device=moments.device), moments)

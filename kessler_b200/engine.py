@@ -212,23 +212,34 @@ def pc_count(t_xyz, c_xyz, thr_m, pairing=N.PAIR_ALL, count=None):
 
 
 # --- scale-out Monte Carlo collision probability (device-side draws) ---------------------------
+def mc_pc_pack(mean_t, chol_t, ref_t, mean_c, chol_c, ref_c):
+    """The host-side parameter block of mc_pc, converted once (contiguous float64: means [6], lower triangles [21], reference
+    states [6]); pass the result as `packed=` to skip the per-call conversions."""
+    host = lambda a, k: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1)[:k])
+    tril = lambda L: np.ascontiguousarray(np.asarray(L, dtype=np.float64)[np.tril_indices(6)])
+    return (host(mean_t, 6), tril(chol_t), host(ref_t, 6), host(mean_c, 6), tril(chol_c), host(ref_c, 6))
+
+
 def mc_pc(mean_t, chol_t, bstar_t, tsince_t, ref_t, mean_c, chol_c, bstar_c, tsince_c, ref_c, seed, sample_offset, n,
-          thr_m, mu_m3s2=398600.5e9, n_dump=0, count=None, err_count=None):
+          thr_m, mu_m3s2=398600.5e9, n_dump=0, count=None, err_count=None, packed=None, scratch=None):
     """ksl_mc_pc.  mean_* [6] = (a [m], e, i, raan, argp, M); chol_* = lower-triangular Cholesky factor [6,6]
     of the element covariance; ref_* [6] reference states in metres.  Returns dict(count int64[1] (accumulated),
     moments_t/moments_c f64[28], err_count int64[1], dump [n_dump, 26] or None) of device tensors."""
     dev = _dev()
-    host = lambda a, k: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1)[:k])
-    tril = lambda L: np.ascontiguousarray(np.asarray(L, dtype=np.float64)[np.tril_indices(6)])
-    mean_t, mean_c, ref_t, ref_c = host(mean_t, 6), host(mean_c, 6), host(ref_t, 6), host(ref_c, 6)
-    lt, lc = tril(chol_t), tril(chol_c)
+    mean_t, lt, ref_t, mean_c, lc, ref_c = packed if packed is not None else mc_pc_pack(mean_t, chol_t, ref_t, mean_c, chol_c, ref_c)
     if count is None:
         count = torch.zeros(1, dtype=torch.int64, device=dev)
     if err_count is None:
         err_count = torch.zeros(1, dtype=torch.int64, device=dev)
     moments = torch.empty(2 * N.NMOMENT, dtype=F64, device=dev)
     dump = torch.empty((int(n_dump), 26), dtype=F64, device=dev) if n_dump else None
-    ws = torch.empty(int(N.lib().ksl_mc_pc_ws(int(n))), dtype=torch.uint8, device=dev)
+    need = int(N.lib().ksl_mc_pc_ws(int(n)))
+    if scratch is not None and scratch.get("ws") is not None and scratch["ws"].numel() >= need and scratch["ws"].device == dev:
+        ws = scratch["ws"]                      # caller-held workspace: repeated launches of one size allocate nothing
+    else:
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        if scratch is not None:
+            scratch["ws"] = ws
     N.check(N.lib().ksl_mc_pc(ptr(mean_t), ptr(lt), float(bstar_t), float(tsince_t), ptr(ref_t), ptr(mean_c), ptr(lc),
                               float(bstar_c), float(tsince_c), ptr(ref_c), int(seed), int(sample_offset), int(n), float(thr_m),
                               float(mu_m3s2), ptr(count), ptr(moments), ptr(moments[N.NMOMENT:]), ptr(err_count), ptr(dump),

@@ -38,8 +38,11 @@ def prepare_pair(t_tle, t_state_m, t_cov_rtn, c_tle, c_state_m, c_cov_rtn, time_
     mean_c, L_c = element_distribution(c_tle, c_state_m, c_cov_rtn)
     ts_t = (time_ca_mjd - t_tle.date_mjd) * 1440.0
     ts_c = (time_ca_mjd - c_tle.date_mjd) * 1440.0
-    return dict(mean_t=mean_t, L_t=L_t, bstar_t=t_tle._bstar, ts_t=ts_t, ref_t=nominal_state_m(t_tle, ts_t),
-                mean_c=mean_c, L_c=L_c, bstar_c=c_tle._bstar, ts_c=ts_c, ref_c=nominal_state_m(c_tle, ts_c))
+    pp = dict(mean_t=mean_t, L_t=L_t, bstar_t=t_tle._bstar, ts_t=ts_t, ref_t=nominal_state_m(t_tle, ts_t),
+              mean_c=mean_c, L_c=L_c, bstar_c=c_tle._bstar, ts_c=ts_c, ref_c=nominal_state_m(c_tle, ts_c))
+    pp["packed"] = engine.mc_pc_pack(pp["mean_t"], pp["L_t"], pp["ref_t"], pp["mean_c"], pp["L_c"], pp["ref_c"])
+    pp["scratch"] = {}
+    return pp
 
 
 def run_prepared(pp, n_total, collision_threshold=70.0, seed=2, n_dump=0, chunk=1 << 28, to_host=True):
@@ -56,10 +59,10 @@ def run_prepared(pp, n_total, collision_threshold=70.0, seed=2, n_dump=0, chunk=
         n = min(chunk, hi - start)
         r = engine.mc_pc(pp["mean_t"], pp["L_t"], pp["bstar_t"], pp["ts_t"], pp["ref_t"], pp["mean_c"], pp["L_c"], pp["bstar_c"],
                          pp["ts_c"], pp["ref_c"], seed, start, n, collision_threshold, n_dump=(n_dump if start == lo else 0),
-                         count=count, err_count=err)
+                         count=count, err_count=err, packed=pp.get("packed"), scratch=pp.get("scratch"))
         count, err = r["count"], r["err_count"]
-        mom_t = r["moments_t"].clone() if mom_t is None else mom_t + r["moments_t"]
-        mom_c = r["moments_c"].clone() if mom_c is None else mom_c + r["moments_c"]
+        mom_t = r["moments_t"] if mom_t is None else mom_t + r["moments_t"]
+        mom_c = r["moments_c"] if mom_c is None else mom_c + r["moments_c"]
         if r["dump"] is not None:
             dump = r["dump"]
     dev = torch.device("cuda", torch.cuda.current_device())
