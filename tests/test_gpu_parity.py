@@ -545,6 +545,35 @@ def test_screen_elems_fused_init_is_bit_identical(eng):
         assert ((a["err"] >> 8) & 16).sum() > 0 and (a["i_min"] == -1).sum() > 0
 
 
+def test_screen_without_workspace_static_group_assignment(eng):
+    """ksl_screen's workspace is optional for per-sample targets: without it the warp kernel hands out its groups of
+    traces by static striding instead of the atomic counter.  Same results, straight through the C ABI."""
+    from kessler_b200 import _native as NV
+    elt, ept, elc, epc, times, _ = _golden_batch(5000, 37)
+    tc = np.ascontiguousarray(times[::100][:301])
+    nf = 30001
+    want = _screen(eng, elt, ept, elc, epc, tc, nf, 5e3, NV.SCREEN_FORCE_WARP)
+    dev = torch.device("cuda", 0)
+    ct, it = eng.sgp4_init(elt)
+    cc, ic = eng.sgp4_init(elc)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_ept, d_epc, d_tc = d(ept), d(epc), d(tc)
+    n = elt.shape[1]
+    out = dict(i_min=torch.empty(n, dtype=torch.int64, device=dev), d_min=torch.empty(n, dtype=torch.float64, device=dev),
+               i_conj=torch.empty(n, dtype=torch.int64, device=dev), d_conj=torch.empty(n, dtype=torch.float64, device=dev),
+               err=torch.empty(n, dtype=torch.int32, device=dev))
+    p = NV.ptr
+    NV.check(NV.lib().ksl_screen(p(ct), p(d_ept), p(it), n, p(cc), p(d_epc), p(ic), n, p(d_tc), len(tc), nf, 5e3, NV.SCREEN_FORCE_WARP,
+                                 p(out["i_min"]), p(out["d_min"]), p(out["i_conj"]), p(out["d_conj"]), p(out["err"]), None, NV.stream_ptr()),
+             "ksl_screen")
+    for k in ("i_min", "i_conj", "err", "d_min"):
+        assert np.array_equal(_np(out[k]), want[k]), k
+    # a shared target does need the workspace (its positions are staged there): refused, not crashed
+    rc = NV.lib().ksl_screen(p(ct), p(d_ept), p(it), 1, p(cc), p(d_epc), p(ic), n, p(d_tc), len(tc), nf, 5e3, 0,
+                             p(out["i_min"]), p(out["d_min"]), p(out["i_conj"]), p(out["d_conj"]), p(out["err"]), None, NV.stream_ptr())
+    assert rc == -3 and b"workspace" in NV.lib().ksl_last_error()
+
+
 def test_screen_host_two_devices_two_threads(eng):
     """ksl_screen_host holds a per-DEVICE lock: two host threads driving two devices run concurrently and each gets
     its own results; two threads on ONE device are serialised and both correct.  (One GPU: the second form only.)"""
