@@ -113,21 +113,6 @@ __global__ void __launch_bounds__(128) k_sgp4_init(const double *__restrict__ el
 // ------------------------------------------------------------------------------------
 constexpr int kPropThreads = 128;
 
-// full state through the fast path (either form), exact route when it declines; c: a fast record
-__device__ __forceinline__ int prop_state_from_fast_record(const double *c, double t, double r[3], double v[3], const double *grid,
-                                                           unsigned int *n_exact) {
-    auto ld = [&](int q) { return c[q]; };
-    const bool small = ksl::fast_record_is_small_e(ld, fabs(t));
-    const bool ok = small ? ksl::sgp4_prop_fast_rv<true, true>(ld, t, r, v, grid) : ksl::sgp4_prop_fast_rv<true, false>(ld, t, r, v, grid);
-    if (ok) return 0;
-    *n_exact += 1;
-    double rx[3], vx[3];
-    const int e = ksl::sgp4_state_exact(ld, t, rx, vx);
-    r[0] = rx[0]; r[1] = rx[1]; r[2] = rx[2];
-    v[0] = vx[0]; v[1] = vx[1]; v[2] = vx[2];
-    return e;
-}
-
 __device__ __forceinline__ void store_states_coalesced(double (*stage)[32 * 6], int warp, int lane, long long first_eval_of_warp,
                                                        long long evals_total, double *__restrict__ rv) {
     __syncwarp();
@@ -140,50 +125,88 @@ __device__ __forceinline__ void store_states_coalesced(double (*stage)[32 * 6], 
     }
 }
 
+constexpr int kPropTile = 2 * kPropThreads;     // epochs per tile: two per thread (two independent dependency chains in flight)
 __global__ void __launch_bounds__(kPropThreads) k_sgp4_prop_tile(const double *__restrict__ consts, long long n,
                                                                  const double *__restrict__ tsince, long long m, int per_sample_t,
-                                                                 long long tiles_per_record, double *__restrict__ rv,
+                                                                 int tiles_per_record, long long n_tiles, double *__restrict__ rv,
                                                                  int *__restrict__ err, unsigned long long *__restrict__ n_exact) {
     __shared__ double stage[kPropThreads / 32][32 * 6];
     __shared__ double s_rec[ksl::KSL_NFAST];
     __shared__ __align__(16) double s_grid[2 * ksl::kGridPoints];
-    const long long i = blockIdx.x / tiles_per_record;
-    const long long j0 = (blockIdx.x - i * tiles_per_record) * kPropThreads;
+    // persistent CTAs: the sincos table is staged once per CTA, then the CTA walks its tiles (256 epochs of one record each)
     for (int q = threadIdx.x; q < 2 * ksl::kGridPoints; q += kPropThreads) s_grid[q] = ksl::kGridSinCos[q];
-    if (threadIdx.x < KSL_NCONST) s_rec[threadIdx.x] = consts[(long long)threadIdx.x * n + i];
-    __syncthreads();
-    if (threadIdx.x == 0) ksl::prepare_fast_record(s_rec, 1);
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long j = j0 + threadIdx.x;
-    int e = 0;
     unsigned int nx = 0;
-    if (j < m) {
-        const double t = per_sample_t ? tsince[i * m + j] : tsince[j];
-        double r[3], v[3];
-        e = prop_state_from_fast_record(s_rec, t, r, v, s_grid, &nx);
-        double *st = &stage[warp][lane * 6];
-        st[0] = r[0]; st[1] = r[1]; st[2] = r[2];
-        st[3] = v[0]; st[4] = v[1]; st[5] = v[2];
-    }
-    // the warp's 32 evaluations are consecutive epochs of record i: [i][j0 + 32 warp ...]; rows end at m
-    {
-        __syncwarp();
-        const long long jw = j0 + warp * 32;
-        const long long valid = (m - jw) * 6;       // doubles of this record left from the warp's first epoch on
-        double *dst = rv + (i * m + jw) * 6;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-            const int o = q * 32 + lane;
-            if (o < valid) dst[o] = stage[warp][o];
+    long long staged = -1;
+    auto ld = [&](int q) { return s_rec[q]; };
+    // a CTA owns a CONTIGUOUS run of tiles: consecutive tiles belong to the same record, which is then staged once per
+    // record and not once per tile (no CTA barrier in between)
+    const long long per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const long long tile_end = ((long long)blockIdx.x + 1) * per_cta < n_tiles ? ((long long)blockIdx.x + 1) * per_cta : n_tiles;
+    for (long long tile = (long long)blockIdx.x * per_cta; tile < tile_end; ++tile) {
+        const long long i = tile / tiles_per_record;
+        const int j0 = (int)(tile - i * tiles_per_record) * kPropTile;
+        if (i != staged) {                       // (uniform over the CTA)
+            __syncthreads();                     // the previous record's readers are done (and, the first time, the table is staged)
+            if (threadIdx.x < KSL_NCONST) s_rec[threadIdx.x] = consts[(long long)threadIdx.x * n + i];
+            __syncthreads();
+            if (threadIdx.x == 0) ksl::prepare_fast_record(s_rec, 1);
+            __syncthreads();
+            staged = i;
         }
+        // thread -> epochs ja = j0 + tid and jb = ja + 128 (clamped for the reads; rows end at m)
+        const long long ja = (long long)j0 + threadIdx.x, jb = ja + kPropThreads;
+        const long long jac = ja < m ? ja : m - 1, jbc = jb < m ? jb : m - 1;
+        const double ta = per_sample_t ? tsince[i * m + jac] : tsince[jac];
+        const double tb = per_sample_t ? tsince[i * m + jbc] : tsince[jbc];
+        // the near-circular form when every lane of the warp qualifies at both epochs (one record per warp: the lanes differ in
+        // |t| only), so that the warp never runs both forms; both evaluations in one straight-line block
+        const bool small = __all_sync(0xffffffffu, ksl::fast_record_is_small_e(ld, fmax(fabs(ta), fabs(tb))));
+        double ra[3], va[3], rb[3], vb[3];
+        bool ok_a, ok_b;
+        if (small) {
+            ok_a = ksl::sgp4_prop_fast_rv<true, true>(ld, ta, ra, va, s_grid);
+            ok_b = ksl::sgp4_prop_fast_rv<true, true>(ld, tb, rb, vb, s_grid);
+        } else {
+            ok_a = ksl::sgp4_prop_fast_rv<true, false>(ld, ta, ra, va, s_grid);
+            ok_b = ksl::sgp4_prop_fast_rv<true, false>(ld, tb, rb, vb, s_grid);
+        }
+        int e = 0;
+        if (!ok_a) {
+            double rx[3], vx[3];
+            e |= ksl::sgp4_state_exact(ld, ta, rx, vx);
+            nx += (ja < m) ? 1u : 0u;
+            ra[0] = rx[0]; ra[1] = rx[1]; ra[2] = rx[2]; va[0] = vx[0]; va[1] = vx[1]; va[2] = vx[2];
+        }
+        if (!ok_b) {
+            double rx[3], vx[3];
+            e |= ksl::sgp4_state_exact(ld, tb, rx, vx);
+            nx += (jb < m) ? 1u : 0u;
+            rb[0] = rx[0]; rb[1] = rx[1]; rb[2] = rx[2]; vb[0] = vx[0]; vb[1] = vx[1]; vb[2] = vx[2];
+        }
+        // coalesced stores: each warp's 32 states of a half-tile are consecutive epochs of record i, transposed through smem
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            double *st = &stage[warp][lane * 6];
+            const double *r = half ? rb : ra, *v = half ? vb : va;
+            st[0] = r[0]; st[1] = r[1]; st[2] = r[2];
+            st[3] = v[0]; st[4] = v[1]; st[5] = v[2];
+            __syncwarp();
+            const long long jw = (long long)j0 + half * kPropThreads + warp * 32;
+            const long long valid = (m - jw) * 6;       // doubles of this record left from the warp's first epoch on (<= 0: none)
+            double *dst = rv + (i * m + jw) * 6;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int o = q * 32 + lane;
+                if (o < valid) dst[o] = stage[warp][o];
+            }
+            __syncwarp();
+        }
+        e = __reduce_or_sync(0xffffffffu, e);
+        if (lane == 0 && err && e) atomicOr(err + i, e);
     }
-    e = __reduce_or_sync(0xffffffffu, e);
     nx = __reduce_add_sync(0xffffffffu, nx);
-    if (lane == 0) {
-        if (err && e) atomicOr(err + i, e);
-        if (n_exact && nx) atomicAdd(n_exact, (unsigned long long)nx);
-    }
+    if (lane == 0 && n_exact && nx) atomicAdd(n_exact, (unsigned long long)nx);
 }
 
 __global__ void __launch_bounds__(kPropThreads) k_sgp4_prop(const double *__restrict__ consts, long long n,
@@ -1800,9 +1823,16 @@ int ksl_sgp4_prop_counted(const double *consts, int64_t n, const double *tsince,
         return fail(KSL_E_ARG, "ksl_sgp4_prop: bad argument");
     if (n == 0 || m == 0) return KSL_OK;
     if (m >= 32) {       // a CTA per (record, 128 epochs): the record staged in shared memory
-        const long long tiles = (m + kPropThreads - 1) / kPropThreads;
-        if (tiles * n > 0x7fffffffLL) return fail(KSL_E_ARG, "ksl_sgp4_prop: n*m too large for one launch");
-        k_sgp4_prop_tile<<<(unsigned)(tiles * n), kPropThreads, 0, S(stream)>>>(consts, n, tsince, m, per_sample_t, tiles, rv_km, err, n_exact);
+        const long long tiles = (m + kPropTile - 1) / kPropTile;
+        if (tiles > 0x7fffffffLL) return fail(KSL_E_ARG, "ksl_sgp4_prop: m too large");
+        int sms = 0;
+        const int rc = sm_count(&sms);
+        if (rc) return rc;
+        const long long n_tiles = tiles * n;
+        long long grid = (long long)sms * 4;            // resident CTAs of 128 threads per SM at <= 128 registers
+        if (grid > n_tiles) grid = n_tiles;
+        k_sgp4_prop_tile<<<(unsigned)grid, kPropThreads, 0, S(stream)>>>(consts, n, tsince, m, per_sample_t, (int)tiles, n_tiles, rv_km, err,
+                                                                         n_exact);
     } else {
         const long long total = (long long)n * m;
         const long long blocks = (total + kPropThreads - 1) / kPropThreads;
