@@ -176,7 +176,7 @@ def run_reference(args):
 def kernel_sources_sha():
     import hashlib
     h = hashlib.sha256()
-    for name in ("kessler_b200.cu", "sgp4_device.cuh", "screen_device.cuh", "sincos_grid_table.cuh"):
+    for name in ("screen_kernels.cuh", "sgp4_device.cuh", "screen_device.cuh", "sincos_grid_table.cuh"):
         h.update(open(os.path.join(ROOT, "kessler_b200", "csrc", name), "rb").read())
     return h.hexdigest()[:16]
 

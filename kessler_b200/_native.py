@@ -15,6 +15,7 @@ _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.environ.get("KSL_LIB_PATH") or os.path.join(_PKG, "lib", "libkessler_b200.so")   # env override: tuning experiments only
 SRC = os.path.join(_PKG, "csrc", "kessler_b200.cu")
 HEADERS = [os.path.join(_PKG, "csrc", "sgp4_device.cuh"), os.path.join(_PKG, "csrc", "screen_device.cuh"),
+           os.path.join(_PKG, "csrc", "screen_kernels.cuh"), os.path.join(_PKG, "csrc", "sincos_grid_table.cuh"),
            os.path.join(_PKG, "csrc", "kepler_device.cuh"),
            os.path.join(_ROOT, "include", "kessler_b200.h")]
 
