@@ -26,7 +26,7 @@ import torch
 from . import engine, util
 from . import _native as N
 from .cdm import ConjunctionDataMessage
-from .model import _quantize_exp_field, quantize_sgp4_inputs, quantize_sgp4_inputs_torch  # noqa: F401
+from .model import _quantize_exp_field, _tdiv, quantize_sgp4_inputs, quantize_sgp4_inputs_torch  # noqa: F401
 from .tle import MU_EARTH, epoch_to_datetime, from_datetime_to_mjd, from_mjd_to_datetime, from_mjd_to_epoch_days_after_1_jan
 
 
@@ -153,7 +153,7 @@ def generate_cdm_batch(model, batch, hits, seed=0, t_new_obs=None, c_new_obs=Non
     y_d, resid_d, _ = engine.newton_elements(rv[:, 0, :], D(bstar))
     two_pi = 2 * math.pi
     wrap = lambda a: torch.remainder(a, two_pi)
-    raw_mm_d = y_d[:, 0] / 60.0
+    raw_mm_d = _tdiv(y_d[:, 0], 60.0)            # IEEE division, as the host path's y[:, 0] / 60.0
     q_d = quantize_sgp4_inputs_torch(raw_mm_d, y_d[:, 1], wrap(y_d[:, 2]), wrap(y_d[:, 3]), wrap(y_d[:, 4]), wrap(y_d[:, 5]), bstar_q)   # TLE(dict)
     epoch_obs_by_slot = np.array([obs_epoch_mjd(t) for t in time_cdm])
     epoch_obs = epoch_obs_by_slot[ci]

@@ -166,12 +166,18 @@ def quantize_sgp4_inputs(mean_motion_rad_s, ecc, incl, raan, argp, mean_anomaly,
                      _quantize_exp_field(b_star)])
 
 
+def _tdiv(x, c):
+    """x / c with IEEE division.  (torch's CUDA kernel for `tensor / python_float` multiplies by the rounded reciprocal,
+    which is one ulp off for most divisors; a 0-dim tensor divisor takes the true-division kernel.)"""
+    return x / torch.full((), float(c), dtype=x.dtype, device=x.device)
+
+
 def _round_decimals_torch(x, decimals):
     """_round_decimals on a torch tensor (any device): (rounded, risky mask).  Same arithmetic -- rint(x 10^d) / 10^d --,
     the (rare) entries within binary noise of a decimal tie are reported instead of formatted."""
     p = 10.0 ** decimals
     scaled = x * p
-    out = torch.round(scaled) / p
+    out = _tdiv(torch.round(scaled), p)
     frac = (scaled - torch.floor(scaled) - 0.5).abs()
     risky = ~(frac > 1e-14 * torch.clamp(scaled.abs(), min=1.0)) | ~torch.isfinite(scaled)
     return out, risky
@@ -189,10 +195,10 @@ def quantize_sgp4_inputs_torch(mean_motion_rad_s, ecc, incl, raan, argp, mean_an
         out, r = _round_decimals_torch(x, d)
         risky = r if risky is None else (risky | r)
         return out
-    rev = q(mean_motion_rad_s * 86400.0 / (2 * math.pi), 8)
+    rev = q(_tdiv(mean_motion_rad_s * 86400.0, 2 * math.pi), 8)
     e = q(ecc, 7)
     e = torch.where(e >= 1.0, torch.full_like(e, 0.9999999), e)
-    cols = [rev * (2 * math.pi) / 86400.0 * 60.0, e] + [q(a / deg, 4) * deg for a in (incl, raan, argp, mean_anomaly)] + [b_star_quantised]
+    cols = [_tdiv(rev * (2 * math.pi), 86400.0) * 60.0, e] + [q(_tdiv(a, deg), 4) * deg for a in (incl, raan, argp, mean_anomaly)] + [b_star_quantised]
     out = torch.stack(cols)
     bad = torch.nonzero(risky).reshape(-1)
     if bad.numel():
@@ -669,7 +675,7 @@ class Conjunction:
                 return None
             lo, hi = float(ma_prior.low), float(ma_prior.high)
             ma = lo + (hi - lo) * torch.rand(n, dtype=torch.float64, device=dev)
-            q, risky = _round_decimals_torch(ma / deg, 4)
+            q, risky = _round_decimals_torch(_tdiv(ma, deg), 4)
             el = torch.from_numpy(given.elements()).to(dev)[:, None].repeat(1, n)
             el[5] = q * deg
             bad = torch.nonzero(risky).reshape(-1)
@@ -849,7 +855,7 @@ class ConjunctionSimplified(Conjunction):
             alt = torch.multinomial(tab['probs_incl'], n, replacement=True)
             idx = torch.where(t_excl, alt, idx)
         el = tab['el'][:, idx].contiguous()
-        q, risky = _round_decimals_torch(ma / deg, 4)
+        q, risky = _round_decimals_torch(_tdiv(ma, deg), 4)
         el[5] = q * deg
         bad = torch.nonzero(risky).reshape(-1)
         if bad.numel():

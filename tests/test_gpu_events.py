@@ -189,3 +189,55 @@ def test_generated_cdms_are_complete_and_survive_the_wire_format(setup, tmp_path
     assert len(mine) == len(cdms) and list(mine["TCA"]) == list(frame["TCA"]) and list(mine["CREATION_DATE"]) == list(frame["CREATION_DATE"])
     for key in ("MISS_DISTANCE", "RELATIVE_VELOCITY_T", "OBJECT1_Y", "OBJECT2_CTDOT_N", "COLLISION_PROBABILITY"):
         assert np.allclose(mine[key].to_numpy(dtype=np.float64), frame[key].to_numpy(dtype=np.float64), rtol=1e-12, atol=1e-9)
+
+
+def test_forward_batch_device_returns_what_the_host_path_would_accept(setup):
+    """The device-resident rejection step (draw, pre-filter, screen, compact on the GPU) hands back accepted draws only:
+    re-screening the returned element sets through the host entry point gives the same indices and distances, every one is
+    a conjunction by the reference's rule (i_conj > 0, no deep-space refusal), passes the altitude pre-filter, and its raw
+    draws are the ones its SGP4 inputs were quantised from."""
+    import math
+    M, eng, model, tles = setup["M"], setup["engine"], setup["model"], setup["tles"]
+    from kessler_b200.tle import MU_EARTH, R_EARTH
+    torch.manual_seed(5)
+    got = None
+    for _ in range(6):
+        c, nh = model.forward_batch_device(65536)
+        if nh >= 3:
+            got = c
+            break
+    assert got is not None and got["elems_t"].shape == (7, nh) and got["t_raw"]["_sites"] == ["mean_anomaly", "sampled_index"]
+    times = model.time_grid()
+    tc = np.ascontiguousarray(times[::100])
+    r = eng.screen_host(got["elems_t"], got["epoch_t"], got["elems_c"], got["epoch_c"], tc, len(times), model._miss_dist_threshold)
+    assert np.array_equal(r["i_min"], got["i_min"]) and np.array_equal(r["i_conj"], got["i_conj"])
+    assert np.array_equal(r["d_min"], got["d_min"]) and np.array_equal(r["d_conj"], got["d_conj"])
+    assert (got["i_conj"] > 0).all() and np.array_equal(got["time_min"], times[got["i_min"]])
+    deg = math.pi / 180.0
+    for who in ("t", "c"):
+        raw, el = got[who + "_raw"], got["elems_" + who]
+        idx = raw["sampled_index"]
+        assert idx.dtype == np.int64 and idx.min() >= 1 and idx.max() < len(tles)
+        base = np.stack([tles[int(i)].elements() for i in idx], axis=1)
+        assert np.array_equal(el[[0, 1, 2, 3, 4, 6]], base[[0, 1, 2, 3, 4, 6]])            # the population's own elements ...
+        assert np.array_equal(el[5], M._round_decimals(raw["mean_anomaly"] / deg, 4) * deg)  # ... and the quantised mean anomaly
+        assert np.array_equal(got["epoch_" + who], np.array([tles[int(i)].date_mjd for i in idx]))
+    a = lambda raw: (MU_EARTH / raw["mean_motion"] ** 2) ** (1.0 / 3.0)
+    apo = lambda raw: a(raw) * (1 + raw["eccentricity"]) - R_EARTH
+    per = lambda raw: a(raw) * (1 - raw["eccentricity"]) - R_EARTH
+    margin = model._miss_dist_threshold + 1000
+    pre = ((apo(got["t_raw"]) + margin) < per(got["c_raw"])) | ((apo(got["c_raw"]) + margin) < per(got["t_raw"]))
+    assert not pre.any()
+    # max_hits caps the number handed back; exclude_object_name is honoured per draw on the device too
+    c2, n2 = model.forward_batch_device(65536, max_hits=1)
+    assert n2 <= 1 and c2["elems_c"].shape[1] == n2
+    for t, name in zip(tles, ["STARLINK-%d" % k if k in (3, 7, 11) else "OBJ-%d" % k for k in range(len(tles))]):
+        t.name = name
+    m2 = M.ConjunctionSimplified(tles=tles, exclude_object_name="STARLINK", time0=60727.13899462018)
+    dev = torch.device("cuda", 0)
+    dt = m2._draw_device("t", 20000, dev)
+    dc = m2._draw_device("c", 20000, dev)
+    ti, ci = dt["raw"]["sampled_index"].cpu().numpy(), dc["raw"]["sampled_index"].cpu().numpy()
+    excl = np.isin(ti, (3, 7, 11))
+    k_incl = len(m2._include_idxs)
+    assert excl.any() and ci[excl].max() < k_incl and ci[~excl].max() == len(tles) - 1     # Categorical(tensor(include_idxs)): values < len(include_idxs)

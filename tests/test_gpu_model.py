@@ -356,3 +356,22 @@ def test_config0_thousand_prior_traces_of_the_default_pair(kb):
     assert np.abs(b["d_min"] - ref["d_min"]).max() < 1e-3                         # metres (tolerance of record: 1 m)
     assert np.array_equal(b["conj"], ref["i_conj"] > 0)
     assert np.array_equal(b["time_min"], times[ref["i_min"]])                     # TCA: same fine-grid epoch, bit for bit
+
+
+def test_torch_quantisation_on_the_device_is_bit_identical_to_the_text_path():
+    """quantize_sgp4_inputs_torch (the GPU-resident ground segment) == quantize_sgp4_inputs (== TLE(dict), checked on the
+    CPU) bit for bit on 2e5 random element sets -- including the divisions, which torch's CUDA kernels would otherwise
+    turn into multiplications by a rounded reciprocal."""
+    import math
+    import kessler_b200.model as M
+    rng = np.random.default_rng(12)
+    n = 200000
+    mm = rng.uniform(5e-4, 1.2e-3, n)
+    ecc = np.abs(rng.normal(0.0, 0.01, n))
+    ang = rng.uniform(0, 2 * math.pi, (4, n))
+    bstar = rng.normal(0, 1e-3, n)
+    want = M.quantize_sgp4_inputs(mm, ecc, ang[0], ang[1], ang[2], ang[3], bstar)
+    dev = torch.device("cuda", 0)
+    d = lambda a: torch.from_numpy(a).to(dev)
+    got = M.quantize_sgp4_inputs_torch(d(mm), d(ecc), d(ang[0]), d(ang[1]), d(ang[2]), d(ang[3]), d(M._quantize_exp_field(bstar))).cpu().numpy()
+    assert np.array_equal(got, want)
