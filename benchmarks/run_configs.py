@@ -9,7 +9,8 @@ configs[2]  1e8-sample Monte Carlo collision-probability estimate of one pair (d
 configs[3]  one-vs-catalog screening: 30k synthetic LEO TLEs vs one target over 7 days at the default
             resolution (shared-target path of the fused kernel; the altitude pre-filter of model.py:567
             reported next to the unfiltered rate).
-Each prints one JSON line (rank 0)."""
+Each prints one JSON line (rank 0).  bench.py's `secondary` carries the driver-run form of all three (device-timed, configs[2] as
+strong scaling); this script is the stand-alone, wall-clock form."""
 import argparse
 import json
 import os
@@ -28,20 +29,10 @@ from kessler_b200.tle import MU_EARTH, R_EARTH  # noqa: E402
 
 
 def synthetic_leo_catalog(n, seed=3):
-    """n near-earth element sets in the spirit of default_prior() (model.py:54-153) restricted to what a
-    catalog screen keeps: period < 225 min and perigee > 120 km."""
-    rng = np.random.default_rng(seed)
-    out = np.zeros((7, 0))
-    while out.shape[1] < n:
-        m = 2 * n
-        n_rad_s = np.where(rng.uniform(size=m) < 0.9, rng.normal(1.03e-3, 4e-5, m), rng.normal(7.8e-4, 1.4e-4, m))
-        ecc = np.abs(np.where(rng.uniform(size=m) < 0.85, rng.normal(0.0029, 0.0025, m), rng.normal(0.0135, 0.0069, m)))
-        a = (MU_EARTH / n_rad_s ** 2) ** (1.0 / 3.0)
-        keep = (n_rad_s > 2 * np.pi / (225.0 * 60.0)) & (a * (1 - ecc) - R_EARTH > 120e3) & (n_rad_s < 1.2e-3)
-        el = np.stack([n_rad_s * 60.0, ecc, rng.uniform(0, np.pi, m), rng.uniform(0, 2 * np.pi, m), rng.uniform(0, 2 * np.pi, m),
-                       rng.uniform(0, 2 * np.pi, m), rng.normal(2e-4, 1.1e-3, m)])[:, keep]
-        out = np.concatenate([out, el], axis=1)
-    return np.ascontiguousarray(out[:, :n])
+    """n element sets drawn from default_prior() (model.py:54-153) with seed 3, rejecting period >= 225 min
+    and perigee < 120 km -- the same catalog bench.py's secondary.configs3_catalog screens."""
+    import bench
+    return bench.default_prior_catalog(int(n), seed=seed)
 
 
 def config3(n_total):
