@@ -817,3 +817,37 @@ def test_mc_pc_kernel_against_oracle_and_shard_invariance(eng):
     # all-pairs form (reference semantics) through the sharded helper
     pc, cnt = MC.all_pairs_probability(x_t[:3000, :3].T, x_c[:2000, :3].T, 70.0)
     assert cnt == C.pc_count(np.ascontiguousarray(x_t[:3000, :3].T), np.ascontiguousarray(x_c[:2000, :3].T), 70.0, 0) > 0
+
+
+def test_empty_and_single_element_batches(eng):
+    """n = 0 and n = 1 through every batched entry point: no launch with an empty grid, no out-of-bounds mask / partial rows."""
+    gt, ept, gc, epc, s = common.golden_pair()
+    z7 = np.zeros((7, 0))
+    c0, e0 = eng.sgp4_init(z7)
+    assert c0.shape == (36, 0) and e0.numel() == 0
+    rv, _ = eng.sgp4_prop(c0, np.linspace(0.0, 10.0, 40))
+    assert rv.shape == (0, 40, 6)
+    times = K.time_grid(s["time0"], 7.0, 6e5)
+    tc = np.ascontiguousarray(times[::100])
+    r = eng.screen_elems(z7, np.zeros(0), z7, np.zeros(0), tc, len(times), 5e3)
+    assert r["i_min"].numel() == 0
+    h = eng.screen_host(z7, np.zeros(0), z7, np.zeros(0), tc, len(times), 5e3)
+    assert h["i_min"].shape == (0,)
+    mom, errc, _ = eng.tca_moments(z7, 100.0, np.zeros(6))
+    assert float(mom[0]) == 0.0 and int(errc[0]) == 0 and np.all(_np(mom) == 0.0)
+    assert int(eng.pc_count(np.zeros((3, 0)), np.zeros((3, 5)), 70.0)[0]) == 0
+    # one trace, one record, one epoch
+    one = eng.screen_elems(gt[:, None], [ept], gc[:, None], [epc], tc, len(times), 5e3)
+    assert int(one["i_min"][0]) == 305768 and int(one["i_conj"][0]) == s["i_conj"]
+    c1, _ = eng.sgp4_init(gt[:, None])
+    rv1, _ = eng.sgp4_prop(c1, [0.0])
+    ref, _ = C.tca_states(gt[:, None], 0.0)
+    assert np.abs(_np(rv1)[0, 0, :3] * 1e3 - ref[0, :3]).max() < 5e-5
+    mom1, _, st1 = eng.tca_moments(gt[:, None], 0.0, ref[0], want_states=True)
+    assert float(mom1[0]) == 1.0 and np.abs(_np(st1)[0, :3] - ref[0, :3]).max() < 5e-5
+    # 33 and 257 epochs per record: the tile kernel's ragged last half-tile
+    for m in (33, 257, 511):
+        ts = np.linspace(-300.0, 300.0, m)
+        got, _ = eng.sgp4_prop(c1, ts)
+        want, _ = C.sgp4_prop(_np(c1), ts)
+        assert np.abs(_np(got)[0, :, :3] - want[0, :, :3]).max() < 1e-8, m
