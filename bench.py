@@ -472,6 +472,8 @@ def run_ours(args):
 
     # ---- peaks ---------------------------------------------------------------------------------
     peak_tf = engine.fp64_peak_tflops() if rank == 0 else 0.0
+    # what a pure DFMA stream sustains at the screen kernel's own shape (16 warps per SM, two dependency chains per warp)
+    peak_shape = engine.fp64_peak_tflops(chains=2, warps_per_sm=16, reps=3) if rank == 0 else 0.0
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -506,8 +508,10 @@ def run_ours(args):
                 "traffic": (prof["dram_bytes_per_trace"] * n) if prof and prof["dram_bytes_per_trace"] else None,
                 "traffic_algorithmic": n * BYTES_PER_TRACE,
                 "profile_files": prof["files"] if prof else None, "profile_matches_source": prof["matches_source"] if prof else None,
-                "peak_source": "measured in this run: dependent-free DFMA probe (ksl_fp64_peak_kernel; ncu of the probe in "
-                               "profiles/: pipe 99 %); MEASURED_PEAKS.json has no FP64 entry",
+                "peak_source": "measured in this run: DFMA probe, 8 independent chains per thread at 64 warps per SM "
+                               "(ksl_fp64_chain_kernel; profiles/r02_fp64_ilp.json has the chains x warps table); "
+                               "MEASURED_PEAKS.json has no FP64 entry",
+                "peak_at_kernel_shape": peak_shape,
                 "hbm": {"achieved_gbs": n * BYTES_PER_TRACE / scr_s / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)",
                         "note": "algorithmic 144 B/trace; the path is FP64-bound, not HBM-bound"}}

@@ -291,6 +291,10 @@ int ksl_host_cache_free(void);
  * dependent-free DFMA loop: blocks x threads x iters x 2*unroll flops; used by
  * bench.py to MEASURE the FP64 peak (MEASURED_PEAKS.json has no FP64 entry). */
 int ksl_fp64_peak_kernel(int blocks, int threads, int64_t iters, double *sink, void *stream);
+/* the same with `chains` (1, 2, 4, 8) independent DFMA chains per thread: blocks x threads x iters x 2*chains flops.
+ * benchmarks/fp64_ilp.py sweeps it over resident warps per SM -- what the pipe sustains at the screen kernel's
+ * 16 warps x 2 chains is the practical ceiling of that kernel's shape. */
+int ksl_fp64_chain_kernel(int blocks, int threads, int64_t iters, int chains, double *sink, void *stream);
 /* number of kernel launches issued by this library since load (all threads) */
 int64_t ksl_launch_count(void);
 

@@ -99,6 +99,7 @@ _SIGNATURES = {
                         _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ksl_host_cache_free": [],
     "ksl_fp64_peak_kernel": [_int, _int, _i64, _vp, _vp],
+    "ksl_fp64_chain_kernel": [_int, _int, _i64, _int, _vp, _vp],
 }
 _RESTYPES = {"ksl_last_error": ctypes.c_char_p, "ksl_launch_count": _i64, "ksl_find_conjunction_ws": _i64,
              "ksl_screen_ws": _i64, "ksl_screen_elems_ws": _i64, "ksl_screen_summary_ws": _i64, "ksl_tca_moments_ws": _i64, "ksl_mc_pc_ws": _i64,

@@ -1170,6 +1170,24 @@ __global__ void k_fp64_peak(long long iters, double *__restrict__ sink) {
     if (r == 123456.789) sink[0] = r;  // never true; keeps the chains alive
 }
 
+// the same with a selectable number of independent chains per thread: how much instruction-level parallelism the FP64
+// pipe needs at a given number of resident warps (the screen kernel runs 16 warps per SM with two chains per warp)
+template <int kChains>
+__global__ void k_fp64_chains(long long iters, double *__restrict__ sink) {
+    double a[kChains];
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) a[c] = 1.0 + threadIdx.x * 1e-9 + c * 1e-9;
+    const double m = 0.999999999, b = 1e-12;
+    for (long long i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int c = 0; c < kChains; ++c) a[c] = fma(a[c], m, b);
+    }
+    double r = 0.0;
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) r += a[c];
+    if (r == 123456.789) sink[0] = r;
+}
+
 }  // namespace
 
 // ======================================================================================
@@ -1675,6 +1693,19 @@ int ksl_sample_prior(const void *params, uint64_t seed, int64_t sample_offset, i
     if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
     k_sample_prior<<<(unsigned)blocks, 256, 0, S(stream)>>>(reinterpret_cast<const PriorField *>(params), (unsigned long long)seed,
                                                             sample_offset, n, raw, elems, flag);
+    KSL_LAUNCH_CHECK();
+    return KSL_OK;
+}
+
+int ksl_fp64_chain_kernel(int blocks, int threads, int64_t iters, int chains, double *sink, void *stream) {
+    if (blocks <= 0 || threads <= 0 || threads > 1024 || iters < 0 || !sink) return fail(KSL_E_ARG, "ksl_fp64_chain_kernel: bad argument");
+    switch (chains) {
+        case 1: k_fp64_chains<1><<<blocks, threads, 0, S(stream)>>>(iters, sink); break;
+        case 2: k_fp64_chains<2><<<blocks, threads, 0, S(stream)>>>(iters, sink); break;
+        case 4: k_fp64_chains<4><<<blocks, threads, 0, S(stream)>>>(iters, sink); break;
+        case 8: k_fp64_chains<8><<<blocks, threads, 0, S(stream)>>>(iters, sink); break;
+        default: return fail(KSL_E_ARG, "ksl_fp64_chain_kernel: chains must be 1, 2, 4 or 8");
+    }
     KSL_LAUNCH_CHECK();
     return KSL_OK;
 }

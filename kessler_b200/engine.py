@@ -385,13 +385,16 @@ def screen_host(elems_t, epoch_t, elems_c, epoch_c, times_coarse, n_fine, thr_m,
 
 
 # --- measurement ---------------------------------------------------------------------------
-def fp64_peak_tflops(iters=20000, reps=5):
-    """Measured DFMA throughput of the current device (dependent-free chains), TFLOP/s."""
+def fp64_peak_tflops(iters=20000, reps=5, chains=8, warps_per_sm=64):
+    """Measured DFMA throughput of the current device, TFLOP/s: `chains` independent chains per thread at `warps_per_sm`
+    resident warps (defaults: the shape that saturates the pipe, 36.8 of the 37.2 TFLOP/s a B200 can issue at 1965 MHz --
+    benchmarks/fp64_ilp.py has the whole table).  Best of `reps`."""
     dev = _dev()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    blocks, threads = sms * 8, 256
+    threads = min(1024, 32 * int(warps_per_sm))
+    blocks = sms * max(1, (32 * int(warps_per_sm)) // threads)
     sink = torch.zeros(1, dtype=F64, device=dev)
-    run = lambda it: N.check(N.lib().ksl_fp64_peak_kernel(blocks, threads, it, ptr(sink), stream_ptr()), "fp64_peak")
+    run = lambda it: N.check(N.lib().ksl_fp64_chain_kernel(blocks, threads, it, int(chains), ptr(sink), stream_ptr()), "fp64_peak")
     run(1000)
     torch.cuda.synchronize()
     best = 0.0
@@ -402,7 +405,7 @@ def fp64_peak_tflops(iters=20000, reps=5):
         e1.record()
         e1.synchronize()
         ms = e0.elapsed_time(e1)
-        flops = 2.0 * 8 * iters * blocks * threads
+        flops = 2.0 * int(chains) * iters * blocks * threads
         best = max(best, flops / (ms * 1e-3) / 1e12)
     return best
 
