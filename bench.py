@@ -225,9 +225,12 @@ def default_prior_catalog(n, seed=3):
     import torch
     from kessler_b200.model import Conjunction
     from kessler_b200.tle import MU_EARTH, R_EARTH
+    import contextlib
+    import io
     torch.manual_seed(seed)
-    m = Conjunction()
-    out, raws = np.zeros((7, 0)), []
+    with contextlib.redirect_stdout(io.StringIO()):      # (the constructor announces its default instruments on stdout)
+        m = Conjunction()
+    out = np.zeros((7, 0))
     while out.shape[1] < n:
         raw, el, _ = m.sample_elements('c', 2 * n)
         a = (MU_EARTH / np.maximum(raw['mean_motion'], 1e-12) ** 2) ** (1.0 / 3.0)
