@@ -196,6 +196,8 @@ def load_profile(kernel="k_screen_warp"):
                 "instr_per_unit": sum(per.values()),
                 "pipe_active_pct": met.get("sm__pipe_fp64_cycles_active_pct"), "issue_active_pct": met.get("smsp__issue_active_pct"),
                 "dram_bytes_per_trace": met.get("bytes_per_trace"), "traces_per_launch": met.get("traces_per_launch"),
+                "operand_limited_cycles_per_warp_eval": met.get("operand_limited_cycles_per_warp_eval"),
+                "dfma_three_register_operands_per_eval": met.get("dfma_three_register_operands_per_eval"),
                 "files": [man["opcode_mix"], man["metrics"]],
                 "matches_source": man.get("kernel_sources_sha16") == kernel_sources_sha()}
     except Exception:
@@ -515,6 +517,16 @@ def run_ours(args):
                                "(ksl_fp64_chain_kernel; profiles/r02_fp64_ilp.json has the chains x warps table); "
                                "MEASURED_PEAKS.json has no FP64 entry",
                 "peak_at_kernel_shape": peak_shape,
+                # The ceiling that matters for THIS instruction stream: a DFMA with three register operands issues every third
+                # cycle on B200, everything else on the FP64 pipe every second (benchmarks/fp64_ilp.py; 24.6 instead of 36.8
+                # TFLOP/s for a pure stream of them).  bound = (3 n3 + 2 n_other) pipe cycles per warp-evaluation from the ncu
+                # capture; measured = launch time x SM clock x schedulers / warp-evaluations of the launch.
+                "operand_limited": (lambda bound, meas: {"pipe_cycles_per_warp_eval_bound": bound, "pipe_cycles_per_warp_eval_measured": meas,
+                                                         "frac": bound / meas,
+                                                         "dfma_three_register_operands_per_eval": prof["dfma_three_register_operands_per_eval"]})(
+                    prof["operand_limited_cycles_per_warp_eval"],
+                    scr_s * (clocks["sm_mhz"] or 1965.0) * 1e6 * torch.cuda.get_device_properties(dev).multi_processor_count * 4 / (evals / 32.0))
+                if prof and prof.get("operand_limited_cycles_per_warp_eval") and clocks else None,
                 "hbm": {"achieved_gbs": n * BYTES_PER_TRACE / scr_s / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)",
                         "note": "algorithmic 144 B/trace; the path is FP64-bound, not HBM-bound"}}

@@ -291,9 +291,11 @@ int ksl_host_cache_free(void);
  * dependent-free DFMA loop: blocks x threads x iters x 2*unroll flops; used by
  * bench.py to MEASURE the FP64 peak (MEASURED_PEAKS.json has no FP64 entry). */
 int ksl_fp64_peak_kernel(int blocks, int threads, int64_t iters, double *sink, void *stream);
-/* the same with `chains` (1, 2, 4, 8) independent DFMA chains per thread: blocks x threads x iters x 2*chains flops.
- * benchmarks/fp64_ilp.py sweeps it over resident warps per SM -- what the pipe sustains at the screen kernel's
- * 16 warps x 2 chains is the practical ceiling of that kernel's shape. */
+/* the same with a selectable shape: chains = n + 16 * mode, n in {1, 2, 4, 8} independent chains per thread, mode =
+ * 0: a = fma(a, M, B) with compile-time constants (one register operand; the pipe's issue peak), 1: a = fma(a, m, b) with
+ * per-thread registers (THREE 64-bit register operands -- what real code looks like), 2: fma with two register operands,
+ * 3: DMUL, 4: DADD (n in {2, 8} for modes 2-4).  blocks x threads x iters x n instructions.  benchmarks/fp64_ilp.py sweeps
+ * it: on B200 a DFMA with three register operands issues every third cycle, not every second (operand bandwidth). */
 int ksl_fp64_chain_kernel(int blocks, int threads, int64_t iters, int chains, double *sink, void *stream);
 /* number of kernel launches issued by this library since load (all threads) */
 int64_t ksl_launch_count(void);

@@ -1172,15 +1172,30 @@ __global__ void k_fp64_peak(long long iters, double *__restrict__ sink) {
 
 // the same with a selectable number of independent chains per thread: how much instruction-level parallelism the FP64
 // pipe needs at a given number of resident warps (the screen kernel runs 16 warps per SM with two chains per warp)
-template <int kChains>
+// kMode -- where the operands of the chain's instruction come from:
+//   0  a = fma(a, M, B)   M, B compile-time constants (constant-bank operands): one 64-bit REGISTER operand per DFMA
+//   1  a = fma(a, m, b)   m, b per-thread registers that differ from chain to chain: THREE register operands (real code)
+//   2  a = fma(a, m, B)   two register operands
+//   3  a = a * m          DMUL, two register operands
+//   4  a = a + b          DADD, two register operands
+template <int kChains, int kMode>
 __global__ void k_fp64_chains(long long iters, double *__restrict__ sink) {
-    double a[kChains];
+    double a[kChains], m[kChains], b[kChains];
 #pragma unroll
-    for (int c = 0; c < kChains; ++c) a[c] = 1.0 + threadIdx.x * 1e-9 + c * 1e-9;
-    const double m = 0.999999999, b = 1e-12;
+    for (int c = 0; c < kChains; ++c) {
+        a[c] = 1.0 + threadIdx.x * 1e-9 + c * 1e-9;
+        m[c] = 0.999999999 - (threadIdx.x + 7 * c) * 1e-13;
+        b[c] = 1e-12 + (threadIdx.x + 3 * c) * 1e-21;
+    }
     for (long long i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int c = 0; c < kChains; ++c) a[c] = fma(a[c], m, b);
+        for (int c = 0; c < kChains; ++c) {
+            if (kMode == 0) a[c] = fma(a[c], 0.999999999, 1e-12);
+            else if (kMode == 1) a[c] = fma(a[c], m[c], b[c]);
+            else if (kMode == 2) a[c] = fma(a[c], m[c], 1e-12);
+            else if (kMode == 3) a[c] = __dmul_rn(a[c], m[c]);
+            else a[c] = __dadd_rn(a[c], b[c]);
+        }
     }
     double r = 0.0;
 #pragma unroll
@@ -1699,13 +1714,15 @@ int ksl_sample_prior(const void *params, uint64_t seed, int64_t sample_offset, i
 
 int ksl_fp64_chain_kernel(int blocks, int threads, int64_t iters, int chains, double *sink, void *stream) {
     if (blocks <= 0 || threads <= 0 || threads > 1024 || iters < 0 || !sink) return fail(KSL_E_ARG, "ksl_fp64_chain_kernel: bad argument");
-    switch (chains) {
-        case 1: k_fp64_chains<1><<<blocks, threads, 0, S(stream)>>>(iters, sink); break;
-        case 2: k_fp64_chains<2><<<blocks, threads, 0, S(stream)>>>(iters, sink); break;
-        case 4: k_fp64_chains<4><<<blocks, threads, 0, S(stream)>>>(iters, sink); break;
-        case 8: k_fp64_chains<8><<<blocks, threads, 0, S(stream)>>>(iters, sink); break;
-        default: return fail(KSL_E_ARG, "ksl_fp64_chain_kernel: chains must be 1, 2, 4 or 8");
-    }
+    const int mode = chains / 16, nch = chains % 16;
+#define KSL_CHAIN_CASE(C, M) \
+    if (nch == C && mode == M) { k_fp64_chains<C, M><<<blocks, threads, 0, S(stream)>>>(iters, sink); launched = true; }
+    bool launched = false;
+    KSL_CHAIN_CASE(1, 0) KSL_CHAIN_CASE(2, 0) KSL_CHAIN_CASE(4, 0) KSL_CHAIN_CASE(8, 0)
+    KSL_CHAIN_CASE(1, 1) KSL_CHAIN_CASE(2, 1) KSL_CHAIN_CASE(4, 1) KSL_CHAIN_CASE(8, 1)
+    KSL_CHAIN_CASE(2, 2) KSL_CHAIN_CASE(8, 2) KSL_CHAIN_CASE(2, 3) KSL_CHAIN_CASE(8, 3) KSL_CHAIN_CASE(2, 4) KSL_CHAIN_CASE(8, 4)
+#undef KSL_CHAIN_CASE
+    if (!launched) return fail(KSL_E_ARG, "ksl_fp64_chain_kernel: unsupported chains / mode combination %d", chains);
     KSL_LAUNCH_CHECK();
     return KSL_OK;
 }

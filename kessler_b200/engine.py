@@ -385,16 +385,17 @@ def screen_host(elems_t, epoch_t, elems_c, epoch_c, times_coarse, n_fine, thr_m,
 
 
 # --- measurement ---------------------------------------------------------------------------
-def fp64_peak_tflops(iters=20000, reps=5, chains=8, warps_per_sm=64):
+def fp64_peak_tflops(iters=20000, reps=5, chains=8, warps_per_sm=64, mode=0):
     """Measured DFMA throughput of the current device, TFLOP/s: `chains` independent chains per thread at `warps_per_sm`
     resident warps (defaults: the shape that saturates the pipe, 36.8 of the 37.2 TFLOP/s a B200 can issue at 1965 MHz --
-    benchmarks/fp64_ilp.py has the whole table).  Best of `reps`."""
+    benchmarks/fp64_ilp.py has the whole table).  mode: operand shape of the chain (0 constants, 1 three register operands, see
+    include/kessler_b200.h).  Best of `reps`."""
     dev = _dev()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     threads = min(1024, 32 * int(warps_per_sm))
     blocks = sms * max(1, (32 * int(warps_per_sm)) // threads)
     sink = torch.zeros(1, dtype=F64, device=dev)
-    run = lambda it: N.check(N.lib().ksl_fp64_chain_kernel(blocks, threads, it, int(chains), ptr(sink), stream_ptr()), "fp64_peak")
+    run = lambda it: N.check(N.lib().ksl_fp64_chain_kernel(blocks, threads, it, int(chains) + 16 * int(mode), ptr(sink), stream_ptr()), "fp64_peak")
     run(1000)
     torch.cuda.synchronize()
     best = 0.0

@@ -56,6 +56,13 @@ def main():
            "executed_flop_per_eval": (2 * counts.get("DFMA", 0) + counts.get("DMUL", 0) + counts.get("DADD", 0)) * 32 / units,
            "fp64_instr_per_eval": sum(counts.get(k, 0) for k in ("DFMA", "DMUL", "DADD", "DSETP")) * 32 / units,
            "instr_per_eval": sum(counts.values()) * 32 / units}
+    shapes = ncu_opcode_mix.fp64_operand_shapes(a.rep)
+    n3 = shapes.get(("DFMA", 3), 0) * 32 / units
+    n_other = (sum(shapes.values()) - shapes.get(("DFMA", 3), 0)) * 32 / units
+    met["dfma_three_register_operands_per_eval"] = n3
+    met["fp64_other_per_eval"] = n_other
+    # cycles of the FP64 pipe one warp-evaluation needs at best: 3 per three-register DFMA, 2 per anything else
+    met["operand_limited_cycles_per_warp_eval"] = 3 * n3 + 2 * n_other
     metrics = f"{a.tag}_{a.kernel}_metrics.json"
     json.dump(met, open(os.path.join(ROOT, "profiles", metrics), "w"), indent=1)
     man_path = os.path.join(ROOT, "profiles", "current.json")

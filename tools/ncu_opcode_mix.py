@@ -33,6 +33,35 @@ def opcode_counts(rep):
     return counts
 
 
+def fp64_operand_shapes(rep):
+    """Executed FP64-pipe instructions split by how many REGISTER source operands they read: {(opcode, n_reg): warp instructions}.
+    On B200 a DFMA with three register operands issues every third cycle, everything else on the pipe every second
+    (benchmarks/fp64_ilp.py), so the split decides what the pipe can deliver for a given instruction stream."""
+    import re
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr_i = next(i for i, r in enumerate(rows) if "Source" in r and "Instructions Executed" in r)
+    hdr = rows[hdr_i]
+    si, ci = hdr.index("Source"), hdr.index("Instructions Executed")
+    out = collections.Counter()
+    for r in rows[hdr_i + 1:]:
+        if len(r) <= max(si, ci):
+            continue
+        text = re.sub(r"^@!?U?P\d+\s+", "", r[si].strip())
+        if not text:
+            continue
+        op = text.split()[0].split(".")[0]
+        if op not in ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX"):
+            continue
+        operands = [o.strip() for o in text[len(text.split()[0]):].split(",")][1:]
+        n_reg = sum(1 for o in operands if re.match(r"^[-|~]*R\d+", o))
+        try:
+            out[(op, n_reg)] += int(float(r[ci]))
+        except ValueError:
+            continue
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("rep")
