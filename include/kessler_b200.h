@@ -207,7 +207,9 @@ int ksl_pc_count(const double *t_xyz, int64_t nt, const double *c_xyz, int64_t n
  * model.py:432-437 in its elementwise form, with the draws generated on the device:
  * for global sample g = sample_offset + i, i < n:
  *   (a,e,i,raan,argp,M) = mean + L z,  z = 6 standard normals from Philox4x32-10 keyed by
- *   (seed, g, object) -- independent of how [0, N) is split over GPUs;
+ *   (seed, g, object) -- independent of how [0, N) is split over GPUs; the deviates are
+ *   single-precision Box-Muller values (24 significant bits, tails to 6.8 sigma) widened to
+ *   FP64, everything from the element vector on is FP64;
  *   a -> mean motion, e < 0 -> 0 (model.py:500,525-533); sgp4init + sgp4 at tsince; metres.
  * mean_*, ref_* [6] and chol_* [21] (row-major lower triangle of the Cholesky factor of the
  * element covariance, model.py:461-478) are HOST pointers (they travel as kernel arguments);
@@ -215,7 +217,10 @@ int ksl_pc_count(const double *t_xyz, int64_t nt, const double *c_xyz, int64_t n
  * moments_t, moments_c [KSL_NMOMENT]: shifted moments of the two states about ref_*; moments_t
  * must have room for 2*KSL_NMOMENT doubles (moments_c may alias moments_t + KSL_NMOMENT).
  * dump (optional, [n_dump][26]): per sample the 7+7 SGP4 inputs and the 6+6 state components,
- * for parity checks against the oracle on IDENTICAL samples.  workspace: ksl_mc_pc_ws(n) bytes. */
+ * for parity checks against the oracle on IDENTICAL samples.  workspace: ksl_mc_pc_ws(n) bytes
+ * (rows of partial moments + one mask word per 16 samples: a sample whose in-register fast path --
+ * sgp4init in its fast form + the fast SGP4 state -- declines is marked there and redone on the
+ * exact route by a second kernel of the same call; ksl_tca_moments works the same way). */
 int64_t ksl_mc_pc_ws(int64_t n);
 int ksl_mc_pc(const double *mean_t, const double *chol_t, double bstar_t, double tsince_t, const double *ref_t,
               const double *mean_c, const double *chol_c, double bstar_c, double tsince_c, const double *ref_c,
