@@ -17,10 +17,10 @@ dev = torch.device("cuda", 0)
 sms = torch.cuda.get_device_properties(dev).multi_processor_count
 sink = torch.zeros(1, dtype=torch.float64, device=dev)
 out = {}
-MODES = {0: "fma_const", 1: "fma_3reg", 2: "fma_2reg", 3: "dmul", 4: "dadd"}
+MODES = {0: "fma_const", 1: "fma_3reg", 2: "fma_2reg", 3: "dmul", 4: "dadd", 5: "fma_R_UR_R", 6: "fma_R_R_UR"}
 for warps in (4, 8, 16, 32, 64):
     row = {}
-    for mode, chain_set in ((0, (1, 2, 4, 8)), (1, (1, 2, 4, 8)), (2, (2, 8)), (3, (2, 8)), (4, (2, 8))):
+    for mode, chain_set in ((0, (1, 2, 4, 8)), (1, (1, 2, 4, 8)), (2, (2, 8)), (3, (2, 8)), (4, (2, 8)), (5, (2, 8)), (6, (2, 8))):
         for chains in chain_set:
             threads = 32 * warps if warps <= 32 else 1024
             blocks = sms * (1 if warps <= 32 else warps // 32)

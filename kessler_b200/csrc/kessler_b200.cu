@@ -1178,20 +1178,29 @@ __global__ void k_fp64_peak(long long iters, double *__restrict__ sink) {
 //   2  a = fma(a, m, B)   two register operands
 //   3  a = a * m          DMUL, two register operands
 //   4  a = a + b          DADD, two register operands
+//   5  a = fma(a, u, b)   u warp-uniform (read from shared memory at a uniform address, so ptxas moves it to a UNIFORM
+//                         register: DFMA R, R, UR, R), b a per-thread register
+//   6  a = fma(a, m, u)   the uniform operand in the addend slot (DFMA R, R, R, UR)
 template <int kChains, int kMode>
 __global__ void k_fp64_chains(long long iters, double *__restrict__ sink) {
     double a[kChains], m[kChains], b[kChains];
+    __shared__ double uni[2 * kChains];
+    if (kMode >= 5) {
+        if (threadIdx.x < 2 * kChains)
+            uni[threadIdx.x] = sink[0] * 1e-300 + (threadIdx.x < kChains ? 0.999999999 - 7e-13 * threadIdx.x : 1e-12 + 3e-21 * threadIdx.x);
+        __syncthreads();
+    }
 #pragma unroll
     for (int c = 0; c < kChains; ++c) {
         a[c] = 1.0 + threadIdx.x * 1e-9 + c * 1e-9;
-        m[c] = 0.999999999 - (threadIdx.x + 7 * c) * 1e-13;
-        b[c] = 1e-12 + (threadIdx.x + 3 * c) * 1e-21;
+        m[c] = kMode == 5 ? uni[c] : 0.999999999 - (threadIdx.x + 7 * c) * 1e-13;
+        b[c] = kMode == 6 ? uni[kChains + c] : 1e-12 + (threadIdx.x + 3 * c) * 1e-21;
     }
     for (long long i = 0; i < iters; ++i) {
 #pragma unroll
         for (int c = 0; c < kChains; ++c) {
             if (kMode == 0) a[c] = fma(a[c], 0.999999999, 1e-12);
-            else if (kMode == 1) a[c] = fma(a[c], m[c], b[c]);
+            else if (kMode == 1 || kMode >= 5) a[c] = fma(a[c], m[c], b[c]);
             else if (kMode == 2) a[c] = fma(a[c], m[c], 1e-12);
             else if (kMode == 3) a[c] = __dmul_rn(a[c], m[c]);
             else a[c] = __dadd_rn(a[c], b[c]);
@@ -1721,6 +1730,7 @@ int ksl_fp64_chain_kernel(int blocks, int threads, int64_t iters, int chains, do
     KSL_CHAIN_CASE(1, 0) KSL_CHAIN_CASE(2, 0) KSL_CHAIN_CASE(4, 0) KSL_CHAIN_CASE(8, 0)
     KSL_CHAIN_CASE(1, 1) KSL_CHAIN_CASE(2, 1) KSL_CHAIN_CASE(4, 1) KSL_CHAIN_CASE(8, 1)
     KSL_CHAIN_CASE(2, 2) KSL_CHAIN_CASE(8, 2) KSL_CHAIN_CASE(2, 3) KSL_CHAIN_CASE(8, 3) KSL_CHAIN_CASE(2, 4) KSL_CHAIN_CASE(8, 4)
+    KSL_CHAIN_CASE(2, 5) KSL_CHAIN_CASE(8, 5) KSL_CHAIN_CASE(2, 6) KSL_CHAIN_CASE(8, 6)
 #undef KSL_CHAIN_CASE
     if (!launched) return fail(KSL_E_ARG, "ksl_fp64_chain_kernel: unsupported chains / mode combination %d", chains);
     KSL_LAUNCH_CHECK();
