@@ -699,8 +699,12 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
     // Drag / long-period block, executed unconditionally: for an `isimp` record (perigee < 220 km)
     // prepare_fast_record zeroes omgcof, xmcof and bstar*cc5, and sgp4init already left d2..d4,
     // t3cof..t5cof at 0, which turns every term below into an exact +0.
+    // (sin, cos)(xmdf) only feed the drag terms: sin the bstar*cc5 term of the eccentricity (< 1e-5: the short kernel's
+    // 7e-14 is 1e-18), cos the perigee / anomaly exchange delm, where the short kernel's 6e-11 is multiplied by
+    // 3 xmcof eta <~ |delm| -- below 2^-4 in the near-circular form (4e-12 rad), up to 1 in the general one (two terms)
     double sx, cx;
-    sincos_grid(xmdf, grid, sx, cx);
+    if (small_e) sincos_grid<1, 1>(xmdf, grid, sx, cx);
+    else sincos_grid<1, 2>(xmdf, grid, sx, cx);
     const double delmtemp = fma_rn(c(KSL_C_ETA), cx, 1.0);
     const double delm = c(KSL_C_XMCOF) * (delmtemp * delmtemp * delmtemp - c(KSL_C_DELMO));
     const double temp0 = fma_rn(c(KSL_C_OMGCOF), t, delm);
@@ -739,12 +743,13 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
     const double xlm = add_rn(add_rn(mm, argpm), nodem);
     // The reference wraps nodem, argpm, xlm and mm = xlm - argpm - nodem to [0, 2 pi) with exact remainders
     // and rebuilds u = (mm + argpm + nodem + long-period term) - nodem from them: modulo 2pi_d that is
-    // (nodem itself stays unwrapped: |nodem| < 64, where reducing by 2pi_d or by 2 pi differs by < 3e-15 rad)
+    // (nodem itself stays unwrapped: |nodem| < 64, where reducing by 2pi_d or by 2 pi differs by < 3e-15 rad).
+    // (Dropping the wrap and letting the Kepler solver's grid reduction do it would save four instructions and cost two
+    // roundings at the magnitude of xlm: the median distance to the oracle goes from 2e-12 km to 5e-10 km -- not taken.)
     const double lm = wrap_pm_pi(xlm) - nodem;
 
     double sarg, carg;
-    if (small_e) sincos_grid<1, 2>(argpm, grid, sarg, carg);    // enters multiplied by em < 0.01: 7e-14 there is 7e-16
-    else sincos_grid(argpm, grid, sarg, carg);
+    sincos_grid<1, 2>(argpm, grid, sarg, carg);    // enters multiplied by em < 0.12 (0.01 in the near-circular form): 7e-14 there is 8e-15 (7e-16)
     const double axnl = em * carg;
     double temp = rcp_1(am * fma_rn(-em, em, 1.0));            // * aycof / xlcof ~ 1e-3: 1e-12 is plenty
     const double aynl = fma_rn(em, sarg, temp * c(KSL_C_AYCOF));
@@ -770,12 +775,12 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
     if (small_e) {
         // |E - E0| <= el + pi / 512 < 0.0162: Halley leaves (el / 6) 0.0162^3 < 8e-9, the Newton step below -- reciprocal
         // refined cubically, (el |d|)^3 < 5e-12 -- leaves (el / 2) (8e-9)^2 + 8e-9 x 5e-12 < 1e-19.
-        // rotation by |d| < 0.0162 (typically 4e-3): sin through d^5 (d^7 / 7! < 6e-16, typically 3e-21), cos through d^6
-        // (d^8 / 8! < 2e-19)
+        // rotation by |d| < 0.0162 (typically 4e-3): sin through d^5 (d^7 / 7! < 6e-16, typically 3e-21), cos through d^4
+        // (d^6 / 6! < 2.5e-14, typically 6e-18: 2e-10 km at the very edge of the form)
         const double d2 = d * d;
         const double ps = fma_rn(d2, kTrigTab[1], kTrigTab[0]);
         const double sd = fma_rn(ps * d2, d, d);
-        const double cd = fma_rn(fma_rn(fma_rn(d2, kTrigTab[6], kTrigTab[5]), d2, kTrigTab[4]), d2, 1.0);
+        const double cd = fma_rn(fma_rn(d2, kTrigTab[5], kTrigTab[4]), d2, 1.0);
         const double s0 = se, c0 = ce;
         se = fma_rn(s0, cd, c0 * sd);
         ce = fma_rn(c0, cd, -(s0 * sd));
@@ -852,7 +857,7 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
         rotate_micro(dsu, sinsu, cossu);
     }
     double snod, cnod;
-    sincos_grid(nodem + dnode, grid, snod, cnod);   // xnode, as the reference forms it
+    sincos_grid(nodem + dnode, grid, snod, cnod);   // xnode, as the reference forms it (full kernels: r^5 / 120 here is 5e-10 km)
     double sini = c(KSL_C_SINIO), cosi = c(KSL_C_COSIO);
     if (small_e) {      // pl > 0.9999 am >= ~1: |dinc| <= 3/8 J2 / pl^2 < 4.1e-4, cos through d^2 leaves d^4 / 24 < 1.2e-15
         const double q2 = dinc * dinc;
@@ -878,12 +883,17 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
         const double er0 = fma_rn(-(am * r0), r0, 1.0);
         const double rsa = fma_rn(r0, fma_rn(0.375, er0, 0.5) * er0, r0);
         const double w = amorl * rsa;
-        double bf = fma_rn(el2, kSqrtTab[6], kSqrtTab[5]);   // sqrt(1 - el2) to 3e-17: the two terms betal leaves out
-        bf = fma_rn(bf, el2, kSqrtTab[4]);
-        bf = fma_rn(bf, el2, kSqrtTab[3]);
-        bf = fma_rn(bf, el2, kSqrtTab[2]);
-        bf = fma_rn(bf, el2, kSqrtTab[1]);
-        bf = fma_rn(bf, el2, kSqrtTab[0]);
+        // sqrt(1 - el2), relative: through x^5 it leaves 21/1024 x^6 < 2e-13 at el2 = 0.0144 (1e-9 m/s, 1e-21 at e = 0.01);
+        // the near-circular form stops at x^2 (x^3 / 16 < 7e-14)
+        double bf;
+        if (small_e) {
+            bf = fma_rn(el2, kSqrtTab[1], kSqrtTab[0]);
+        } else {
+            bf = fma_rn(el2, kSqrtTab[4], kSqrtTab[3]);
+            bf = fma_rn(bf, el2, kSqrtTab[2]);
+            bf = fma_rn(bf, el2, kSqrtTab[1]);
+            bf = fma_rn(bf, el2, kSqrtTab[0]);
+        }
         const double rvdotl = w * fma_rn(bf, el2, 1.0);
         const double k1 = (0.5 * kJ2) * ipl * (rsa * rsa * rsa);           // temp1 nm / xke
         const double mvt = fma_rn(-k1 * c(KSL_C_X1MTH2), sin2u, w * esine);
