@@ -749,7 +749,10 @@ KSL_HD bool sgp4_prop_fast_rv(Load &&c, double t, double r[3], double v[3], cons
     const double lm = wrap_pm_pi(xlm) - nodem;
 
     double sarg, carg;
-    sincos_grid<1, 2>(argpm, grid, sarg, carg);    // enters multiplied by em < 0.12 (0.01 in the near-circular form): 7e-14 there is 8e-15 (7e-16)
+    // (the short sine would do in the general form as well -- em < 0.12 leaves 8e-15 -- but the kernels built with it ran
+    // slower: K2 1.065 ms against 1.009 per 4.9e7 evaluations, instruction scheduling, measured twice)
+    if (small_e) sincos_grid<1, 2>(argpm, grid, sarg, carg);    // enters multiplied by em < 0.01: 7e-14 there is 7e-16
+    else sincos_grid(argpm, grid, sarg, carg);
     const double axnl = em * carg;
     double temp = rcp_1(am * fma_rn(-em, em, 1.0));            // * aycof / xlcof ~ 1e-3: 1e-12 is plenty
     const double aynl = fma_rn(em, sarg, temp * c(KSL_C_AYCOF));
