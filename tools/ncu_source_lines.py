@@ -16,7 +16,7 @@ def source_lines(rep):
     rows = list(csv.reader(io.StringIO(raw)))
     out, fname, hdr = [], None, None
     for r in rows:
-        if len(r) == 2 and r[0] == "File Name":
+        if len(r) == 2 and r[0] in ("File Name", "File Path"):
             fname = r[1]
             continue
         if r and r[0] == "Line No":
