@@ -1021,12 +1021,14 @@ KSL_HD int sgp4_init_state(const double el[7], double t, double r[3], double v[3
 
 // sgp4init (fast form) + full state, everything in registers and nothing out of line: `ok` false = the sample needs the
 // exact route (sgp4_init + sgp4_prop), nothing usable was written.  *err: sgp4init's flag (deep space).
+// small_e: evaluate through the near-circular form (the caller's guess for the whole launch; a sample outside it is declined)
+template <bool small_e = false>
 KSL_HD bool sgp4_init_state_fast(const double el[7], double t, double r[3], double v[3], const double *grid, int *err) {
     double c[KSL_NCONST];
     *err = sgp4_init_fast(el, [&](int k, double val) { c[k] = val; }, grid);
     auto ld = [&](int k) { return c[k]; };
     const FastView<decltype(ld)> view{ld, c[KSL_C_ISIMP] != 0.0};
-    return sgp4_prop_fast_rv<true>(view, t, r, v, grid);
+    return sgp4_prop_fast_rv<true, small_e>(view, t, r, v, grid);
 }
 
 // position at t through the fast path, falling back to the exact path when needed (c: masked record).  The exact path

@@ -727,6 +727,25 @@ def test_mc_kernels_exact_route_for_declined_samples(eng):
                   count=a["count"], err_count=a["err_count"])
     assert int(b["count"][0]) == want
     assert np.array_equal(a["dump"].cpu().numpy(), d[:999]) and np.array_equal(b["dump"].cpu().numpy(), d[999:999 + 64])
+    # K6 picks the near-circular form of the fast path when both clouds fit it (decided per launch from the mean elements and
+    # the spread of e).  Three clouds: well inside it; around e = 1.5e-4 +- 1e-4, where the samples drawn below zero are clamped
+    # to e = 0, declined by that form (em < 1e-6) and redone on the exact route; and just outside it (general form).
+    for e_mean, e_sig in ((4.0e-3, 2.0e-4), (1.5e-4, 1.0e-4), (8.5e-3, 2.0e-4)):
+        mean[0], mean[1] = 6.9e6, e_mean
+        L[1, 1] = e_sig
+        r = eng.mc_pc(mean, L, t_tle._bstar, ts, ref, mean, L * 1.5, t_tle._bstar, ts, ref, 13, 0, 20000, 3000.0, n_dump=20000)
+        d = r["dump"].cpu().numpy()
+        el_t, el_c, x_t, x_c = d[:, :7].T.copy(), d[:, 7:14].T.copy(), d[:, 14:20], d[:, 20:26]
+        if e_mean < 1e-3:
+            assert 0.02 < (el_t[1] == 0.0).mean() < 0.2
+        ref_t, et = C.tca_states(el_t, ts)
+        ref_c, ec = C.tca_states(el_c, ts)
+        assert np.abs(x_t[:, :3] - ref_t[:, :3]).max() < 1e-3 and np.abs(x_c[:, :3] - ref_c[:, :3]).max() < 1e-3, e_mean
+        assert np.median(np.abs(x_t[:, :3] - ref_t[:, :3])) < 1e-6
+        assert np.abs(x_t[:, 3:] - ref_t[:, 3:]).max() < 1e-6 and np.abs(x_c[:, 3:] - ref_c[:, 3:]).max() < 1e-6
+        assert int(r["count"][0]) == C.pc_count(np.ascontiguousarray(x_t[:, :3].T), np.ascontiguousarray(x_c[:, :3].T), 3000.0, 1)
+        assert int(r["err_count"][0]) == int(((et | ec) != 0).sum())
+        assert r["moments_t"].cpu().numpy()[0] == 20000
 
 
 def test_pc_count_bit_exact(eng):
