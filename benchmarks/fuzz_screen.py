@@ -1,0 +1,143 @@
+#!/usr/bin/env python
+"""Differential fuzz of the fused trace kernels on one GPU: random grids, thresholds, batch shapes and orbit families, each
+case run through the closed-form search of the warp kernel (both entry points: resident records and fused sgp4init),
+the full enumeration of the same kernel (`brute`, itself pinned on the C oracle by tests/test_gpu_parity.py) and the
+CTA-per-trace kernel; every fine-grid index and distance must agree bit for bit.  A random subset of each case goes through
+the C oracle as well.  Not part of the test suite (minutes of GPU time); run it after touching the search logic:
+
+    python benchmarks/fuzz_screen.py --seconds 240 [--seed0 0]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import common  # noqa: E402
+from kessler_b200 import _native as NV, engine  # noqa: E402
+from oracle import c_oracle as C  # noqa: E402
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def related_pairs(n, rng):
+    """Clouds around the golden pair: mean anomalies either random or within 1e-4 rad of the conjunction geometry,
+    small spreads in the other elements -- several close approaches per week, slow and fast relative motion."""
+    et, ept, ec, epc, _ = common.golden_pair()
+    elt, elc = np.repeat(et[:, None], n, 1), np.repeat(ec[:, None], n, 1)
+    near = rng.random(n) < 0.5
+    for arr, base in ((elt, et), (elc, ec)):
+        arr[5] = np.where(near, base[5] + rng.normal(size=n) * 10.0 ** rng.uniform(-6, -3), rng.uniform(0, 2 * np.pi, n))
+        arr[0] *= 1.0 + rng.normal(size=n) * 10.0 ** rng.uniform(-8, -4)
+        arr[2] += rng.normal(size=n) * 10.0 ** rng.uniform(-7, -3)
+        arr[3] += rng.normal(size=n) * 10.0 ** rng.uniform(-7, -3)
+    co = rng.random(n) < 0.15                       # co-orbital: the chaser is the target a little ahead
+    elc[:, co] = elt[:, co]
+    elc[5, co] += rng.normal(size=int(co.sum())) * 1e-4
+    return elt, np.full(n, ept), elc, np.full(n, epc), ept
+
+
+def case(eng, seed, stats):
+    rng = np.random.default_rng(seed)
+    n = int(rng.choice([1, 7, 33, 257, 1500, 4000, 70000], p=[0.1, 0.15, 0.15, 0.2, 0.2, 0.12, 0.08]))   # >= 65536: sgp4init fused
+    family = rng.choice(["related", "catalog", "shared"])
+    if family == "related":
+        elt, ept, elc, epc, ep0 = related_pairs(n, rng)
+    else:
+        _, ep0, _, _, _ = common.golden_pair()
+        elt = common.synthetic_catalog(n, seed=seed + 1)
+        elc = common.synthetic_catalog(n, seed=seed + 2, include_edge=bool(rng.random() < 0.3))
+        ept, epc = ep0 + rng.uniform(-3, 3, n), ep0 + rng.uniform(-3, 3, n)
+        if family == "shared":
+            gt, _, _, _, _ = common.golden_pair()
+            elt, ept = gt[:, None].copy(), np.array([ep0])
+    n_coarse = int(rng.choice([2, 3, 31, 32, 33, 64, 65, 255, 513, 1000] + ([] if n > 4000 else [2049, 6000, 6144, 6145, 7001])))
+    if rng.random() < 0.5:
+        n_fine = (n_coarse - 1) * int(rng.integers(1, 120)) + 1
+    else:
+        n_fine = int(rng.integers(1, 120 * n_coarse))
+    days = float(rng.choice([0.05, 1.0, 7.0]))
+    tc = (ep0 - days / 2) + np.arange(n_coarse) * (days / max(n_coarse - 1, 1))
+    thr = float(rng.choice([70.0, 1e3, 5e3, 5e4, 1e6, 2e7]))
+    elt, elc = np.ascontiguousarray(elt), np.ascontiguousarray(elc)
+    ct, it = eng.sgp4_init(elt)
+    cc, ic = eng.sgp4_init(elc)
+
+    def run(flags):
+        r = eng.screen(ct, ept, cc, epc, tc, n_fine, thr, flags, init_err_t=it, init_err_c=ic)
+        return {k: _np(v) for k, v in r.items()}
+
+    brute = run(NV.SCREEN_FORCE_WARP | 1)
+    warp = run(NV.SCREEN_FORCE_WARP)
+    fused = {k: _np(v) for k, v in eng.screen_elems(torch.from_numpy(elt).cuda(), torch.from_numpy(np.asarray(ept, dtype=np.float64)).cuda(),
+                                                     torch.from_numpy(elc).cuda(), torch.from_numpy(np.asarray(epc, dtype=np.float64)).cuda(),
+                                                     torch.from_numpy(tc).cuda(), n_fine, thr).items()}
+    cta = run(NV.SCREEN_FORCE_CTA) if n <= 1500 else None
+    tag = dict(seed=seed, n=n, family=str(family), n_coarse=n_coarse, n_fine=n_fine, days=days, thr=thr)
+    for name, r in (("warp", warp), ("fused", fused), ("cta", cta)):
+        if r is None:
+            continue
+        for k in ("i_min", "i_conj", "err"):
+            if not np.array_equal(r[k], brute[k]):
+                bad = np.flatnonzero(r[k] != brute[k])
+                raise SystemExit(f"MISMATCH {name}.{k} {tag} at {bad[:8]}: {r[k][bad[:8]]} vs {brute[k][bad[:8]]}")
+        for k in ("d_min", "d_conj"):
+            if not np.array_equal(r[k], brute[k], equal_nan=True):
+                bad = np.flatnonzero(~((r[k] == brute[k]) | (np.isnan(r[k]) & np.isnan(brute[k]))))
+                raise SystemExit(f"MISMATCH {name}.{k} {tag} at {bad[:8]}: {r[k][bad[:8]]} vs {brute[k][bad[:8]]}")
+    # a few traces against the C oracle (full enumeration on the CPU)
+    budget = max(1, int(2.0e7 // max(n_fine, 1)))
+    sub = rng.choice(n, size=min(n, budget, 16), replace=False)
+    ref = C.screen(elt if elt.shape[1] == 1 else np.ascontiguousarray(elt[:, sub]), ept if elt.shape[1] == 1 else np.asarray(ept)[sub],
+                   np.ascontiguousarray(elc[:, sub]), np.asarray(epc)[sub], tc, n_fine, thr)
+    # (a trace with a Vallado error bit still carries numbers -- 1e29 m for an eccentricity beyond 1 -- whose arg-min is as
+    # ill-conditioned as they are: the flag must agree, the indices are compared on clean traces)
+    if not np.array_equal(ref["err"], warp["err"][sub]):
+        raise SystemExit(f"MISMATCH oracle.err {tag}: {ref['err']} vs {warp['err'][sub]}")
+    clean = ref["err"] == 0
+    for k in ("i_min", "i_conj"):
+        if not np.array_equal(ref[k][clean], warp[k][sub][clean]):
+            raise SystemExit(f"MISMATCH oracle.{k} {tag}: {ref[k]} vs {warp[k][sub]} err {ref['err']}")
+    stats["oracle_flagged"] = stats.get("oracle_flagged", 0) + int((~clean).sum())
+    fin = np.isfinite(ref["d_min"]) & clean
+    # 1e-3 m = the tolerance of record, at orbital scale (to 1e8 m); an unflagged object with an absurd negative drag term
+    # can sit 5e9 m away a day from its epoch, where all that is left is a relative statement
+    dd = np.abs(ref["d_min"][fin] - warp["d_min"][sub][fin])
+    tol = np.where(ref["d_min"][fin] <= 1e8, 1e-3, 1e-9 * np.abs(ref["d_min"][fin]))
+    if (dd > tol).any():
+        w = int(np.argmax(dd / tol))
+        raise SystemExit(f"MISMATCH oracle.d_min {tag}: {ref['d_min'][fin][w]!r} vs {warp['d_min'][sub][fin][w]!r}")
+    stats["max_dmin_diff_m"] = max(stats.get("max_dmin_diff_m", 0.0), float(dd[ref["d_min"][fin] <= 1e8].max(initial=0.0)))
+    stats["cases"] += 1
+    stats["traces"] += n
+    stats["conj"] += int((brute["i_conj"] >= 0).sum())
+    stats["flagged"] += int((brute["err"] != 0).sum())
+    stats["oracle_traces"] += len(sub)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=240.0)
+    ap.add_argument("--seed0", type=int, default=0)
+    a = ap.parse_args()
+    torch.cuda.set_device(0)
+    eng = engine
+    stats = dict(cases=0, traces=0, conj=0, flagged=0, oracle_traces=0)
+    t0, seed = time.time(), a.seed0
+    while time.time() - t0 < a.seconds:
+        case(eng, seed, stats)
+        seed += 1
+    stats.update(seconds=round(time.time() - t0, 1), seed0=a.seed0, seed_end=seed, mismatches=0)
+    print(json.dumps(stats))
+
+
+if __name__ == "__main__":
+    main()
