@@ -692,7 +692,10 @@ __global__ void __launch_bounds__(kMcThreads, KSL_MC_MIN_CTAS) k_mc_pc(const McO
         const bool ok = ksl::sgp4_init_state_fast<kSmallE>(el, o[28], x, x + 3, s_grid, &ierr);
 #pragma unroll
         for (int q = 0; q < 6; ++q) x[q] *= 1e3;
-        const bool ok_pair = ok && (__shfl_xor_sync(0xffffffffu, ok ? 1 : 0, 1) != 0);
+        // (the shuffle stands on its own line: behind `ok &&` the lanes whose own evaluation declined would skip a
+        // full-mask shuffle -- undefined, and a hang with some code generations)
+        const int ok_other = __shfl_xor_sync(0xffffffffu, ok ? 1 : 0, 1);
+        const bool ok_pair = ok && (ok_other != 0);
         const unsigned int declined = __ballot_sync(0xffffffffu, active && !ok_pair);
         if (declined && lane == 0) {
             masks[it] = declined;
@@ -1595,15 +1598,23 @@ int64_t ksl_mc_pc_ws(int64_t n) {
 // sgp4init on the HOST (the device code is __host__ __device__), the eccentricity is widened by six standard deviations
 // of its marginal (row 1 of the Cholesky factor), and the record's own test decides.  A performance hint only: a sample
 // outside the form is declined by the kernel and redone by the exact route.
+struct HostRecStore {   // (functors rather than host lambdas: the callees are __host__ __device__ templates)
+    double *rec;
+    __host__ __device__ void operator()(int k, double v) const { rec[k] = v; }
+};
+struct HostRecLoad {
+    const double *rec;
+    __host__ __device__ double operator()(int k) const { return rec[k]; }
+};
 static bool mc_cloud_is_small_e(const McObject &o, double mu) {
     const double a = o.mean[0];
     if (!(a > 0.0) || !(mu > 0.0)) return false;
     double el[7] = {sqrt(mu / (a * a * a)) * 60.0, o.mean[1] < 0.0 ? 0.0 : o.mean[1], o.mean[2], o.mean[3], o.mean[4], o.mean[5], o.bstar};
     double rec[ksl::KSL_NFAST] = {0.0};
-    if (ksl::sgp4_init(el, [&](int k, double v) { rec[k] = v; }) != 0) return false;
+    if (ksl::sgp4_init(el, HostRecStore{rec}) != 0) return false;
     ksl::prepare_fast_record(rec, 1);
     rec[KSL_C_ECCO] += 6.0 * sqrt(o.chol[1] * o.chol[1] + o.chol[2] * o.chol[2]);
-    return ksl::fast_record_is_small_e([&](int k) { return rec[k]; }, fabs(o.tsince));
+    return ksl::fast_record_is_small_e(HostRecLoad{rec}, fabs(o.tsince));
 }
 
 int ksl_mc_pc(const double *mean_t, const double *chol_t, double bstar_t, double tsince_t, const double *ref_t,

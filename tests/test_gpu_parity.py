@@ -748,6 +748,32 @@ def test_mc_kernels_exact_route_for_declined_samples(eng):
         assert r["moments_t"].cpu().numpy()[0] == 20000
 
 
+@pytest.mark.timeout(300)
+def test_mc_pc_mixed_declines_inside_a_warp(eng):
+    """Regression (found by benchmarks/fuzz_mc.py): a cloud around e = 3e-5 +- 3e-5 against one around e = 8e-5 +- 4e-4 --
+    in almost every warp some lanes' fast path declines and their pair partners' does not.  The pair-wide `ok` used to be
+    formed as `ok && shfl(...)`, a full-mask shuffle that the declining lanes skipped: undefined, and with one code
+    generation of the kernel a hang.  Checked against the oracle on the dumped draws."""
+    mu = 398600.5e9
+    mean_t = np.array([8.3365e6, 2.7575e-05, 0.32675, 0.28312, 5.6296, 4.2057])
+    mean_c = np.array([7.6744e6, 8.2491e-05, 1.3897, 2.7412, 4.2432, 6.1571])
+    L_t = np.diag([5.4, 3.1e-5, 5.1e-6, 3.7e-5, 8.4e-3, 7.1e-4])
+    L_c = np.diag([3.5, 4.4e-4, 2.4e-5, 1.2e-4, 4.5e-5, 6.9e-6])
+    L_t[3, 1], L_c[4, 2] = 1.0e-5, -2.0e-5
+    ts_t, ts_c, n = -5069.33, -4177.63, 20000
+    ref = np.zeros(6)
+    r = eng.mc_pc(mean_t, L_t, 5.0447e-4, ts_t, ref, mean_c, L_c, -6.3973e-4, ts_c, ref, 2, 735233264412, n, 1.0e5, mu_m3s2=mu, n_dump=n)
+    d = r["dump"].cpu().numpy()
+    el_t, el_c, x_t, x_c = d[:, :7].T.copy(), d[:, 7:14].T.copy(), d[:, 14:20], d[:, 20:26]
+    assert 0.05 < (el_t[1] == 0.0).mean() < 0.5 and 0.2 < (el_c[1] == 0.0).mean() < 0.6      # clamped draws: exact route
+    ref_t, et = C.tca_states(el_t, ts_t)
+    ref_c, ec = C.tca_states(el_c, ts_c)
+    assert np.abs(x_t[:, :3] - ref_t[:, :3]).max() < 1e-3 and np.abs(x_c[:, :3] - ref_c[:, :3]).max() < 1e-3
+    assert int(r["count"][0]) == C.pc_count(np.ascontiguousarray(x_t[:, :3].T), np.ascontiguousarray(x_c[:, :3].T), 1.0e5, 1)
+    assert int(r["err_count"][0]) == int(((et | ec) != 0).sum())
+    assert r["moments_t"].cpu().numpy()[0] == n and r["moments_c"].cpu().numpy()[0] == n
+
+
 def test_pc_count_bit_exact(eng):
     """model.py:432-437 at the reference size (10^4 x 10^4) and ragged sizes: integer-exact."""
     rng = np.random.default_rng(4)
