@@ -172,12 +172,15 @@ KSL_HD bool segment_bounds_f32(const float d0[3], const float d1[3], float dl, f
         qmin = a0 + (a1 + a1) + a2;
         slope = -2.0f * (a1 + a2);
     } else {                               // interior vertex (a2 > -a1 > 0)
-        qmin = a0 - a1 * a1 / a2;
+        // (a1 / a2) a1, not a1 a1 / a2: the ratio lies in (-1, 0), while the square overflows once the separation passes
+        // 1e9.6 km -- the garbage of a flagged trace, but garbage the enumeration orders all the same; an overflow here used
+        // to give qmin = ub = -inf, a "bound" that pruned the rest of the trace (found by benchmarks/fuzz_screen.py)
+        qmin = a0 - (a1 / a2) * a1;
         slope = 0.0f;
     }
     *lb = qmin - margin;
     *ub = qmin + fmaf(slope, dl, a2 * dl * dl) + margin;
-    return (a0 < INFINITY) && (a2 < INFINITY) && (*ub == *ub);
+    return (a0 < INFINITY) && (a2 < INFINITY) && (fabsf(*lb) < INFINITY) && (fabsf(*ub) < INFINITY);
 }
 // the target of the FP32 test: what the bound has to exceed, km^2 (cur in m^2; +inf until the first visit)
 KSL_HD float segment_want_f32(double cur, bool conj_open, double thr2) {

@@ -155,6 +155,28 @@ int64_t hc_skip_compare(const double *d0, const double *d1, const double *cur, i
     return bad;
 }
 
+// segment_bounds_f32 (the lazy search's deferral bounds) on n segments against the exact quadratic in FP64: whenever it
+// returns true, lb must not exceed the quadratic's minimum over [0, 1], ub must not fall below it, and both must be finite.
+// Returns the number of violations; *bounded = how many segments it bounded at all.
+int64_t hc_bounds_check(const double *d0, const double *d1, int64_t n, double dl, int64_t *bounded) {
+    int64_t bad = 0, nb = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const double *a = d0 + 3 * i, *b = d1 + 3 * i;
+        const float f0[3] = {(float)a[0], (float)a[1], (float)a[2]}, f1[3] = {(float)b[0], (float)b[1], (float)b[2]};
+        float lb, ub;
+        if (!ksl::segment_bounds_f32(f0, f1, (float)dl, &lb, &ub)) continue;
+        ++nb;
+        const double bx = b[0] - a[0], by = b[1] - a[1], bz = b[2] - a[2];
+        const double a0 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2], a1 = a[0] * bx + a[1] * by + a[2] * bz, a2 = bx * bx + by * by + bz * bz;
+        double l = a2 > 0.0 ? -a1 / a2 : 0.0;
+        l = l < 0.0 ? 0.0 : (l > 1.0 ? 1.0 : l);
+        const double qmin = a0 + 2.0 * a1 * l + a2 * l * l;
+        if (!(std::fabs((double)lb) < INFINITY) || !(std::fabs((double)ub) < INFINITY) || (double)lb > qmin || (double)ub < qmin) ++bad;
+    }
+    *bounded = nb;
+    return bad;
+}
+
 int hc_screen(const double *consts_t, const double *epoch_t, int64_t n_t, const double *consts_c, const double *epoch_c,
               int64_t n, const double *times_coarse, int64_t n_coarse, int64_t n_fine, double thr, int mode,
               int64_t *i_min, double *d_min, int64_t *i_conj, double *d_conj, int32_t *err) {

@@ -336,6 +336,32 @@ def test_screen_catalog_lazy_search_equals_enumeration(eng):
     assert ok.sum() > 0.7 * n
 
 
+def test_screen_flagged_trace_with_astronomic_separations(eng):
+    """Regression (benchmarks/fuzz_screen.py, seed 508877): a chaser with bstar = 0.077 decays inside the window and SGP4 then
+    returns positions between 3e3 and 4e11 km -- a flagged trace, but one whose numbers the enumeration still orders.  The
+    lazy search's FP32 bound overflowed on such a segment (a1^2), returned -inf as an upper bound of the trace's minimum
+    and pruned everything after it: i_min 6281 instead of 7993.  Closed form == enumeration == oracle, one-vs-catalog shape."""
+    from kessler_b200 import _native as NV
+    gt, ept, _, _, _ = common.golden_pair()
+    bad = np.array([0.07014295, 0.00539253, 2.44460953, 3.20263614, 1.52616371, 0.01961597, 0.07709445])
+    n = 64
+    elc = common.synthetic_catalog(n, seed=77, include_edge=False)
+    elc[:, 5], elc[:, 33] = bad, bad
+    epc = ept + np.random.default_rng(5).uniform(-3, 3, n)
+    epc[5] = epc[33] = ept - 1.62659754
+    tc = (ept - 3.5) + np.arange(255) * (7.0 / 254)
+    n_fine, thr = 25569, 2.0e7
+    ref = C.screen(gt[:, None], [ept], elc, epc, tc, n_fine, thr)
+    assert ref["err"][5] == (9 << 8) and ref["i_min"][5] == 7993
+    for flags in (NV.SCREEN_FORCE_WARP, NV.SCREEN_FORCE_WARP | 1, NV.SCREEN_FORCE_CTA):
+        r = _screen(eng, gt[:, None], [ept], elc, epc, tc, n_fine, thr, flags)
+        assert np.array_equal(r["err"], ref["err"])
+        for k in (5, 33):
+            assert r["i_min"][k] == ref["i_min"][k] and r["i_conj"][k] == ref["i_conj"][k], (flags, k, r["i_min"][k])
+        clean = ref["err"] == 0
+        assert np.array_equal(r["i_min"][clean], ref["i_min"][clean]) and np.array_equal(r["i_conj"][clean], ref["i_conj"][clean])
+
+
 def test_screen_degenerate_identical_objects(eng):
     el, ep = common.population_elems()
     tc = ep[0] + np.arange(300) * 0.001

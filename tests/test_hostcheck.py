@@ -254,6 +254,26 @@ def test_f32_skip_test_is_conservative(hc):
         assert 0 < s32.value <= s64.value and s32.value > 0.3 * s64.value    # ... and it still prunes (7 of 9 cases sit on the boundary)
 
 
+def test_lazy_search_bounds_are_bounds_at_any_magnitude(hc):
+    """segment_bounds_f32: lb <= min of the segment's quadratic <= ub whenever it claims to have bounded the segment -- also
+    for separations of 1e10 .. 1e15 km (the garbage of a decayed, flagged object), where a1^2 overflows FP32: it used to
+    return ub = -inf there, which pruned the rest of the trace (benchmarks/fuzz_screen.py, seed 508877)."""
+    rng = np.random.default_rng(9)
+    n = 300000
+    mag = 10.0 ** rng.uniform(-1, 16, size=(n, 1))
+    d0 = rng.normal(size=(n, 3)) * mag
+    d1 = d0 + rng.normal(size=(n, 3)) * mag * 10.0 ** rng.uniform(-4, 1, size=(n, 1))
+    hc.hc_bounds_check.restype = ctypes.c_int64
+    nb = ctypes.c_int64()
+    for dl in (0.02, 0.25):
+        bad = hc.hc_bounds_check(_p(np.ascontiguousarray(d0), D), _p(np.ascontiguousarray(d1), D), ctypes.c_int64(n), ctypes.c_double(dl),
+                                 ctypes.byref(nb))
+        assert bad == 0
+        assert nb.value > 0.5 * n                 # (it declines only where FP32 cannot hold the squares at all)
+    big = np.abs(d0).max(axis=1) > 1e10
+    assert big.sum() > 0.2 * n
+
+
 def test_sincos_grid_table_is_the_generated_one():
     """kessler_b200/csrc/sincos_grid_table.cuh is the output of tools/make_sincos_grid.py (correctly rounded with mpmath),
     and its entries are sin / cos of the grid angles (libm on the rounded angle agrees to the angle's rounding, 1e-15)."""
