@@ -24,6 +24,10 @@ from kessler_b200 import _native as NV, engine  # noqa: E402
 from oracle import c_oracle as C  # noqa: E402
 
 
+class Mismatch(Exception):
+    pass
+
+
 def _np(t):
     return t.detach().cpu().numpy()
 
@@ -88,11 +92,11 @@ def case(eng, seed, stats):
         for k in ("i_min", "i_conj", "err"):
             if not np.array_equal(r[k], brute[k]):
                 bad = np.flatnonzero(r[k] != brute[k])
-                raise SystemExit(f"MISMATCH {name}.{k} {tag} at {bad[:8]}: {r[k][bad[:8]]} vs {brute[k][bad[:8]]}")
+                raise Mismatch(f"MISMATCH {name}.{k} {tag} at {bad[:8]}: {r[k][bad[:8]]} vs {brute[k][bad[:8]]}")
         for k in ("d_min", "d_conj"):
             if not np.array_equal(r[k], brute[k], equal_nan=True):
                 bad = np.flatnonzero(~((r[k] == brute[k]) | (np.isnan(r[k]) & np.isnan(brute[k]))))
-                raise SystemExit(f"MISMATCH {name}.{k} {tag} at {bad[:8]}: {r[k][bad[:8]]} vs {brute[k][bad[:8]]}")
+                raise Mismatch(f"MISMATCH {name}.{k} {tag} at {bad[:8]}: {r[k][bad[:8]]} vs {brute[k][bad[:8]]}")
     # a few traces against the C oracle (full enumeration on the CPU)
     budget = max(1, int(2.0e7 // max(n_fine, 1)))
     sub = rng.choice(n, size=min(n, budget, 16), replace=False)
@@ -101,11 +105,26 @@ def case(eng, seed, stats):
     # (a trace with a Vallado error bit still carries numbers -- 1e29 m for an eccentricity beyond 1 -- whose arg-min is as
     # ill-conditioned as they are: the flag must agree, the indices are compared on clean traces)
     if not np.array_equal(ref["err"], warp["err"][sub]):
-        raise SystemExit(f"MISMATCH oracle.err {tag}: {ref['err']} vs {warp['err'][sub]}")
+        raise Mismatch(f"MISMATCH oracle.err {tag}: {ref['err']} vs {warp['err'][sub]}")
     clean = ref["err"] == 0
     for k in ("i_min", "i_conj"):
         if not np.array_equal(ref[k][clean], warp[k][sub][clean]):
-            raise SystemExit(f"MISMATCH oracle.{k} {tag}: {ref[k]} vs {warp[k][sub]} err {ref['err']}")
+            w = np.flatnonzero(clean & (ref[k] != warp[k][sub]))
+            # a tie to rounding is not a mismatch: with a 9 ms fine step the two points next to the minimum differ by less
+            # than the 5e-12 km the two SGP4 implementations differ by (seed 1043303: 13006794.651927697 m at 419321 against
+            # ...690 at 419322), and a fine point can sit within that of the threshold
+            if k == "i_min":
+                tie = np.abs(ref["d_min"][w] - warp["d_min"][sub][w]) < 1e-6
+            else:
+                dg, do = warp["d_conj"][sub][w], ref["d_conj"][w]
+                tie = np.abs(np.where(np.isnan(dg), do, dg) - thr) < 1e-6
+            stats["ties"] = stats.get("ties", 0) + int(tie.sum())
+            w = w[~tie]
+            if len(w) == 0:
+                continue
+            raise Mismatch(f"MISMATCH oracle.{k} {tag}: traces {sub[w].tolist()}: oracle {ref[k][w].tolist()} d_min {ref['d_min'][w].tolist()} "
+                           f"d_conj {ref['d_conj'][w].tolist()} vs gpu {warp[k][sub][w].tolist()} d_min {warp['d_min'][sub][w].tolist()} "
+                           f"d_conj {warp['d_conj'][sub][w].tolist()}")
     stats["oracle_flagged"] = stats.get("oracle_flagged", 0) + int((~clean).sum())
     fin = np.isfinite(ref["d_min"]) & clean
     # 1e-3 m = the tolerance of record, at orbital scale (to 1e8 m); an unflagged object with an absurd negative drag term
@@ -114,7 +133,7 @@ def case(eng, seed, stats):
     tol = np.where(ref["d_min"][fin] <= 1e8, 1e-3, 1e-9 * np.abs(ref["d_min"][fin]))
     if (dd > tol).any():
         w = int(np.argmax(dd / tol))
-        raise SystemExit(f"MISMATCH oracle.d_min {tag}: {ref['d_min'][fin][w]!r} vs {warp['d_min'][sub][fin][w]!r}")
+        raise Mismatch(f"MISMATCH oracle.d_min {tag}: {ref['d_min'][fin][w]!r} vs {warp['d_min'][sub][fin][w]!r}")
     stats["max_dmin_diff_m"] = max(stats.get("max_dmin_diff_m", 0.0), float(dd[ref["d_min"][fin] <= 1e8].max(initial=0.0)))
     stats["cases"] += 1
     stats["traces"] += n
@@ -132,11 +151,22 @@ def main():
     eng = engine
     stats = dict(cases=0, traces=0, conj=0, flagged=0, oracle_traces=0)
     t0, seed = time.time(), a.seed0
+    failures = []
     while time.time() - t0 < a.seconds:
-        case(eng, seed, stats)
+        try:
+            case(eng, seed, stats)
+        except Mismatch as e:              # keep going: the list of failing seeds is what a debugging session starts from
+            failures.append(str(e))
         seed += 1
-    stats.update(seconds=round(time.time() - t0, 1), seed0=a.seed0, seed_end=seed, mismatches=0)
+    stats.update(seconds=round(time.time() - t0, 1), seed0=a.seed0, seed_end=seed, mismatches=len(failures))
     print(json.dumps(stats))
+    for f in failures[:10]:
+        print(f)
+    if failures:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "fuzz_screen_failures.txt"), "w") as fh:
+            fh.write("\n".join(failures) + "\n")
+        raise SystemExit(1)
 
 
 if __name__ == "__main__":
