@@ -1820,11 +1820,24 @@ int screen_host_locked(HostCache &hc, const double *elems_t, const double *epoch
     const bool shared = (n_t == 1);
     const int nchunk = (n >= (1 << 18)) ? 4 : 1;
     const size_t un = (size_t)n, unc = (size_t)n_coarse;
-    const size_t m = (un + (size_t)nchunk - 1) / (size_t)nchunk;          // samples per chunk (the last may be shorter)
+    // chunk boundaries: a SHORT first chunk (1/16 of the batch) -- its host->device copy is the one transfer nothing can
+    // hide --, the rest in three equal parts
+    size_t bound[5] = {0, un, un, un, un};
+    if (nchunk > 1) {
+        const size_t first = un / 16, per = (un - first + 2) / 3;
+        for (int j = 1; j < nchunk; ++j) bound[j] = first + (size_t)(j - 1) * per < un ? first + (size_t)(j - 1) * per : un;
+    }
+    size_t m = 0, ws_bytes = 0;                                            // the longest chunk; the largest workspace any chunk needs
+    for (int j = 0; j < nchunk; ++j) {                                     // (a chunk below the fusing threshold stages its records)
+        const size_t len = bound[j + 1] - bound[j];
+        if (len == 0) continue;
+        m = len > m ? len : m;
+        const size_t w = (size_t)ksl_screen_elems_ws((int64_t)(shared ? 1 : len), (int64_t)len, n_coarse);
+        ws_bytes = w > ws_bytes ? w : ws_bytes;
+    }
     const int nslot = nchunk > 1 ? 2 : 1;
     const size_t mt = shared ? 1 : m;
     auto pad = [](size_t b) { return ((b + 255) / 256) * 256; };
-    const size_t ws_bytes = (size_t)ksl_screen_elems_ws((int64_t)mt, (int64_t)m, n_coarse);
     const size_t slot_bytes = pad(8 * 7 * m) + pad(8 * m) + pad(8 * 7 * mt) + pad(8 * mt) + pad(ws_bytes);
     const size_t need = pad(8 * unc) + 4 * pad(8 * un) + pad(4 * un) + (size_t)nslot * slot_bytes +
                         pad((size_t)ksl_screen_summary_ws(n)) + pad(8 * KSL_SUM_NCOUNT) + pad(8 * KSL_SUM_NMOMENT) + 4096;
@@ -1860,9 +1873,9 @@ int screen_host_locked(HostCache &hc, const double *elems_t, const double *epoch
     // chunk's host->device copy from overlapping anything (measured: 189 ms per 1e6 traces that way; with pinned buffers
     // the order makes no difference).
     auto copy_back = [&](int j) -> int {
-        const size_t off = (size_t)j * m;
-        if (j < 0 || off >= un) return KSL_OK;
-        const size_t len = (off + m <= un) ? m : un - off;
+        if (j < 0) return KSL_OK;
+        const size_t off = bound[j], len = bound[j + 1] - bound[j];
+        if (len == 0) return KSL_OK;
         cudaStream_t st = streams[j % nslot];
         KSL_CUDA(cudaMemcpyAsync(i_min + off, d_imin + off, 8 * len, cudaMemcpyDeviceToHost, st));
         KSL_CUDA(cudaMemcpyAsync(d_min + off, d_dmin + off, 8 * len, cudaMemcpyDeviceToHost, st));
@@ -1873,9 +1886,8 @@ int screen_host_locked(HostCache &hc, const double *elems_t, const double *epoch
     };
     int j_last = -1;
     for (int j = 0; j < nchunk; ++j) {
-        const size_t off = (size_t)j * m;
-        if (off >= un) break;
-        const size_t len = (off + m <= un) ? m : un - off;
+        const size_t off = bound[j], len = bound[j + 1] - bound[j];
+        if (len == 0) break;
         Slot &sl = slot[j % nslot];
         cudaStream_t st = streams[j % nslot];
         if (j == 1) KSL_CUDA(cudaStreamWaitEvent(st, hc.ev_ready, 0));       // the time grid, copied on the other stream
