@@ -277,8 +277,9 @@ int ksl_sample_prior(const void *params, uint64_t seed, int64_t sample_offset, i
 /* ---- end-to-end entry points: HOST buffers in, HOST buffers out ----------------
  * What a Kessler-side binding calls for a batch of traces.  Allocates (and caches
  * per device) its staging and scratch buffers; synchronous.  Batches of 2^18 samples
- * and more are streamed through in four chunks on two streams, so that the copies
- * overlap the kernels (use pinned host buffers to benefit); results do not depend
+ * and more are streamed through in four chunks on two streams (a short first one,
+ * whose upload nothing can hide, then three equal ones), so that the copies overlap
+ * the kernels -- with pinned and with pageable host buffers; results do not depend
  * on the chunking.
  *   elems_t SoA [7][n_t], epoch_t [n_t], elems_c SoA [7][n], epoch_c [n],
  *   times_coarse [n_coarse]  -- all host.  Outputs host [n] (err may be NULL).
