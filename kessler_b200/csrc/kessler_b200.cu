@@ -117,12 +117,13 @@ __device__ __forceinline__ void store_states_coalesced(double (*stage)[32 * 6], 
 }
 
 constexpr int kPropTile = 2 * kPropThreads;     // epochs per tile: two per thread (two independent dependency chains in flight)
-__global__ void __launch_bounds__(kPropThreads) k_sgp4_prop_tile(const double *__restrict__ consts, long long n,
+__global__ void __launch_bounds__(kPropThreads, 4) k_sgp4_prop_tile(const double *__restrict__ consts, long long n,
                                                                  const double *__restrict__ tsince, long long m, int per_sample_t,
                                                                  int tiles_per_record, long long n_tiles, double *__restrict__ rv,
                                                                  int *__restrict__ err, unsigned long long *__restrict__ n_exact) {
     __shared__ double stage[kPropThreads / 32][32 * 6];
     __shared__ double s_rec[ksl::KSL_NFAST];
+    __shared__ double s_tsmall;      // |tsince| below which the staged record takes the near-circular form
     __shared__ __align__(16) double s_grid[2 * ksl::kGridPoints];
     // persistent CTAs: the sincos table is staged once per CTA, then the CTA walks its tiles (256 epochs of one record each)
     for (int q = threadIdx.x; q < 2 * ksl::kGridPoints; q += kPropThreads) s_grid[q] = ksl::kGridSinCos[q];
@@ -141,7 +142,10 @@ __global__ void __launch_bounds__(kPropThreads) k_sgp4_prop_tile(const double *_
             __syncthreads();                     // the previous record's readers are done (and, the first time, the table is staged)
             if (threadIdx.x < KSL_NCONST) s_rec[threadIdx.x] = consts[(long long)threadIdx.x * n + i];
             __syncthreads();
-            if (threadIdx.x == 0) ksl::prepare_fast_record(s_rec, 1);
+            if (threadIdx.x == 0) {
+                ksl::prepare_fast_record(s_rec, 1);
+                s_tsmall = ksl::fast_record_small_e_tmax(ld);
+            }
             __syncthreads();
             staged = i;
         }
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(kPropThreads) k_sgp4_prop_tile(const double *_
         const double tb = per_sample_t ? tsince[i * m + jbc] : tsince[jbc];
         // the near-circular form when every lane of the warp qualifies at both epochs (one record per warp: the lanes differ in
         // |t| only), so that the warp never runs both forms; both evaluations in one straight-line block
-        const bool small = __all_sync(0xffffffffu, ksl::fast_record_is_small_e(ld, fmax(fabs(ta), fabs(tb))));
+        const bool small = __all_sync(0xffffffffu, fmax(fabs(ta), fabs(tb)) < s_tsmall);
         double ra[3], va[3], rb[3], vb[3];
         bool ok_a, ok_b;
         if (small) {
@@ -1613,7 +1617,12 @@ static bool mc_cloud_is_small_e(const McObject &o, double mu) {
     double rec[ksl::KSL_NFAST] = {0.0};
     if (ksl::sgp4_init(el, HostRecStore{rec}) != 0) return false;
     ksl::prepare_fast_record(rec, 1);
-    rec[KSL_C_ECCO] += 6.0 * sqrt(o.chol[1] * o.chol[1] + o.chol[2] * o.chol[2]);
+    // six standard deviations up for the form's upper bound, six down for its lower one (it declines em < 1e-6, where the
+    // general form clamps: a cloud that reaches e = 0 -- draws below zero are clamped there -- belongs to the general form)
+    const double spread = 6.0 * sqrt(o.chol[1] * o.chol[1] + o.chol[2] * o.chol[2]);
+    rec[KSL_C_ECCO] = o.mean[1] - spread;
+    if (!ksl::fast_record_is_small_e(HostRecLoad{rec}, fabs(o.tsince))) return false;
+    rec[KSL_C_ECCO] = o.mean[1] + spread;
     return ksl::fast_record_is_small_e(HostRecLoad{rec}, fabs(o.tsince));
 }
 

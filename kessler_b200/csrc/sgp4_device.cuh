@@ -921,11 +921,31 @@ KSL_HD bool sgp4_prop_fast(Load &&c, double t, double r[3], const double *grid) 
 // Only a performance hint -- a wrong guess costs exact-path evaluations (el2 is tested per evaluation), never accuracy.
 template <typename Load>
 KSL_HD bool fast_record_is_small_e(Load &&c, double tmax) {
-    const double bound = c(KSL_C_ECCO) + fabs(c(KSL_F_BC4)) * tmax + 2.0 * fabs(c(KSL_F_BC5)) + 1.5e-3;
+    const double drag_e = fabs(c(KSL_F_BC4)) * tmax + 2.0 * fabs(c(KSL_F_BC5));
+    const double bound = c(KSL_C_ECCO) + drag_e + 1.5e-3;
+    // ... and from below: that form declines em < 1e-6 (the general one clamps there, as the reference does), so a record
+    // that is circular to the last digit of its TLE would take the exact path at every epoch
+    const bool above_clamp = c(KSL_C_ECCO) - drag_e > 2.0e-6;
     // ... and the drag angle temp0 = omgcof t + xmcof ((1 + eta cos M)^3 - delmo) must stay inside that form's short kernels
     const double ae = 1.0 + fabs(c(KSL_C_ETA));
     const double drag_angle = fabs(c(KSL_C_OMGCOF)) * tmax + fabs(c(KSL_C_XMCOF)) * (ae * ae * ae + fabs(c(KSL_C_DELMO)));
-    return bound < 0.0095 && drag_angle < 0.06;
+    return bound < 0.0095 && drag_angle < 0.06 && above_clamp;
+}
+
+// The same selection solved for tmax: the near-circular form is worth selecting for |tsince| < the value returned (every
+// condition of fast_record_is_small_e is monotone in tmax); <= 0: never.  For callers that decide per tile of epochs (K2).
+template <typename Load>
+KSL_HD double fast_record_small_e_tmax(Load &&c) {
+    const double bc4 = fabs(c(KSL_F_BC4)), bc5 = 2.0 * fabs(c(KSL_F_BC5)), om = fabs(c(KSL_C_OMGCOF));
+    const double ae = 1.0 + fabs(c(KSL_C_ETA));
+    const double room_up = 0.0095 - 1.5e-3 - bc5 - c(KSL_C_ECCO);                 // bound < 0.0095
+    const double room_dn = c(KSL_C_ECCO) - bc5 - 2.0e-6;                           // above the em >= 1e-6 clamp
+    const double room_an = 0.06 - fabs(c(KSL_C_XMCOF)) * (ae * ae * ae + fabs(c(KSL_C_DELMO)));   // drag angle < 0.06
+    if (!(room_up > 0.0 && room_dn > 0.0 && room_an > 0.0)) return -1.0;
+    double t = INFINITY;
+    if (bc4 > 0.0) t = fmin(t, fmin(room_up, room_dn) / bc4);
+    if (om > 0.0) t = fmin(t, room_an / om);
+    return t;
 }
 
 // In-place preparation of a private (shared-memory / local) copy of a record, KSL_NFAST entries of `stride`

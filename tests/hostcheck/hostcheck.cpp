@@ -138,6 +138,20 @@ int hc_set_use_table(int v) { s_use_table = v; return 0; }
 static int s_use_f32 = 1;
 int hc_set_use_f32(int v) { s_use_f32 = v; return 0; }
 
+// the two ways of selecting the near-circular form: is_small[i * m + j] = fast_record_is_small_e(record i, tmax[j]),
+// t_limit[i] = fast_record_small_e_tmax(record i)
+int hc_small_e_selection(const double *consts, int64_t n, const double *tmax, int64_t m, int32_t *is_small, double *t_limit) {
+    for (int64_t i = 0; i < n; ++i) {
+        double cm[ksl::KSL_NFAST];
+        for (int k = 0; k < KSL_NCONST; ++k) cm[k] = consts[(int64_t)k * n + i];
+        ksl::prepare_fast_record(cm, 1);
+        auto ld = [&](int k) { return cm[k]; };
+        t_limit[i] = ksl::fast_record_small_e_tmax(ld);
+        for (int64_t j = 0; j < m; ++j) is_small[i * m + j] = ksl::fast_record_is_small_e(ld, tmax[j]) ? 1 : 0;
+    }
+    return 0;
+}
+
 // FP32 skip test vs the FP64 one on n segments (d0, d1: [n][3] km; cur: [n] m^2).  Returns the number of segments the
 // FP32 test would skip although the FP64 test -- with its own slack -- keeps them (must be 0), and the two skip counts.
 int64_t hc_skip_compare(const double *d0, const double *d1, const double *cur, int64_t n, double thr2, int conj_open,

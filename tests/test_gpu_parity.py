@@ -153,6 +153,22 @@ def test_sgp4_fast_path_sweep_ten_million_points(eng):
     assert np.array_equal(np.isnan(rv[bad]), np.isnan(rv_ref[bad]))
 
 
+def test_circular_records_stay_on_the_fast_path(eng):
+    """A TLE that is circular to its last digit (e = 0, 1e-7, 9e-7): the near-circular form of the fast path declines
+    em < 1e-6, so its selection must leave such records to the general form (which clamps em at 1e-6 as the reference
+    does) -- not one evaluation may fall back to the exact path, and the states are the oracle's."""
+    gt, _, gc, _, _ = common.golden_pair()
+    el = np.repeat(gt[:, None], 6, 1)
+    el[1] = [0.0, 1.0e-7, 9.0e-7, 2.0e-6, 5.0e-5, 8.0e-4]
+    ts = np.linspace(-5040.0, 5040.0, 1201)
+    c_ref, _ = C.sgp4_init(el)
+    rv_ref, e_ref = C.sgp4_prop(c_ref, ts)
+    c_own, _ = eng.sgp4_init(el)
+    rv, e, n_exact = eng.sgp4_prop_counted(c_own, ts)
+    assert n_exact == 0 and (_np(e) == 0).all() and (e_ref == 0).all()
+    assert np.abs(_np(rv)[..., :3] - rv_ref[..., :3]).max() < POS_TIGHT_KM
+
+
 def test_reference_unit_test_state_at_epoch(eng):
     """tests/test_util.py:105-131 through the GPU: sgp4(tle, 0) -> Kepler elements, 5 places."""
     from oracle import sgp4_ref as S

@@ -254,6 +254,27 @@ def test_f32_skip_test_is_conservative(hc):
         assert 0 < s32.value <= s64.value and s32.value > 0.3 * s64.value    # ... and it still prunes (7 of 9 cases sit on the boundary)
 
 
+def test_near_circular_selection_by_record_and_by_time_limit_agree(hc):
+    """fast_record_is_small_e(record, tmax) (the screen kernels: once per trace) and tmax < fast_record_small_e_tmax(record)
+    (K2: once per record, compared per tile) are the same decision away from the boundary; records that are circular to
+    the last digit of a TLE (e < 2e-6) never select the form -- it declines em < 1e-6, the general form clamps there."""
+    el = common.synthetic_catalog(4000, seed=23)
+    el[1, 100:140] = np.linspace(0.0, 4.0e-6, 40)
+    c, e0 = C.sgp4_init(el)
+    tmax = np.array([0.0, 1.0, 720.0, 5040.0, 2.0e4, 6.0e4])
+    n, m = el.shape[1], len(tmax)
+    is_small, t_limit = np.zeros((n, m), np.int32), np.zeros(n)
+    hc.hc_small_e_selection(_p(np.ascontiguousarray(c), D), ctypes.c_int64(n), _p(tmax, D), ctypes.c_int64(m), _p(is_small, I32),
+                            _p(t_limit, D))
+    ok = e0 == 0
+    by_limit = tmax[None, :] < t_limit[:, None]
+    near = np.abs(tmax[None, :] - t_limit[:, None]) <= 1e-9 * np.maximum(tmax[None, :], 1.0)
+    assert np.array_equal(is_small[ok].astype(bool) | near[ok], by_limit[ok] | near[ok])
+    assert 0.2 < is_small[ok, 3].mean() < 0.9                       # a week: most of the LEO catalog qualifies
+    assert not is_small[100:120].any() and (t_limit[100:120] <= 0).all()          # e <= 2e-6
+    assert is_small[130:140, 1].all()                                             # e >= 3e-6, one minute from the epoch
+
+
 def test_lazy_search_bounds_are_bounds_at_any_magnitude(hc):
     """segment_bounds_f32: lb <= min of the segment's quadratic <= ub whenever it claims to have bounded the segment -- also
     for separations of 1e10 .. 1e15 km (the garbage of a decayed, flagged object), where a1^2 overflows FP32: it used to
