@@ -220,7 +220,9 @@ int ksl_pc_count(const double *t_xyz, int64_t nt, const double *c_xyz, int64_t n
  * for parity checks against the oracle on IDENTICAL samples.  workspace: ksl_mc_pc_ws(n) bytes
  * (rows of partial moments + one mask word per 16 samples: a sample whose in-register fast path --
  * sgp4init in its fast form + the fast SGP4 state -- declines is marked there and redone on the
- * exact route by a second kernel of the same call; ksl_tca_moments works the same way). */
+ * exact route by a second kernel of the same call; ksl_tca_moments works the same way).  The fast
+ * path runs in its near-circular form when both clouds fit it (decided per call on the host from the
+ * mean elements and six standard deviations of the eccentricity): a choice of speed, not of result. */
 int64_t ksl_mc_pc_ws(int64_t n);
 int ksl_mc_pc(const double *mean_t, const double *chol_t, double bstar_t, double tsince_t, const double *ref_t,
               const double *mean_c, const double *chol_c, double bstar_c, double tsince_c, const double *ref_c,
