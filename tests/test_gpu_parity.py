@@ -923,6 +923,12 @@ def test_empty_and_single_element_batches(eng):
     mom, errc, _ = eng.tca_moments(z7, 100.0, np.zeros(6))
     assert float(mom[0]) == 0.0 and int(errc[0]) == 0 and np.all(_np(mom) == 0.0)
     assert int(eng.pc_count(np.zeros((3, 0)), np.zeros((3, 5)), 70.0)[0]) == 0
+    # an empty shard of the Monte Carlo sample range (more ranks than samples)
+    mean = np.array([6.9e6, 1e-3, 0.9, 1.0, 2.0, 3.0])
+    L = np.diag([10.0, 1e-6, 1e-6, 1e-6, 1e-5, 1e-5])
+    r0 = eng.mc_pc(mean, L, 1e-4, 10.0, np.zeros(6), mean, L, 1e-4, 10.0, np.zeros(6), 1, 0, 0, 70.0)
+    assert int(r0["count"][0]) == 0 and int(r0["err_count"][0]) == 0
+    assert np.all(_np(r0["moments_t"]) == 0.0) and np.all(_np(r0["moments_c"]) == 0.0)
     # one trace, one record, one epoch
     one = eng.screen_elems(gt[:, None], [ept], gc[:, None], [epc], tc, len(times), 5e3)
     assert int(one["i_min"][0]) == 305768 and int(one["i_conj"][0]) == s["i_conj"]
